@@ -1,0 +1,978 @@
+// C-ABI of frender_b200 (see include/frender_b200.h).  Host-side orchestration only: streams,
+// staging buffers, launches, D2H of results.  No CPU compute path exists here by design.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <dlfcn.h>
+#include <zlib.h>
+
+#include "common.cuh"
+#include "match_kernel.cuh"
+#include "route_kernel.cuh"
+#include "scan_kernel.cuh"
+#include "synth_kernel.cuh"
+#include "table_kernels.cuh"
+
+using namespace frb;
+
+namespace {
+
+constexpr int kStages = 3;
+thread_local std::string g_last_error;
+
+struct KeyList {  // device arrays of one (key,count,first) list
+    unsigned long long *keys = nullptr, *counts = nullptr, *first = nullptr;
+    uint64_t n = 0, reads = 0;
+    uint32_t ordinal = 0;
+};
+
+struct ProfPair {
+    cudaEvent_t a, b;
+    int cls;
+};
+
+}  // namespace
+
+struct frb_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    uint32_t log2 = 0;
+    uint64_t cap = 0;
+    Slot *file_tab = nullptr, *total_tab = nullptr;
+    DevState* st = nullptr;
+    DevState* st_host = nullptr;  // pinned mirror
+    unsigned long long* status = nullptr;
+    size_t status_cap = 0;
+    // host-chunk staging
+    unsigned char* stage[kStages] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_copied[kStages], stage_done[kStages];
+    size_t stage_cap = 0;
+    int stage_next = 0;
+    // gz pipeline ring (pinned)
+    unsigned char* ring[kStages] = {nullptr, nullptr, nullptr};
+    // results
+    std::vector<KeyList> files;
+    KeyList total;
+    bool total_ready = false, in_file = false;
+    uint32_t cur_ordinal = 0;
+    uint64_t cur_limit = ~0ULL;
+    // sheet
+    unsigned long long *sheet_fwd = nullptr, *sheet_rc = nullptr;
+    int* sheet_group = nullptr;
+    unsigned char* sheet_use_rc = nullptr;
+    unsigned long long *f_sum = nullptr, *rc_sum = nullptr;
+    uint32_t rows = 0, l1 = 0, l2 = 0;
+    // matcher outputs (device, grown on demand)
+    int *m1 = nullptr, *m2 = nullptr, *srow = nullptr, *m2rc = nullptr, *srowrc = nullptr;
+    unsigned char *type = nullptr, *typerc = nullptr;
+    uint64_t match_cap = 0;
+    // temp for sort
+    void* cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    // route
+    Slot* route_tab = nullptr;
+    uint64_t route_cap = 0;
+    uint32_t n_sinks = 0;
+    RouteBufs rb;
+    // synth
+    SynthArgs synth{};
+    unsigned *synth_i7 = nullptr, *synth_i5 = nullptr;
+    unsigned long long* synth_cdf = nullptr;
+    unsigned long long *synth_len = nullptr, *synth_off = nullptr;
+    uint64_t synth_cap = 0;
+    bool synth_ready = false;
+    // nccl
+    void* nccl_comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    // measurement
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool prof = false;
+    std::vector<ProfPair> prof_pending;
+    std::vector<ProfPair> prof_free;
+    double prof_ms[FRB_K_NUM] = {0};
+    uint64_t prof_n[FRB_K_NUM] = {0};
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(frb_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                         \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(c, FRB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                          \
+    } while (0)
+#define TRY(expr)                   \
+    do {                            \
+        int rc_ = (expr);           \
+        if (rc_ != FRB_OK) return rc_; \
+    } while (0)
+
+struct ProfScope {  // brackets a kernel (class) with events when profiling is on
+    frb_ctx* c;
+    ProfPair p{};
+    bool on;
+    ProfScope(frb_ctx* ctx, int cls) : c(ctx), on(ctx->prof) {
+        if (!on) return;
+        if (!c->prof_free.empty()) {
+            p = c->prof_free.back();
+            c->prof_free.pop_back();
+        } else {
+            cudaEventCreate(&p.a);
+            cudaEventCreate(&p.b);
+        }
+        p.cls = cls;
+        cudaEventRecord(p.a, c->compute);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(p.b, c->compute);
+        c->prof_pending.push_back(p);
+    }
+};
+
+void prof_collect(frb_ctx* c) {  // call after the compute stream is idle
+    for (auto& p : c->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->prof_ms[p.cls] += ms;
+            c->prof_n[p.cls] += 1;
+        }
+        c->prof_free.push_back(p);
+    }
+    c->prof_pending.clear();
+}
+
+int grid_for(uint64_t n, int threads, int sm_count, int per_sm) {
+    uint64_t blocks = (n + threads - 1) / threads;
+    uint64_t cap = static_cast<uint64_t>(sm_count) * per_sm;
+    return static_cast<int>(std::max<uint64_t>(1, std::min(blocks, cap)));
+}
+
+int device_error_check(frb_ctx* c) {  // compute stream must be idle
+    CU(c, cudaMemcpyAsync(c->st_host, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    prof_collect(c);
+    const int code = c->st_host->err_code;
+    if (code == 0) return FRB_OK;
+    const unsigned long long pos = c->st_host->err_pos;
+    char keytxt[24];
+    frb_unpack_key(pos, keytxt);
+    // clear so that the context stays usable after the caller handled the error
+    CU(c, cudaMemsetAsync(&c->st->err_code, 0, sizeof(int), c->compute));
+    switch (code) {
+        case FRB_ERR_BAD_HEADER:
+            return fail(c, code, "read %llu: header line has no second space-separated field", pos);
+        case FRB_ERR_BAD_ALPHABET:
+            return fail(c, code, "read %llu: index field holds a symbol outside ACGTN+", pos);
+        case FRB_ERR_KEY_TOO_LONG:
+            return fail(c, code, "read %llu: index field longer than 21 symbols", pos);
+        case FRB_ERR_TABLE_FULL:
+            return fail(c, code, "unique-key table full (2^%u slots); recreate the context with a larger table",
+                        c->log2);
+        case FRB_ERR_BAD_LENGTH:
+            return fail(c, code, "Barcode %s doesn't match the index lengths of the sample sheet (%u+%u)", keytxt,
+                        c->l1, c->l2);
+        case FRB_ERR_KEY_NOT_FOUND:
+            return fail(c, code, "Couldn't find barcode %s in supplied frender result file!", keytxt);
+        default:
+            return fail(c, code, "device error %d at %llu", code, pos);
+    }
+}
+
+int free_list(frb_ctx* c, KeyList& l) {
+    if (l.keys) CU(c, cudaFree(l.keys));
+    if (l.counts) CU(c, cudaFree(l.counts));
+    if (l.first) CU(c, cudaFree(l.first));
+    l = KeyList{};
+    return FRB_OK;
+}
+
+int clear_table(frb_ctx* c, Slot* tab) {
+    ProfScope ps(c, FRB_K_OTHER);
+    clear_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(tab, c->cap);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return FRB_OK;
+}
+
+int ensure_cub_tmp(frb_ctx* c, size_t bytes) {
+    if (bytes <= c->cub_tmp_bytes) return FRB_OK;
+    if (c->cub_tmp) CU(c, cudaFree(c->cub_tmp));
+    c->cub_tmp = nullptr;
+    c->cub_tmp_bytes = 0;
+    CU(c, cudaMalloc(&c->cub_tmp, bytes));
+    c->cub_tmp_bytes = bytes;
+    return FRB_OK;
+}
+
+// Table -> list sorted by `first` (first-appearance order, F:172-177 / F:199-205).
+int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
+    out->n = n;
+    if (n == 0) return FRB_OK;
+    if (n >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
+    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr;
+    unsigned *i0 = nullptr, *i1 = nullptr;
+    CU(c, cudaMalloc(&k0, n * 8));
+    CU(c, cudaMalloc(&c0, n * 8));
+    CU(c, cudaMalloc(&f0, n * 8));
+    CU(c, cudaMalloc(&i0, n * 4));
+    CU(c, cudaMalloc(&i1, n * 4));
+    CU(c, cudaMalloc(&out->keys, n * 8));
+    CU(c, cudaMalloc(&out->counts, n * 8));
+    CU(c, cudaMalloc(&out->first, n * 8));
+    {
+        ProfScope ps(c, FRB_K_EXPORT);
+        CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
+        compact_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
+            tab, c->cap, k0, c0, f0, &c->st->scratch, n);
+        iota_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i0, n);
+        c->launches += 2;
+        size_t tmp = 0;
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0, 64,
+                                              c->compute));
+        TRY(ensure_cub_tmp(c, tmp));
+        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0, 64,
+                                              c->compute));
+        gather2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i1, k0, c0, out->keys,
+                                                                                       out->counts, n);
+        c->launches += 8;  // cub radix sort passes (approximate) + gather
+        CU(c, cudaGetLastError());
+    }
+    CU(c, cudaStreamSynchronize(c->compute));
+    prof_collect(c);
+    CU(c, cudaFree(k0));
+    CU(c, cudaFree(c0));
+    CU(c, cudaFree(f0));
+    CU(c, cudaFree(i0));
+    CU(c, cudaFree(i1));
+    return FRB_OK;
+}
+
+int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t line_base, int rule,
+                unsigned long long* keys_out, unsigned long long* rec_off_out, Slot* table, uint64_t pos_base,
+                uint64_t out_cap = ~0ULL) {
+    if (nbytes == 0) return FRB_OK;
+    if (reinterpret_cast<uintptr_t>(dev) & 15) return fail(c, FRB_ERR_ARG, "chunk pointer must be 16-byte aligned");
+    const uint64_t n_tiles = (nbytes + kTile - 1) / kTile;
+    if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
+    if (n_tiles + 1 > c->status_cap) {
+        if (c->status) CU(c, cudaFree(c->status));
+        c->status = nullptr;
+        c->status_cap = 0;
+        const size_t want = std::max<size_t>(n_tiles + 1, 1 << 16);
+        CU(c, cudaMalloc(&c->status, want * 8));
+        c->status_cap = want;
+    }
+    CU(c, cudaMemsetAsync(c->status, 0, (n_tiles + 1) * 8, c->compute));
+    ScanArgs a{};
+    a.data = dev;
+    a.nbytes = nbytes;
+    a.use_carry = (line_base == FRB_CARRY);
+    a.line_base = a.use_carry ? 0 : line_base;
+    a.read_limit = c->cur_limit;
+    a.pos_base = pos_base;
+    a.table = table;
+    a.table_mask = c->cap - 1;
+    a.status = c->status;
+    a.st = c->st;
+    a.keys_out = keys_out;
+    a.rec_off_out = rec_off_out;
+    a.out_cap = out_cap;
+    a.n_tiles = static_cast<unsigned>(n_tiles);
+    a.rule = rule;
+    a.no_tma = getenv("FRB_SCAN_NO_TMA") != nullptr;
+    static unsigned* dbg = nullptr;
+    if (getenv("FRB_DEBUG")) {
+        if (!dbg) cudaMalloc(&dbg, 2048 * 4);
+        cudaMemset(dbg, 0xEE, 2048 * 4);
+        a.dbg = dbg;
+    }
+    const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * kCtasPerSm));
+    {
+        ProfScope ps(c, FRB_K_SCAN);
+        scan_kernel<<<grid, kThreads, kScanSmem, c->compute>>>(a);
+        c->launches++;
+    }
+    CU(c, cudaGetLastError());
+    if (a.dbg) {
+        std::vector<unsigned> h(2048);
+        cudaStreamSynchronize(c->compute);
+        cudaMemcpy(h.data(), a.dbg, 2048 * 4, cudaMemcpyDeviceToHost);
+        const char* names[8] = {"cnt", "total", "before", "word0", "lo_lo", "lo_hi", "hi_lo", "hi_hi"};
+        (void)names;
+        for (int i = 56; i < 104; ++i)
+            fprintf(stderr, "DBG tid %d cnt %u total %u before %u incl %u wbase %u\n", i, h[i], h[256 + i], h[512 + i],
+                    h[768 + i], h[1024 + i]);
+    }
+    return FRB_OK;
+}
+
+int ensure_stages(frb_ctx* c) {
+    if (c->stage[0]) return FRB_OK;
+    const char* env = getenv("FRB_STAGE_MB");
+    c->stage_cap = static_cast<size_t>(env ? atoi(env) : 64) << 20;
+    for (int i = 0; i < kStages; ++i) {
+        CU(c, cudaMalloc(&c->stage[i], c->stage_cap + 64));
+        CU(c, cudaEventCreateWithFlags(&c->stage_copied[i], cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->stage_done[i], cudaEventDisableTiming));
+    }
+    return FRB_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int frb_version(void) { return 100; }
+
+int frb_device_count(int* n) {
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(nullptr, FRB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return FRB_OK;
+}
+
+const char* frb_last_error(frb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(nullptr, FRB_ERR_CUDA, "no CUDA device: frender_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, FRB_ERR_ARG, "device %d out of range (%d present)", device, n);
+    if (table_log2 < 10 || table_log2 > 32) return fail(nullptr, FRB_ERR_ARG, "table_log2 must be in [10, 32]");
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, FRB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    frb_ctx* c = new frb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->log2 = table_log2;
+    c->cap = 1ULL << table_log2;
+    CU(c, cudaSetDevice(device));
+    CU(c, cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CU(c, cudaMalloc(&c->file_tab, c->cap * sizeof(Slot)));
+    CU(c, cudaMalloc(&c->total_tab, c->cap * sizeof(Slot)));
+    CU(c, cudaMalloc(&c->st, sizeof(DevState)));
+    CU(c, cudaMemset(c->st, 0, sizeof(DevState)));
+    CU(c, cudaMallocHost(&c->st_host, sizeof(DevState)));
+    CU(c, cudaEventCreate(&c->t0));
+    CU(c, cudaEventCreate(&c->t1));
+    CU(c, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+    CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TRY(clear_table(c, c->total_tab));
+    CU(c, cudaStreamSynchronize(c->compute));
+    *out = c;
+    return FRB_OK;
+}
+
+void frb_destroy(frb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& f : c->files) free_list(c, f);
+    free_list(c, c->total);
+    cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status);
+    for (int i = 0; i < kStages; ++i) {
+        if (c->stage[i]) cudaFree(c->stage[i]), cudaEventDestroy(c->stage_copied[i]), cudaEventDestroy(c->stage_done[i]);
+        if (c->ring[i]) cudaFreeHost(c->ring[i]);
+    }
+    cudaFree(c->sheet_fwd), cudaFree(c->sheet_rc), cudaFree(c->sheet_group), cudaFree(c->sheet_use_rc);
+    cudaFree(c->f_sum), cudaFree(c->rc_sum);
+    cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
+    cudaFree(c->type), cudaFree(c->typerc), cudaFree(c->cub_tmp), cudaFree(c->route_tab);
+    route_free(c->rb);
+    cudaFree(c->synth_i7), cudaFree(c->synth_i5), cudaFree(c->synth_cdf), cudaFree(c->synth_len), cudaFree(c->synth_off);
+    for (auto& p : c->prof_pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
+    for (auto& p : c->prof_free) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
+    cudaEventDestroy(c->t0), cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->compute), cudaStreamDestroy(c->copy);
+    delete c;
+}
+
+int frb_sync(frb_ctx* c) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->copy));
+    CU(c, cudaStreamSynchronize(c->compute));
+    return device_error_check(c);
+}
+
+// ---- memory ---------------------------------------------------------------------------------
+int frb_host_alloc(void** p, size_t nbytes) {
+    CU(nullptr, cudaMallocHost(p, nbytes));
+    return FRB_OK;
+}
+int frb_host_free(void* p) {
+    CU(nullptr, cudaFreeHost(p));
+    return FRB_OK;
+}
+int frb_dev_alloc(frb_ctx* c, size_t nbytes, void** dptr) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMalloc(dptr, nbytes));
+    return FRB_OK;
+}
+int frb_dev_free(frb_ctx* c, void* dptr) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaFree(dptr));
+    return FRB_OK;
+}
+int frb_h2d(frb_ctx* c, void* dptr, const void* host, size_t nbytes) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(dptr, host, nbytes, cudaMemcpyHostToDevice, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    return FRB_OK;
+}
+int frb_d2h(frb_ctx* c, void* host, const void* dptr, size_t nbytes) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(host, dptr, nbytes, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    return FRB_OK;
+}
+int frb_mem_info(frb_ctx* c, uint64_t* free_bytes, uint64_t* total_bytes) {
+    size_t f = 0, t = 0;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemGetInfo(&f, &t));
+    *free_bytes = f, *total_bytes = t;
+    return FRB_OK;
+}
+
+// ---- key packing ----------------------------------------------------------------------------
+int frb_pack_key(const char* s, size_t len, int sheet_mode, uint64_t* out) {
+    if (len > kMaxSyms) return FRB_ERR_KEY_TOO_LONG;
+    uint64_t k = 0;
+    for (size_t i = 0; i < len; ++i) {
+        unsigned ch = static_cast<unsigned char>(s[i]);
+        if (sheet_mode && ch >= 'a' && ch <= 'z') ch -= 32;  // matching is case-insensitive, F:226
+        unsigned code = enc_read(ch);
+        if (code == 0) {
+            if (!sheet_mode) return FRB_ERR_BAD_ALPHABET;
+            code = 7;
+        }
+        k |= static_cast<uint64_t>(code) << (3 * i);
+    }
+    *out = k;
+    return FRB_OK;
+}
+int frb_unpack_key(uint64_t key, char* out) {
+    int n = 0;
+    while (n < kMaxSyms) {
+        const unsigned code = static_cast<unsigned>(key >> (3 * n)) & 7u;
+        if (!code) break;
+        out[n++] = dec_sym(code);
+    }
+    out[n] = 0;
+    return n;
+}
+
+// ---- hot path A -----------------------------------------------------------------------------
+int frb_scan_begin(frb_ctx* c, uint32_t file_ordinal, uint64_t read_limit) {
+    CU(c, cudaSetDevice(c->device));
+    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_begin: previous file not ended");
+    if (file_ordinal >= (1u << 23)) return fail(c, FRB_ERR_ARG, "file ordinal too large");
+    c->cur_ordinal = file_ordinal;
+    c->cur_limit = read_limit ? read_limit : ~0ULL;
+    CU(c, cudaMemsetAsync(c->st, 0, offsetof(DevState, occupied_total), c->compute));
+    TRY(clear_table(c, c->file_tab));
+    c->in_file = true;
+    return FRB_OK;
+}
+
+int frb_scan_chunk_dev(frb_ctx* c, const void* dev, uint64_t nbytes, uint64_t line_base, int rule,
+                       uint64_t* keys_out_dev, uint64_t* rec_off_out_dev) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_chunk: no file begun");
+    return launch_scan(c, static_cast<const unsigned char*>(dev), nbytes, line_base, rule,
+                       reinterpret_cast<unsigned long long*>(keys_out_dev),
+                       reinterpret_cast<unsigned long long*>(rec_off_out_dev), c->file_tab, 0);
+}
+
+int frb_scan_chunk_host(frb_ctx* c, const void* host, uint64_t nbytes, uint64_t line_base, int rule) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_chunk: no file begun");
+    TRY(ensure_stages(c));
+    const unsigned char* p = static_cast<const unsigned char*>(host);
+    uint64_t left = nbytes;
+    bool first = true;
+    while (left) {
+        uint64_t piece = std::min<uint64_t>(left, c->stage_cap);
+        if (piece < left) {  // cut after the last newline of the piece
+            const void* nl = memrchr(p, '\n', piece);
+            if (!nl) return fail(c, FRB_ERR_ARG, "a single line exceeds the staging buffer (%zu bytes)", c->stage_cap);
+            piece = static_cast<const unsigned char*>(nl) - p + 1;
+        }
+        const int s = c->stage_next;
+        c->stage_next = (s + 1) % kStages;
+        CU(c, cudaStreamWaitEvent(c->copy, c->stage_done[s], 0));  // kernel that last read this stage
+        CU(c, cudaMemcpyAsync(c->stage[s], p, piece, cudaMemcpyHostToDevice, c->copy));
+        CU(c, cudaEventRecord(c->stage_copied[s], c->copy));
+        CU(c, cudaStreamWaitEvent(c->compute, c->stage_copied[s], 0));
+        TRY(launch_scan(c, c->stage[s], piece, first ? line_base : FRB_CARRY, rule, nullptr, nullptr, c->file_tab, 0));
+        CU(c, cudaEventRecord(c->stage_done[s], c->compute));
+        CU(c, cudaEventSynchronize(c->stage_copied[s]));  // host bytes consumed; kernel still runs
+        p += piece;
+        left -= piece;
+        first = false;
+    }
+    return FRB_OK;
+}
+
+int frb_scan_end(frb_ctx* c, uint64_t* n_reads, uint64_t* n_unique) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_end: no file begun");
+    c->in_file = false;
+    CU(c, cudaStreamSynchronize(c->copy));
+    CU(c, cudaStreamSynchronize(c->compute));
+    TRY(device_error_check(c));
+    KeyList fl;
+    fl.reads = c->st_host->n_reads;
+    fl.ordinal = c->cur_ordinal;
+    TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl));
+    if (fl.n) {  // fold into "total" (F:199-203); first = (file ordinal, read ordinal)
+        ProfScope ps(c, FRB_K_EXPORT);
+        merge_list_kernel<<<static_cast<unsigned>((fl.n + 255) / 256), 256, 0, c->compute>>>(
+            c->total_tab, c->cap - 1, fl.keys, fl.counts, fl.first, fl.n,
+            static_cast<unsigned long long>(fl.ordinal) << 40, &c->st->occupied_total, c->st);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    c->files.push_back(fl);
+    c->total_ready = false;
+    if (n_reads) *n_reads = fl.reads;
+    if (n_unique) *n_unique = fl.n;
+    return FRB_OK;
+}
+
+int frb_file_count(frb_ctx* c, uint32_t* n_files) {
+    *n_files = static_cast<uint32_t>(c->files.size());
+    return FRB_OK;
+}
+int frb_file_size(frb_ctx* c, uint32_t i, uint64_t* n_unique, uint64_t* n_reads) {
+    if (i >= c->files.size()) return fail(c, FRB_ERR_ARG, "file index out of range");
+    if (n_unique) *n_unique = c->files[i].n;
+    if (n_reads) *n_reads = c->files[i].reads;
+    return FRB_OK;
+}
+static int export_list(frb_ctx* c, const KeyList& l, uint64_t* keys, uint64_t* counts, uint64_t* first, uint64_t cap) {
+    if (cap < l.n) return fail(c, FRB_ERR_ARG, "export buffer too small (%llu < %llu)", (unsigned long long)cap,
+                               (unsigned long long)l.n);
+    if (!l.n) return FRB_OK;
+    CU(c, cudaSetDevice(c->device));
+    if (keys) CU(c, cudaMemcpyAsync(keys, l.keys, l.n * 8, cudaMemcpyDeviceToHost, c->compute));
+    if (counts) CU(c, cudaMemcpyAsync(counts, l.counts, l.n * 8, cudaMemcpyDeviceToHost, c->compute));
+    if (first) CU(c, cudaMemcpyAsync(first, l.first, l.n * 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    return FRB_OK;
+}
+int frb_file_export(frb_ctx* c, uint32_t i, uint64_t* keys, uint64_t* counts, uint64_t* first_read, uint64_t cap) {
+    if (i >= c->files.size()) return fail(c, FRB_ERR_ARG, "file index out of range");
+    return export_list(c, c->files[i], keys, counts, first_read, cap);
+}
+
+int frb_total_finish(frb_ctx* c, uint64_t* n_unique) {
+    CU(c, cudaSetDevice(c->device));
+    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_total_finish: a file is still open");
+    if (!c->total_ready) {
+        CU(c, cudaStreamSynchronize(c->compute));
+        TRY(device_error_check(c));
+        TRY(free_list(c, c->total));
+        TRY(table_to_sorted_list(c, c->total_tab, c->st_host->occupied_total, &c->total));
+        c->total_ready = true;
+    }
+    if (n_unique) *n_unique = c->total.n;
+    return FRB_OK;
+}
+int frb_total_export(frb_ctx* c, uint64_t* keys, uint64_t* counts, uint64_t* first_pos, uint64_t cap) {
+    if (!c->total_ready) return fail(c, FRB_ERR_STATE, "frb_total_export: call frb_total_finish first");
+    return export_list(c, c->total, keys, counts, first_pos, cap);
+}
+int frb_total_load(frb_ctx* c, const uint64_t* keys, const uint64_t* counts, uint64_t n) {
+    CU(c, cudaSetDevice(c->device));
+    TRY(free_list(c, c->total));
+    c->total.n = n;
+    if (n) {
+        CU(c, cudaMalloc(&c->total.keys, n * 8));
+        CU(c, cudaMalloc(&c->total.counts, n * 8));
+        CU(c, cudaMalloc(&c->total.first, n * 8));
+        CU(c, cudaMemcpyAsync(c->total.keys, keys, n * 8, cudaMemcpyHostToDevice, c->compute));
+        CU(c, cudaMemcpyAsync(c->total.counts, counts, n * 8, cudaMemcpyHostToDevice, c->compute));
+        CU(c, cudaMemsetAsync(c->total.first, 0, n * 8, c->compute));
+        CU(c, cudaStreamSynchronize(c->compute));
+    }
+    c->total_ready = true;
+    return FRB_OK;
+}
+int frb_reset(frb_ctx* c) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->compute));
+    for (auto& f : c->files) TRY(free_list(c, f));
+    c->files.clear();
+    TRY(free_list(c, c->total));
+    c->total_ready = false;
+    c->in_file = false;
+    CU(c, cudaMemsetAsync(c->st, 0, sizeof(DevState), c->compute));
+    TRY(clear_table(c, c->total_tab));
+    return FRB_OK;
+}
+
+// ---- gz pipeline ----------------------------------------------------------------------------
+namespace {
+// In-place universal-newline translation of buf[0, n) ("\r\n" -> "\n", lone "\r" -> "\n", as
+// text-mode gzip.open does, F:159).  A "\r" as very last byte is held back (*pending) because
+// the byte after it decides.  Returns the new length.
+size_t normalize_cr(unsigned char* buf, size_t n, bool* pending, bool at_eof) {
+    size_t w = 0;
+    for (size_t r = 0; r < n; ++r) {
+        if (buf[r] != '\r') {
+            buf[w++] = buf[r];
+            continue;
+        }
+        if (r + 1 < n) {
+            buf[w++] = '\n';
+            if (buf[r + 1] == '\n') ++r;
+        } else if (at_eof) {
+            buf[w++] = '\n';
+        } else {
+            *pending = true;
+        }
+    }
+    return w;
+}
+}  // namespace
+
+int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t read_limit, uint64_t* n_reads,
+                uint64_t* n_unique, uint64_t* raw_bytes) {
+    CU(c, cudaSetDevice(c->device));
+    TRY(ensure_stages(c));
+    for (int i = 0; i < kStages; ++i)
+        if (!c->ring[i]) CU(c, cudaMallocHost(&c->ring[i], c->stage_cap));
+    gzFile gz = gzopen(path, "rb");
+    if (!gz) return fail(c, FRB_ERR_IO, "cannot open %s", path);
+    gzbuffer(gz, 1 << 20);
+    TRY(frb_scan_begin(c, file_ordinal, read_limit));
+
+    struct Item {
+        int slot;
+        size_t bytes;
+        bool eof;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Item> ready;
+    int free_slots = kStages;
+    bool stop = false;
+    std::string io_err;
+    uint64_t total_raw = 0;
+
+    std::thread reader([&] {
+        std::vector<unsigned char> tail;
+        bool cr_pending = false;
+        int slot = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return free_slots > 0 || stop; });
+                if (stop) return;
+                --free_slots;
+            }
+            unsigned char* buf = c->ring[slot];
+            size_t have = tail.size();
+            if (have) memcpy(buf, tail.data(), have);
+            tail.clear();
+            if (cr_pending) buf[have++] = '\r', cr_pending = false;
+            bool eof = false;
+            while (have < c->stage_cap) {
+                const unsigned want = static_cast<unsigned>(std::min<size_t>(c->stage_cap - have, 1u << 30));
+                const int got = gzread(gz, buf + have, want);
+                if (got < 0) {
+                    int errnum = 0;
+                    io_err = gzerror(gz, &errnum);
+                    eof = true;
+                    break;
+                }
+                if (got == 0) {
+                    eof = true;
+                    break;
+                }
+                if (memchr(buf + have, '\r', got)) {
+                    // rare path: translate this piece (a trailing '\r' waits for its successor)
+                    size_t m = normalize_cr(buf + have, got, &cr_pending, false);
+                    have += m;
+                } else {
+                    have += got;
+                }
+            }
+            if (eof && cr_pending) buf[have++] = '\n', cr_pending = false;
+            size_t usable = have;
+            if (!eof) {
+                const void* nl = memrchr(buf, '\n', have);
+                if (!nl) {
+                    io_err = "a single line exceeds the staging buffer";
+                    eof = true;
+                    usable = 0;
+                } else {
+                    usable = static_cast<const unsigned char*>(nl) - buf + 1;
+                    tail.assign(buf + usable, buf + have);
+                }
+            }
+            total_raw += usable;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready.push_back({slot, usable, eof});
+            }
+            cv.notify_all();
+            if (eof) return;
+            slot = (slot + 1) % kStages;
+        }
+    });
+
+    int rc = FRB_OK;
+    for (;;) {
+        Item it;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !ready.empty(); });
+            it = ready.front();
+            ready.erase(ready.begin());
+        }
+        if (rc == FRB_OK && it.bytes) rc = frb_scan_chunk_host(c, c->ring[it.slot], it.bytes, FRB_CARRY, FRB_RULE_SCAN);
+        bool enough = false;
+        if (rc == FRB_OK && read_limit) {  // -s: stop reading once the head sample is complete
+            cudaStreamSynchronize(c->compute);
+            cudaMemcpy(c->st_host, c->st, sizeof(DevState), cudaMemcpyDeviceToHost);
+            enough = c->st_host->n_reads >= read_limit;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            ++free_slots;
+            if (rc != FRB_OK || enough) stop = true;
+        }
+        cv.notify_all();
+        if (it.eof || rc != FRB_OK || enough) break;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+    }
+    cv.notify_all();
+    reader.join();
+    gzclose(gz);
+    if (rc == FRB_OK && !io_err.empty()) rc = fail(c, FRB_ERR_IO, "%s: %s", path, io_err.c_str());
+    if (rc != FRB_OK) {
+        c->in_file = false;
+        cudaStreamSynchronize(c->compute);
+        return rc;
+    }
+    if (raw_bytes) *raw_bytes = total_raw;
+    return frb_scan_end(c, n_reads, n_unique);
+}
+
+// ---- hot path B -----------------------------------------------------------------------------
+int frb_sheet_load(frb_ctx* c, const uint64_t* fwd, const uint64_t* rc, const int32_t* group, uint32_t n_rows,
+                   uint32_t l1, uint32_t l2) {
+    CU(c, cudaSetDevice(c->device));
+    if (l1 == 0 || l1 + (l2 ? 1 + l2 : 0) > kMaxSyms) return fail(c, FRB_ERR_ARG, "index lengths %u+%u unsupported (max 21 symbols incl. '+')", l1, l2);
+    if (n_rows > 5000) return fail(c, FRB_ERR_ARG, "sample sheet with %u rows exceeds the 5000-row limit", n_rows);
+    for (uint32_t r = 0; r < n_rows; ++r)
+        if (group[r] < 0 || static_cast<uint32_t>(group[r]) >= n_rows) return fail(c, FRB_ERR_ARG, "bad group id");
+    CU(c, cudaStreamSynchronize(c->compute));
+    cudaFree(c->sheet_fwd), cudaFree(c->sheet_rc), cudaFree(c->sheet_group), cudaFree(c->sheet_use_rc);
+    cudaFree(c->f_sum), cudaFree(c->rc_sum);
+    c->sheet_fwd = c->sheet_rc = nullptr, c->sheet_group = nullptr, c->sheet_use_rc = nullptr;
+    c->f_sum = c->rc_sum = nullptr;
+    const size_t n = std::max<uint32_t>(n_rows, 1);
+    CU(c, cudaMalloc(&c->sheet_fwd, n * 8));
+    CU(c, cudaMalloc(&c->sheet_rc, n * 8));
+    CU(c, cudaMalloc(&c->sheet_group, n * 4));
+    CU(c, cudaMalloc(&c->sheet_use_rc, n));
+    CU(c, cudaMalloc(&c->f_sum, n * 8));
+    CU(c, cudaMalloc(&c->rc_sum, n * 8));
+    if (n_rows) {
+        CU(c, cudaMemcpy(c->sheet_fwd, fwd, n_rows * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->sheet_rc, rc, n_rows * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->sheet_group, group, n_rows * 4, cudaMemcpyHostToDevice));
+    }
+    c->rows = n_rows, c->l1 = l1, c->l2 = l2;
+    return FRB_OK;
+}
+
+int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_rows, int32_t* m1_row, int32_t* m2_row,
+              uint8_t* type, int32_t* sample_row, int32_t* m2rc_row, uint8_t* type_rc, int32_t* sample_rc_row,
+              uint64_t* f_sum, uint64_t* rc_sum) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->total_ready) return fail(c, FRB_ERR_STATE, "frb_match: no total list (frb_total_finish / frb_total_load)");
+    if (!c->sheet_fwd) return fail(c, FRB_ERR_STATE, "frb_match: no sample sheet loaded");
+    if (rc_mode && c->l2 == 0) return fail(c, FRB_ERR_ARG, "frb_match: rc_mode needs a dual-index sheet");
+    const uint64_t n = c->total.n;
+    if (n > c->match_cap) {
+        cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
+        cudaFree(c->type), cudaFree(c->typerc);
+        c->match_cap = 0;
+        CU(c, cudaMalloc(&c->m1, n * 4));
+        CU(c, cudaMalloc(&c->m2, n * 4));
+        CU(c, cudaMalloc(&c->srow, n * 4));
+        CU(c, cudaMalloc(&c->m2rc, n * 4));
+        CU(c, cudaMalloc(&c->srowrc, n * 4));
+        CU(c, cudaMalloc(&c->type, n));
+        CU(c, cudaMalloc(&c->typerc, n));
+        c->match_cap = n;
+    }
+    const size_t rows1 = std::max<uint32_t>(c->rows, 1);
+    if (use_rc_rows && c->rows)
+        CU(c, cudaMemcpyAsync(c->sheet_use_rc, use_rc_rows, c->rows, cudaMemcpyHostToDevice, c->compute));
+    CU(c, cudaMemsetAsync(c->f_sum, 0, rows1 * 8, c->compute));
+    CU(c, cudaMemsetAsync(c->rc_sum, 0, rows1 * 8, c->compute));
+    if (n) {
+        MatchArgs a{};
+        a.keys = c->total.keys, a.counts = c->total.counts, a.n = n;
+        a.sheet_fwd = c->sheet_fwd, a.sheet_rc = c->sheet_rc, a.group = c->sheet_group;
+        a.use_rc = use_rc_rows ? c->sheet_use_rc : nullptr;
+        a.rows = c->rows, a.l1 = c->l1, a.l2 = c->l2, a.n_subs = n_subs, a.rc_mode = rc_mode;
+        a.m1 = c->m1, a.m2 = c->m2, a.srow = c->srow, a.type = c->type;
+        a.m2rc = c->m2rc, a.srowrc = c->srowrc, a.typerc = c->typerc;
+        a.f_sum = c->f_sum, a.rc_sum = c->rc_sum, a.st = c->st;
+        const size_t smem = static_cast<size_t>(c->rows) * (4 * 8 + 4) + 16;
+        ProfScope ps(c, FRB_K_MATCH);
+        match_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads, smem, c->compute>>>(a);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    if (n) {
+        if (m1_row) CU(c, cudaMemcpyAsync(m1_row, c->m1, n * 4, cudaMemcpyDeviceToHost, c->compute));
+        if (m2_row) CU(c, cudaMemcpyAsync(m2_row, c->m2, n * 4, cudaMemcpyDeviceToHost, c->compute));
+        if (type) CU(c, cudaMemcpyAsync(type, c->type, n, cudaMemcpyDeviceToHost, c->compute));
+        if (sample_row) CU(c, cudaMemcpyAsync(sample_row, c->srow, n * 4, cudaMemcpyDeviceToHost, c->compute));
+        if (rc_mode) {
+            if (m2rc_row) CU(c, cudaMemcpyAsync(m2rc_row, c->m2rc, n * 4, cudaMemcpyDeviceToHost, c->compute));
+            if (type_rc) CU(c, cudaMemcpyAsync(type_rc, c->typerc, n, cudaMemcpyDeviceToHost, c->compute));
+            if (sample_rc_row) CU(c, cudaMemcpyAsync(sample_rc_row, c->srowrc, n * 4, cudaMemcpyDeviceToHost, c->compute));
+        }
+    }
+    if (f_sum && c->rows) CU(c, cudaMemcpyAsync(f_sum, c->f_sum, c->rows * 8, cudaMemcpyDeviceToHost, c->compute));
+    if (rc_sum && c->rows) CU(c, cudaMemcpyAsync(rc_sum, c->rc_sum, c->rows * 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    return device_error_check(c);
+}
+
+// ---- synthetic input ------------------------------------------------------------------------
+int frb_synth_load(frb_ctx* c, uint64_t seed, uint32_t l1, uint32_t l2, uint32_t n_samples, const uint32_t* emit_i7,
+                   const uint32_t* emit_i5, const uint64_t* cdf, uint32_t lane, uint32_t read_len, uint32_t sub_t,
+                   uint32_t n_t, uint64_t rand_t, uint64_t hop_t) {
+    CU(c, cudaSetDevice(c->device));
+    if (l1 > 12 || l2 > 12 || n_samples == 0 || lane > 9) return fail(c, FRB_ERR_ARG, "frb_synth_load: bad shape");
+    cudaFree(c->synth_i7), cudaFree(c->synth_i5), cudaFree(c->synth_cdf);
+    CU(c, cudaMalloc(&c->synth_i7, n_samples * 4));
+    CU(c, cudaMalloc(&c->synth_i5, n_samples * 4));
+    CU(c, cudaMalloc(&c->synth_cdf, n_samples * 8));
+    CU(c, cudaMemcpy(c->synth_i7, emit_i7, n_samples * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->synth_i5, emit_i5, n_samples * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->synth_cdf, cdf, n_samples * 8, cudaMemcpyHostToDevice));
+    SynthArgs& a = c->synth;
+    a.seed = seed, a.emit_i7 = c->synth_i7, a.emit_i5 = c->synth_i5, a.cdf = c->synth_cdf;
+    a.rand_t = rand_t, a.hop_t = hop_t, a.l1 = l1, a.l2 = l2, a.n_samples = n_samples, a.lane = lane;
+    a.read_len = read_len, a.sub_t = sub_t, a.n_t = n_t;
+    c->synth_ready = true;
+    return FRB_OK;
+}
+
+int frb_synth_generate(frb_ctx* c, uint64_t g0, uint64_t g1, int read_no, void* dev_out, uint64_t cap_bytes,
+                       uint64_t* nbytes) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->synth_ready) return fail(c, FRB_ERR_STATE, "frb_synth_generate: frb_synth_load first");
+    if (g1 < g0 || g1 - g0 >= (1ULL << 31)) return fail(c, FRB_ERR_ARG, "frb_synth_generate: bad range");
+    const uint64_t n = g1 - g0;
+    *nbytes = 0;
+    if (n == 0) return FRB_OK;
+    if (n > c->synth_cap) {
+        cudaFree(c->synth_len), cudaFree(c->synth_off);
+        c->synth_cap = 0;
+        CU(c, cudaMalloc(&c->synth_len, n * 8));
+        CU(c, cudaMalloc(&c->synth_off, n * 8));
+        c->synth_cap = n;
+    }
+    SynthArgs a = c->synth;
+    a.g0 = g0, a.n = n, a.read_no = read_no;
+    synth_len_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(a, c->synth_len);
+    size_t tmp = 0;
+    CU(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->synth_len, c->synth_off, static_cast<int>(n), c->compute));
+    TRY(ensure_cub_tmp(c, tmp));
+    CU(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp, tmp, c->synth_len, c->synth_off, static_cast<int>(n), c->compute));
+    unsigned long long last_off = 0, last_len = 0;
+    CU(c, cudaMemcpyAsync(&last_off, c->synth_off + (n - 1), 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaMemcpyAsync(&last_len, c->synth_len + (n - 1), 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    const uint64_t total = last_off + last_len;
+    if (total > cap_bytes) return fail(c, FRB_ERR_ARG, "frb_synth_generate: need %llu bytes, buffer has %llu",
+                                       (unsigned long long)total, (unsigned long long)cap_bytes);
+    synth_write_kernel<<<grid_for(n * 32, 256, c->sm_count, 8), 256, 0, c->compute>>>(
+        a, c->synth_off, static_cast<unsigned char*>(dev_out));
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->compute));
+    *nbytes = total;
+    return FRB_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------
+int frb_timer_start(frb_ctx* c) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->t0, c->compute));
+    return FRB_OK;
+}
+int frb_timer_stop(frb_ctx* c, float* ms) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->t1, c->compute));
+    CU(c, cudaEventSynchronize(c->t1));
+    CU(c, cudaEventElapsedTime(ms, c->t0, c->t1));
+    return FRB_OK;
+}
+int frb_prof_enable(frb_ctx* c, int on) {
+    c->prof = on != 0;
+    return FRB_OK;
+}
+int frb_prof_read(frb_ctx* c, int kclass, double* ms_total, uint64_t* launches, int reset) {
+    if (kclass < 0 || kclass >= FRB_K_NUM) return fail(c, FRB_ERR_ARG, "bad kernel class");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->compute));
+    prof_collect(c);
+    if (ms_total) *ms_total = c->prof_ms[kclass];
+    if (launches) *launches = c->prof_n[kclass];
+    if (reset) c->prof_ms[kclass] = 0, c->prof_n[kclass] = 0;
+    return FRB_OK;
+}
+uint64_t frb_launch_count(frb_ctx* c) { return c->launches; }
+
+}  // extern "C"
+
+#include "frb_route.inl"
+#include "frb_nccl.inl"

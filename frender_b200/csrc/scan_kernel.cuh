@@ -1,0 +1,475 @@
+// Hot path A: fused read-name parse + 3-bit key packing + unique-combination count.
+// Replaces scan_file's loop (reference frender.py:161-177): "every 4th line from the start of
+// the file", key = 2nd space token's last ':' field (F:169) or, for demux, the last ':' field of
+// the whole line (F:778).
+//
+// One persistent CTA per (SM x 3) walks 32 KiB tiles of the decompressed FASTQ:
+//   * the tile (+ the 512 B before it) is brought into shared memory by one TMA bulk copy
+//     (cp.async.bulk + mbarrier), double buffered so the next tile streams in while this one
+//     is processed -- every input byte crosses HBM once;
+//   * each thread turns its 128 contiguous bytes into a 128-bit newline mask with 16-byte
+//     shared loads and SIMD-in-word byte compares; a block scan plus a decoupled look-back
+//     over per-tile newline counts (single pass, no second read of the data) gives every
+//     newline its line number, hence "line % 4 == 0" and the read ordinal;
+//   * a header line is owned by the tile holding its terminating newline; one thread per
+//     owned header extracts and packs the key (branch-light backward scan over <= 22 bytes +
+//     a word-parallel space count) and the warp folds equal keys (__match_any_sync) before a
+//     single atomic update of the 32-byte table slot (count += n, first = min).
+#pragma once
+#include "common.cuh"
+
+namespace frb {
+
+constexpr int kTile = 32768;
+constexpr int kHalo = 512;
+constexpr int kBuf = kTile + kHalo;
+constexpr int kThreads = 256;
+constexpr int kPerThread = kTile / kThreads;  // 128 bytes
+constexpr int kHdrCap = 1024;
+constexpr unsigned kUnknown = 0xFFFFu;
+constexpr int kRuleOffsetsOnly = 2;  // internal: no key, record offsets only
+constexpr int kScanSmem = 2 * kBuf + 2 * kHdrCap * (int)sizeof(uint16_t);
+constexpr int kCtasPerSm = 3;
+
+#define kFlagAgg (1ULL << 62)
+#define kFlagInc (2ULL << 62)
+#define kValMask ((1ULL << 62) - 1)
+
+struct ScanArgs {
+    const unsigned char* data;      // chunk, 16-byte aligned, begins at a line start
+    unsigned long long nbytes;
+    unsigned long long line_base;   // lines of the file before this chunk (ignored if use_carry)
+    unsigned long long read_limit;  // reads with ordinal >= limit are not tallied (-s, F:163-165)
+    unsigned long long pos_base;    // added to the read ordinal to form `first`
+    Slot* table;
+    unsigned long long table_mask;
+    unsigned long long* status;     // [0] tile counter, [1 + t] look-back word of tile t
+    DevState* st;
+    unsigned long long* keys_out;     // optional: key of read r at [r - first read of chunk]
+    unsigned long long* rec_off_out;  // optional: chunk offset of the record start, same index
+    unsigned long long out_cap;       // entries available in keys_out / rec_off_out
+    unsigned int n_tiles;
+    int use_carry;
+    int rule;
+    unsigned* dbg;  // debug dump (tile 0) or null
+    int no_tma;  // debug / A-B: stage tiles with plain 16-byte loads instead of the bulk copy
+};
+
+// ---- PTX helpers: mbarrier + TMA bulk copy ------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    // whole spin loop in one asm block (the form ptxas knows), then an explicit warp reconvergence:
+    // lanes leave the loop at different times and the warp-collective code that follows
+    // (shuffles, ballots) must not run on a partial warp.
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FRB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FRB_DONE_%=;\n\t"
+        "bra FRB_WAIT_%=;\n\t"
+        "FRB_DONE_%=:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    // not __syncwarp(): nvcc sees straight-line code here and drops it
+    asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// ---- byte-compare primitives ---------------------------------------------------------------
+// bit 7 of every byte of w that equals the byte replicated in `pat`; exact (no borrow leaks).
+__device__ __forceinline__ unsigned eq_flags(unsigned w, unsigned pat) {
+    unsigned x = w ^ pat;
+    unsigned t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x) & 0x80808080u;
+}
+// flags at bits 7/15/23/31 -> 4 adjacent bits (byte 0 -> bit 0)
+__device__ __forceinline__ unsigned gather4(unsigned y) { return (((y >> 7) * 0x00204081u) >> 21) & 0xFu; }
+__device__ __forceinline__ unsigned newline_mask16(const uint4 v) {
+    return gather4(eq_flags(v.x, 0x0A0A0A0Au)) | (gather4(eq_flags(v.y, 0x0A0A0A0Au)) << 4) |
+           (gather4(eq_flags(v.z, 0x0A0A0A0Au)) << 8) | (gather4(eq_flags(v.w, 0x0A0A0A0Au)) << 12);
+}
+
+// occurrences of `ch` in buf[sb, eb), word-parallel over aligned shared-memory words
+__device__ __forceinline__ unsigned count_byte(const unsigned char* buf, unsigned sb, unsigned eb, unsigned pat) {
+    unsigned cnt = 0;
+    for (unsigned p = sb & ~3u; p < eb; p += 4) {
+        unsigned y = eq_flags(*reinterpret_cast<const unsigned*>(buf + p), pat);
+        if (p < sb) y &= 0xFFFFFFFFu << (8 * (sb - p));
+        if (p + 4 > eb) y &= 0xFFFFFFFFu >> (8 * (p + 4 - eb));
+        cnt += __popc(y);
+    }
+    return cnt;
+}
+
+// Exact, byte-serial statement of both key rules over one header line (no trailing newline).
+// Used for the rare lines the fast path declines (second space, key > 21, line not in smem).
+__host__ __device__ inline int parse_serial(const unsigned char* s, unsigned long long len, int rule,
+                                            unsigned long long* key_out) {
+    unsigned long long i = 0;
+    if (rule == FRB_RULE_SCAN) {
+        while (i < len && s[i] != ' ') ++i;
+        if (i >= len) return FRB_ERR_BAD_HEADER;  // split(" ")[1] -> IndexError, F:169
+        ++i;
+    }
+    unsigned long long k = 0;
+    int n = 0;
+    bool bad = false, too_long = false;
+    for (; i < len; ++i) {
+        unsigned c = s[i];
+        if (rule == FRB_RULE_SCAN && c == ' ') break;
+        if (c == ':') {
+            k = 0, n = 0, bad = false, too_long = false;
+            continue;
+        }
+        unsigned code = enc_read(c);
+        bad |= (code == 0);
+        if (n >= kMaxSyms) too_long = true;
+        else k |= static_cast<unsigned long long>(code) << (3 * n);
+        ++n;
+    }
+    if (bad) return FRB_ERR_BAD_ALPHABET;
+    if (too_long) return FRB_ERR_KEY_TOO_LONG;
+    *key_out = k;
+    return 0;
+}
+
+// Key of the header line occupying buffer positions [sb, eb) (sb == kUnknown: starts before
+// the staged bytes).  Buffer position p is chunk offset tile_off + p - kHalo.
+__device__ __forceinline__ int parse_header(const unsigned char* buf, const unsigned char* lut, unsigned sb,
+                                            unsigned eb, const ScanArgs& a, unsigned long long tile_off,
+                                            unsigned long long* key_out, unsigned long long* start_out) {
+    const bool scan_rule = (a.rule == FRB_RULE_SCAN);
+    if (a.rule == kRuleOffsetsOnly) {  // record boundaries only (R1 side of the demux router)
+        if (sb != kUnknown) {
+            *start_out = tile_off + sb - kHalo;
+        } else {
+            unsigned long long s_g = tile_off + eb - kHalo;
+            while (s_g > 0 && a.data[s_g - 1] != '\n') --s_g;
+            *start_out = s_g;
+        }
+        *key_out = 0;
+        return 0;
+    }
+    if (sb != kUnknown) {
+        *start_out = tile_off + sb - kHalo;
+        unsigned spaces = 1;
+        if (scan_rule) {
+            spaces = count_byte(buf, sb, eb, 0x20202020u);
+            if (spaces == 0) return FRB_ERR_BAD_HEADER;
+        }
+        if (spaces == 1) {
+            // exactly one space: the key is the text after the last ':' or ' ' of the line
+            unsigned long long k = 0;
+            bool open = true, bad = false;
+#pragma unroll
+            for (int j = 0; j < kMaxSyms + 1; ++j) {
+                const int p = static_cast<int>(eb) - 1 - j;
+                const unsigned c = (p >= static_cast<int>(sb)) ? buf[p] : static_cast<unsigned>(':');
+                const bool delim = (c == ':') || (scan_rule && c == ' ');
+                open = open && !delim;
+                const unsigned code = lut[c];
+                if (open) {
+                    k = (k << 3) | code;
+                    bad |= (code == 0);
+                }
+            }
+            if (!open) {
+                if (bad) return FRB_ERR_BAD_ALPHABET;
+                *key_out = k;
+                return 0;
+            }
+        }
+    }
+    const unsigned long long e_g = tile_off + eb - kHalo;
+    unsigned long long s_g;
+    if (sb != kUnknown) {
+        s_g = tile_off + sb - kHalo;
+    } else {
+        s_g = e_g;
+        while (s_g > 0 && a.data[s_g - 1] != '\n') --s_g;
+    }
+    *start_out = s_g;
+    return parse_serial(a.data + s_g, e_g - s_g, a.rule, key_out);
+}
+
+// Decoupled look-back over per-tile newline counts; returns the number of newlines before
+// tile t and publishes this tile's inclusive prefix.  Called by one full warp.
+__device__ __forceinline__ unsigned long long tile_prefix(volatile unsigned long long* status, unsigned t,
+                                                          unsigned total, int lane) {
+    if (t == 0) {
+        if (lane == 0) status[0] = kFlagInc | total;
+        return 0;
+    }
+    if (lane == 0) status[t] = kFlagAgg | total;
+    unsigned long long excl = 0;
+    long long idx = static_cast<long long>(t) - 1;
+    for (;;) {
+        const long long j = idx - lane;
+        bool done;
+        for (;;) {
+            const unsigned long long s = (j >= 0) ? status[j] : kFlagInc;
+            const unsigned none = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 0);
+            const unsigned inc = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
+            const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+            const unsigned relevant = (first_inc >= 31) ? 0xFFFFFFFFu : ((2u << first_inc) - 1u);
+            if ((none & relevant) == 0) {
+                unsigned long long v = (lane <= first_inc) ? (s & kValMask) : 0ULL;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                excl += v;
+                done = first_inc < 32;
+                break;
+            }
+        }
+        if (done) break;
+        idx -= 32;
+    }
+    if (lane == 0) status[t] = kFlagInc | (excl + total);
+    return excl;
+}
+
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* const bufs[2] = {smem, smem + kBuf};
+    uint16_t* const s_start = reinterpret_cast<uint16_t*>(smem + 2 * kBuf);
+    uint16_t* const s_end = s_start + kHdrCap;
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_tile[2];
+    __shared__ unsigned s_warp[kThreads / 32];
+    __shared__ unsigned s_halo_start;
+    __shared__ unsigned char s_lut[256];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long L0 =
+        a.use_carry ? *reinterpret_cast<volatile unsigned long long*>(&a.st->line_carry) : a.line_base;
+    const unsigned long long chunk_first_read = (L0 + 3) >> 2;
+
+    auto issue = [&](int b, unsigned t) {
+        const unsigned long long off = static_cast<unsigned long long>(t) * kTile;
+        const unsigned halo = t ? kHalo : 0;
+        const unsigned long long left = a.nbytes - off;
+        const unsigned avail = static_cast<unsigned>(left < kTile ? left : kTile) + halo;
+        const unsigned bulk = avail & ~15u;
+        if (bulk && !a.no_tma) {
+            mbar_expect_tx(&s_bar[b], bulk);
+            bulk_g2s(bufs[b] + (kHalo - halo), a.data + off - halo, bulk, &s_bar[b]);
+        } else {
+            mbar_arrive(&s_bar[b]);
+        }
+    };
+
+    s_lut[tid] = static_cast<unsigned char>(enc_read(tid));
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        const unsigned t = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
+        s_tile[0] = t;
+        if (t < a.n_tiles) issue(0, t);
+    }
+    __syncthreads();
+
+    unsigned parity = 0;  // bit b = phase parity of s_bar[b]
+    volatile unsigned long long* status = a.status + 1;
+    for (int b = 0;; b ^= 1) {
+        const unsigned t = s_tile[b];
+        if (t >= a.n_tiles) break;
+        if (tid == 0) {
+            const unsigned nt = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
+            s_tile[b ^ 1] = nt;
+            if (nt < a.n_tiles) issue(b ^ 1, nt);
+        }
+        unsigned char* const buf = bufs[b];
+        mbar_wait(&s_bar[b], (parity >> b) & 1u);
+        parity ^= 1u << b;
+
+        const unsigned long long tile_off = static_cast<unsigned long long>(t) * kTile;
+        const unsigned long long left = a.nbytes - tile_off;
+        const unsigned valid = static_cast<unsigned>(left < kTile ? left : kTile);
+        const bool is_last = (t == a.n_tiles - 1);
+        {   // bytes past the last 16-byte multiple of the bulk copy (final tile only)
+            const unsigned halo = t ? kHalo : 0;
+            const unsigned avail = valid + halo, bulk = avail & ~15u;
+            if (a.no_tma) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.data + tile_off - halo);
+                uint4* dst = reinterpret_cast<uint4*>(buf + (kHalo - halo));
+                for (unsigned i = tid; i < bulk / 16; i += kThreads) dst[i] = src[i];
+                if (avail == bulk) __syncthreads();
+            }
+            if (avail != bulk) {
+                if (tid < static_cast<int>(avail - bulk))
+                    buf[(kHalo - halo) + bulk + tid] = a.data[tile_off - halo + bulk + tid];
+                __syncthreads();
+            }
+        }
+
+        // ---- phase 1: 128-bit newline mask of this thread's 128 bytes ------------------------
+        unsigned long long lo = 0, hi = 0;
+        {
+            const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + tid * (kPerThread / 16);
+#pragma unroll
+            for (int j = 0; j < kPerThread / 16; ++j) {
+                const int seg = (j + tid) & 7;  // rotate so a quarter-warp hits 8 distinct bank groups
+                const unsigned long long m = newline_mask16(t4[seg]);
+                const int sh = (seg & 3) * 16;
+                if (seg < 4) lo |= m << sh;
+                else hi |= m << sh;
+            }
+            const int nv = static_cast<int>(valid) - tid * kPerThread;
+            if (nv < kPerThread) {
+                if (nv <= 0) lo = 0, hi = 0;
+                else if (nv < 64) lo &= (1ULL << nv) - 1, hi = 0;
+                else hi &= (1ULL << (nv - 64)) - 1;
+            }
+        }
+        const unsigned cnt = __popcll(lo) + __popcll(hi);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            const unsigned v = s_warp[w];
+            if (w < warp) wbase += v;
+            total += v;
+        }
+        const unsigned before = wbase + incl - cnt;
+        if (a.dbg && t == 0) {
+            a.dbg[tid] = cnt;
+            a.dbg[256 + tid] = total;
+            a.dbg[512 + tid] = before;
+            a.dbg[768 + tid] = incl;
+            a.dbg[1024 + tid] = wbase;
+            a.dbg[1280 + tid] = static_cast<unsigned>(lo >> 32);
+            a.dbg[1536 + tid] = static_cast<unsigned>(hi);
+            a.dbg[1792 + tid] = static_cast<unsigned>(hi >> 32);
+        }
+        // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
+        const unsigned vnl = (is_last && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
+
+        if (warp == 0) {
+            const unsigned long long excl = tile_prefix(status, t, total, lane);
+            if (lane == 0) s_prefix = excl;
+        } else if (warp == kThreads / 32 - 1) {
+            // where does the line that straddles the tile start begin? (last newline of the halo)
+            if (t == 0) {
+                if (lane == 0) s_halo_start = kHalo;
+            } else {
+                const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane]);
+                const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+                if (any == 0) {
+                    if (lane == 0) s_halo_start = kUnknown;
+                } else if (lane == 31 - __clz(any)) {
+                    s_halo_start = lane * 16 + (31 - __clz(m)) + 1;
+                }
+            }
+        }
+        __syncthreads();
+
+        const unsigned long long K0 = L0 + s_prefix;  // index of the first newline of the tile
+        const unsigned long long o_first = (K0 + 3) >> 2;
+        const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
+        const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
+
+        for (unsigned hbase = 0; hbase < n_owned; hbase += kHdrCap) {
+            // ---- phase 1b: line numbers -> header [start, end) positions ---------------------
+            {
+                unsigned long long k = K0 + before;
+                const unsigned long long obase = o_first + hbase;
+                unsigned long long m = lo;
+                unsigned pos0 = kHalo + tid * kPerThread;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    while (m) {
+                        const unsigned p = pos0 + (__ffsll(static_cast<long long>(m)) - 1);
+                        m &= m - 1;
+                        const unsigned r = static_cast<unsigned>(k) & 3u;
+                        if (r == 0) {  // newline 4o ends header line 4o
+                            const unsigned long long rel = (k >> 2) - obase;
+                            if (rel < kHdrCap) s_end[rel] = static_cast<uint16_t>(p);
+                        } else if (r == 3) {  // newline 4o-1: header line 4o starts right after
+                            const unsigned long long rel = ((k + 1) >> 2) - obase;
+                            if (rel < kHdrCap) s_start[rel] = static_cast<uint16_t>(p + 1);
+                        }
+                        ++k;
+                    }
+                    m = hi;
+                    pos0 += 64;
+                }
+                if (tid == 0) {
+                    if (hbase == 0 && (K0 & 3) == 0) s_start[0] = static_cast<uint16_t>(s_halo_start);
+                    if (vnl) {
+                        const unsigned long long kv = K0 + total;
+                        const unsigned long long rel = (kv >> 2) - obase;
+                        if ((kv & 3) == 0 && rel < kHdrCap) s_end[rel] = static_cast<uint16_t>(kHalo + valid);
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 2 + 3: key extraction, warp-aggregated count ---------------------------
+            const unsigned npass = (n_owned - hbase < kHdrCap) ? (n_owned - hbase) : kHdrCap;
+            for (unsigned h0 = 0; h0 < npass; h0 += kThreads) {
+                const unsigned h = h0 + tid;
+                const unsigned long long o = o_first + hbase + h;
+                bool have = (h < npass) && (o < a.read_limit);
+                unsigned long long key = 0, start_g = 0;
+                if (have) {
+                    const int rc = parse_header(buf, s_lut, s_start[h], s_end[h], a, tile_off, &key, &start_g);
+                    if (rc) {
+                        raise_error(a.st, rc, o);
+                        have = false;
+                    }
+                }
+                const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
+                if (have) {
+                    const unsigned same = __match_any_sync(grp, key);
+                    if (a.table && lane == __ffs(same) - 1)  // lowest lane = lowest read ordinal of the group
+                        table_add(a.table, a.table_mask, key, __popc(same), a.pos_base + o, &a.st->occupied,
+                                  a.st);
+                    const unsigned long long slot = o - chunk_first_read;
+                    if (slot < a.out_cap) {
+                        if (a.keys_out) a.keys_out[slot] = key;
+                        if (a.rec_off_out) a.rec_off_out[slot] = start_g;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        if (tid == 0) {
+            const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
+            if (c_hi > o_first) atomicAdd(&a.st->n_reads, c_hi - o_first);
+            if (is_last) a.st->line_carry = K0 + total + vnl;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace frb

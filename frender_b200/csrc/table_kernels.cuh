@@ -1,0 +1,78 @@
+// Unique-key table maintenance: clear, compaction to (key,count,first) lists, merge of a list
+// into another table (per-file tables -> "total", F:199-205; per-rank totals -> merged total).
+#pragma once
+#include "common.cuh"
+
+namespace frb {
+
+__global__ void __launch_bounds__(256) clear_table_kernel(Slot* tab, unsigned long long cap) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    ulonglong4* t4 = reinterpret_cast<ulonglong4*>(tab);
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < cap;
+         i += stride)
+        t4[i] = make_ulonglong4(kEmpty, 0ULL, ~0ULL, 0ULL);
+}
+
+// Occupied slots -> dense arrays (arbitrary order); *counter receives the number written.
+__global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restrict__ tab, unsigned long long cap,
+                                                            unsigned long long* __restrict__ keys,
+                                                            unsigned long long* __restrict__ counts,
+                                                            unsigned long long* __restrict__ first,
+                                                            unsigned long long* counter,
+                                                            unsigned long long out_cap) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long cap_up = (cap + 31) & ~31ULL;
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+         i < cap_up; i += stride) {
+        ulonglong4 s = make_ulonglong4(kEmpty, 0, 0, 0);
+        if (i < cap) s = reinterpret_cast<const ulonglong4*>(tab)[i];
+        const bool occ = s.x != kEmpty;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, occ);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(counter, static_cast<unsigned long long>(__popc(m)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (occ) {
+                const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+                if (idx < out_cap) {
+                    keys[idx] = s.x;
+                    counts[idx] = s.y;
+                    first[idx] = s.z;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(unsigned* idx, unsigned long long n) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n) idx[i] = static_cast<unsigned>(i);
+}
+
+__global__ void __launch_bounds__(256) gather2_kernel(const unsigned* __restrict__ perm,
+                                                      const unsigned long long* __restrict__ a_in,
+                                                      const unsigned long long* __restrict__ b_in,
+                                                      unsigned long long* __restrict__ a_out,
+                                                      unsigned long long* __restrict__ b_out, unsigned long long n) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const unsigned p = perm[i];
+        a_out[i] = a_in[p];
+        b_out[i] = b_in[p];
+    }
+}
+
+// dst[key] += counts, first = min(first, pos_base + first_in)
+__global__ void __launch_bounds__(256) merge_list_kernel(Slot* dst, unsigned long long mask,
+                                                         const unsigned long long* __restrict__ keys,
+                                                         const unsigned long long* __restrict__ counts,
+                                                         const unsigned long long* __restrict__ first,
+                                                         unsigned long long n, unsigned long long pos_base,
+                                                         unsigned long long* occupied, DevState* st) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n) table_add(dst, mask, keys[i], counts[i], first ? pos_base + first[i] : pos_base + i, occupied, st);
+}
+
+}  // namespace frb

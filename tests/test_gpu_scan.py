@@ -1,0 +1,152 @@
+"""GPU parity: CUDA path (through the C-ABI) against the oracle and the reference's golden outputs."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from frender_b200.engine import Context
+    c = Context(0, table_log2=18)
+    yield c
+    c.close()
+
+
+def test_pack_roundtrip():
+    from frender_b200.engine import pack_keys, unpack_keys
+    keys = ["AAAAAAAA+GGGGGGGG", "ACGTN+NTGCA", "", "ACGTAC", "NNNNNNNNNN+ACGTACGTAC", "A+C+G"]
+    assert unpack_keys(pack_keys(keys)) == keys
+
+
+def test_header_rules(ctx, golden):
+    """Every header KAT through the kernel, both key rules (F:169, F:778)."""
+    import frender_b200._lib as L
+    from frender_b200.engine import FrbError
+    for case in golden["headers"]:
+        line = case["line"].rstrip("\n")
+        rec = (line + "\nACGT\n+\nFFFF\n").encode()
+        for rule, want in ((L.RULE_SCAN, case["scan"]), (L.RULE_DEMUX, case["demux"])):
+            ctx.reset()
+            ok = all(ch in "ACGTN+" for ch in want) and len(want) <= 21
+            if ok:
+                reads, uniq = ctx.scan_bytes(rec * 3, rule=rule)
+                assert reads == 3 and uniq == 1
+                assert ctx.counter()["total"] == {want: 3}, (case, rule)
+            else:
+                with pytest.raises(FrbError):
+                    ctx.scan_bytes(rec * 3, rule=rule)
+
+
+def test_tally_edges(ctx, golden, tmp_path):
+    from conftest import unb64
+    from frender_b200.engine import FrbError, tally_barcodes
+    for name, case in golden["edge"].items():
+        data = unb64(case["data"])
+        path = tmp_path / f"{name}_R1.fastq.gz"
+        step = (len(data) + case["members"] - 1) // case["members"] if case["members"] > 1 else max(len(data), 1)
+        with open(path, "wb") as fh:
+            if not data:
+                fh.write(gzip.compress(b""))
+            for off in range(0, len(data), step):
+                fh.write(gzip.compress(data[off:off + step]))
+        if "raises" in case or name == "lowercase_key":
+            with pytest.raises(FrbError):
+                tally_barcodes(1, [path], case["sample"], ctx=ctx)
+        else:
+            got = tally_barcodes(1, [path], case["sample"], ctx=ctx)
+            assert [list(x) for x in got["total"].items()] == case["total"], name
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "multi", "sampled"])
+def test_scan_stages_golden(ctx, golden, golden_dir, name):
+    """tally -> first pass -> orientation call -> second pass against the reference's outputs."""
+    from frender_b200.engine import tally_barcodes
+    case = golden["scan"][name]
+    files = [os.path.join(golden_dir, f"{name}__{f}") for f in case["files"]]
+    counter = tally_barcodes(1, files, case["sample"], ctx=ctx)
+    counter = {k.split("__", 1)[-1]: v for k, v in counter.items()}
+    assert {k: [list(x) for x in v.items()] for k, v in counter.items()} == case["tally"]
+    assert list(counter) == list(case["tally"])
+    indexes = case["indexes"]
+    first, raw = ctx.process(None, indexes, case["n"], case["rc"])
+    assert [[k, v] for k, v in first.items()] == case["first_pass"]
+    results, calls, oriented = ctx.analyze(indexes, case["n"], case["rc"])
+    if case["rc"]:
+        assert [[k, v] for k, v in calls.items()] == case["rc_calls"]
+        assert oriented == case["oriented_idx2"]
+    want = [[k, {f: v for f, v in rec.items() if f != "demux_ok"}] for k, rec in case["final"]]
+    assert [[k, v] for k, v in results.items()] == want
+
+
+def test_matcher_kats(ctx, golden):
+    from frender_b200.engine import process
+    m = golden["matcher"]
+    idx = {"id": m["id"], "idx1": m["idx1"], "idx2": m["idx2"]}
+    for c in m["classify"]:
+        got = process(1, {c["idx1"] + "+" + c["idx2"]: 5}, idx, c["n"], False, ctx=ctx)
+        want = dict(c["want"], reads=5)
+        assert got == {c["idx1"] + "+" + c["idx2"]: want}, c
+    for c in m["rc"]:
+        idx = {"id": c["id"], "idx1": c["idx1"], "idx2": c["idx2"]}
+        got = process(1, {c["key"]: c["reads"]}, idx, c["n"], c["rc_mode"], ctx=ctx)
+        assert got == {c["key"]: c["want"]} and list(got[c["key"]]) == list(c["want"]), c
+
+
+def test_length_mismatch_raises(ctx):
+    from frender_b200.engine import process
+    idx = {"id": ["a"], "idx1": ["AAAAAAAA"], "idx2": ["CCCCCCCC"]}
+    with pytest.raises(AssertionError):
+        process(1, {"AAAA+CCCCCCCC": 1}, idx, 1, False, ctx=ctx)
+    with pytest.raises(ValueError):                    # no '+': unpacking fails as in F:306
+        process(1, {"AAAAAAAA": 1}, idx, 1, False, ctx=ctx)
+    with pytest.raises(AssertionError):
+        process(1, {"AAAAAAAA+CCCCCCC": 1}, idx, 1, False, ctx=ctx)
+
+
+@pytest.mark.parametrize("chunk", [None, 4096, 40000, 1 << 20])
+def test_chunking_invariance(ctx, chunk):
+    """Any chunking of the stream gives the oracle's counts in the oracle's order."""
+    import frender_oracle as O
+    from frender_b200 import synth
+    spec = synth.make_spec("C2", n_samples=32)
+    data = synth.generate(spec, 100, 20100)
+    want, visited = O.tally_text(data.decode().splitlines(keepends=True))
+    ctx.reset()
+    reads, uniq = ctx.scan_bytes(data, chunk=chunk)
+    assert reads == visited == 20000 and uniq == len(want)
+    assert list(ctx.counter()["total"].items()) == list(want.items())
+
+
+def test_keys_per_read_and_offsets(ctx):
+    """Per-read packed keys and record offsets from the resident-buffer entry point."""
+    import frender_b200._lib as L
+    from frender_b200 import synth
+    from frender_b200.engine import C, unpack_keys
+    spec = synth.make_spec("C1", n_samples=16)
+    n = 30000
+    data = synth.generate(spec, 0, n)
+    h = ctx._h
+    ctx.reset()
+    dbuf, dkeys, doffs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ctx._ck(L.lib.frb_dev_alloc(h, len(data) + 64, C.byref(dbuf)))
+    ctx._ck(L.lib.frb_dev_alloc(h, n * 8, C.byref(dkeys)))
+    ctx._ck(L.lib.frb_dev_alloc(h, n * 8, C.byref(doffs)))
+    arr = np.frombuffer(data, np.uint8)
+    ctx._ck(L.lib.frb_h2d(h, dbuf, arr.ctypes.data_as(C.c_void_p), len(data)))
+    ctx._ck(L.lib.frb_scan_begin(h, 0, 0))
+    ctx._ck(L.lib.frb_scan_chunk_dev(h, dbuf, len(data), 0, L.RULE_SCAN, dkeys, doffs))
+    reads, uniq = C.c_uint64(), C.c_uint64()
+    ctx._ck(L.lib.frb_scan_end(h, C.byref(reads), C.byref(uniq)))
+    keys, offs = np.empty(n, np.uint64), np.empty(n, np.uint64)
+    ctx._ck(L.lib.frb_d2h(h, keys.ctypes.data_as(C.c_void_p), dkeys, n * 8))
+    ctx._ck(L.lib.frb_d2h(h, offs.ctypes.data_as(C.c_void_p), doffs, n * 8))
+    for p in (dbuf, dkeys, doffs):
+        ctx._ck(L.lib.frb_dev_free(h, p))
+    assert reads.value == n
+    assert unpack_keys(keys) == synth.keys_of(spec, 0, n)
+    starts = np.flatnonzero(arr == 10)[3::4][:-1] + 1
+    assert offs[0] == 0 and (offs[1:] == starts).all()
