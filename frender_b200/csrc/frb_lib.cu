@@ -29,7 +29,7 @@ using namespace frb;
 
 namespace {
 
-constexpr int kStages = 3;
+constexpr int kHostStages = 3;
 thread_local std::string g_last_error;
 
 struct KeyList {  // device arrays of one (key,count,first) list
@@ -56,12 +56,12 @@ struct frb_ctx {
     unsigned long long* status = nullptr;
     size_t status_cap = 0;
     // host-chunk staging
-    unsigned char* stage[kStages] = {nullptr, nullptr, nullptr};
-    cudaEvent_t stage_copied[kStages], stage_done[kStages];
+    unsigned char* stage[kHostStages] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_copied[kHostStages], stage_done[kHostStages];
     size_t stage_cap = 0;
     int stage_next = 0;
     // gz pipeline ring (pinned)
-    unsigned char* ring[kStages] = {nullptr, nullptr, nullptr};
+    unsigned char* ring[kHostStages] = {nullptr, nullptr, nullptr};
     // results
     std::vector<KeyList> files;
     KeyList total;
@@ -205,10 +205,23 @@ int device_error_check(frb_ctx* c) {  // compute stream must be idle
     }
 }
 
+// Stream-ordered allocations for everything sized by the number of unique keys: served from the
+// device's memory pool (release threshold = never), so a steady-state step makes no driver calls
+// that synchronise the device.
+template <typename T>
+int dmalloc(frb_ctx* c, T** p, size_t bytes) {
+    CU(c, cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 8, c->compute));
+    return FRB_OK;
+}
+int dfree(frb_ctx* c, void* p) {
+    if (p) CU(c, cudaFreeAsync(p, c->compute));
+    return FRB_OK;
+}
+
 int free_list(frb_ctx* c, KeyList& l) {
-    if (l.keys) CU(c, cudaFree(l.keys));
-    if (l.counts) CU(c, cudaFree(l.counts));
-    if (l.first) CU(c, cudaFree(l.first));
+    TRY(dfree(c, l.keys));
+    TRY(dfree(c, l.counts));
+    TRY(dfree(c, l.first));
     l = KeyList{};
     return FRB_OK;
 }
@@ -223,6 +236,7 @@ int clear_table(frb_ctx* c, Slot* tab) {
 
 int ensure_cub_tmp(frb_ctx* c, size_t bytes) {
     if (bytes <= c->cub_tmp_bytes) return FRB_OK;
+    bytes += bytes / 2;
     if (c->cub_tmp) CU(c, cudaFree(c->cub_tmp));
     c->cub_tmp = nullptr;
     c->cub_tmp_bytes = 0;
@@ -238,14 +252,14 @@ int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
     if (n >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
     unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr;
     unsigned *i0 = nullptr, *i1 = nullptr;
-    CU(c, cudaMalloc(&k0, n * 8));
-    CU(c, cudaMalloc(&c0, n * 8));
-    CU(c, cudaMalloc(&f0, n * 8));
-    CU(c, cudaMalloc(&i0, n * 4));
-    CU(c, cudaMalloc(&i1, n * 4));
-    CU(c, cudaMalloc(&out->keys, n * 8));
-    CU(c, cudaMalloc(&out->counts, n * 8));
-    CU(c, cudaMalloc(&out->first, n * 8));
+    TRY(dmalloc(c, &k0, n * 8));
+    TRY(dmalloc(c, &c0, n * 8));
+    TRY(dmalloc(c, &f0, n * 8));
+    TRY(dmalloc(c, &i0, n * 4));
+    TRY(dmalloc(c, &i1, n * 4));
+    TRY(dmalloc(c, &out->keys, n * 8));
+    TRY(dmalloc(c, &out->counts, n * 8));
+    TRY(dmalloc(c, &out->first, n * 8));
     {
         ProfScope ps(c, FRB_K_EXPORT);
         CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
@@ -264,13 +278,11 @@ int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
         c->launches += 8;  // cub radix sort passes (approximate) + gather
         CU(c, cudaGetLastError());
     }
-    CU(c, cudaStreamSynchronize(c->compute));
-    prof_collect(c);
-    CU(c, cudaFree(k0));
-    CU(c, cudaFree(c0));
-    CU(c, cudaFree(f0));
-    CU(c, cudaFree(i0));
-    CU(c, cudaFree(i1));
+    TRY(dfree(c, k0));
+    TRY(dfree(c, c0));
+    TRY(dfree(c, f0));
+    TRY(dfree(c, i0));
+    TRY(dfree(c, i1));
     return FRB_OK;
 }
 
@@ -279,7 +291,9 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
                 uint64_t out_cap = ~0ULL) {
     if (nbytes == 0) return FRB_OK;
     if (reinterpret_cast<uintptr_t>(dev) & 15) return fail(c, FRB_ERR_ARG, "chunk pointer must be 16-byte aligned");
-    const uint64_t n_tiles = (nbytes + kTile - 1) / kTile;
+    static const int nt = getenv("FRB_SCAN_THREADS") ? atoi(getenv("FRB_SCAN_THREADS")) : 256;
+    const uint64_t tile = static_cast<uint64_t>(nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile);
+    const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
     if (n_tiles + 1 > c->status_cap) {
         if (c->status) CU(c, cudaFree(c->status));
@@ -307,28 +321,37 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.n_tiles = static_cast<unsigned>(n_tiles);
     a.rule = rule;
     a.no_tma = getenv("FRB_SCAN_NO_TMA") != nullptr;
-    static unsigned* dbg = nullptr;
-    if (getenv("FRB_DEBUG")) {
-        if (!dbg) cudaMalloc(&dbg, 2048 * 4);
-        cudaMemset(dbg, 0xEE, 2048 * 4);
-        a.dbg = dbg;
+    a.dbg_flags = getenv("FRB_DBG_FLAGS") ? atoi(getenv("FRB_DBG_FLAGS")) : 0;
+    static unsigned long long* timing = nullptr;
+    if (getenv("FRB_SCAN_TIMING")) {
+        if (!timing) cudaMalloc(&timing, 64);
+        cudaMemsetAsync(timing, 0, 64, c->compute);
+        a.timing = timing;
     }
-    const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * kCtasPerSm));
     {
         ProfScope ps(c, FRB_K_SCAN);
-        scan_kernel<<<grid, kThreads, kScanSmem, c->compute>>>(a);
+        if (nt == 128) {
+            using Cfg = ScanCfg<128>;
+            const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
+            scan_kernel<128><<<grid, Cfg::threads, Cfg::smem, c->compute>>>(a);
+        } else {
+            using Cfg = ScanCfg<256>;
+            const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
+            scan_kernel<256><<<grid, Cfg::threads, Cfg::smem, c->compute>>>(a);
+        }
         c->launches++;
     }
     CU(c, cudaGetLastError());
-    if (a.dbg) {
-        std::vector<unsigned> h(2048);
+    if (a.timing) {
+        unsigned long long h[8];
         cudaStreamSynchronize(c->compute);
-        cudaMemcpy(h.data(), a.dbg, 2048 * 4, cudaMemcpyDeviceToHost);
-        const char* names[8] = {"cnt", "total", "before", "word0", "lo_lo", "lo_hi", "hi_lo", "hi_hi"};
-        (void)names;
-        for (int i = 56; i < 104; ++i)
-            fprintf(stderr, "DBG tid %d cnt %u total %u before %u incl %u wbase %u\n", i, h[i], h[256 + i], h[512 + i],
-                    h[768 + i], h[1024 + i]);
+        cudaMemcpy(h, a.timing, 64, cudaMemcpyDeviceToHost);
+        const char* names[6] = {"wait", "count", "lookback", "positions", "parse+insert", "tail"};
+        double sum = 0;
+        for (int i = 0; i < 6; ++i) sum += static_cast<double>(h[i]);
+        fprintf(stderr, "SCAN TIMING tiles %llu cycles/tile %.0f:", h[6], sum / (h[6] ? h[6] : 1));
+        for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f (%.0f%%)", names[i], (double)h[i] / (h[6] ? h[6] : 1), 100.0 * h[i] / sum);
+        fprintf(stderr, "\n");
     }
     return FRB_OK;
 }
@@ -337,7 +360,7 @@ int ensure_stages(frb_ctx* c) {
     if (c->stage[0]) return FRB_OK;
     const char* env = getenv("FRB_STAGE_MB");
     c->stage_cap = static_cast<size_t>(env ? atoi(env) : 64) << 20;
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kHostStages; ++i) {
         CU(c, cudaMalloc(&c->stage[i], c->stage_cap + 64));
         CU(c, cudaEventCreateWithFlags(&c->stage_copied[i], cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->stage_done[i], cudaEventDisableTiming));
@@ -381,6 +404,12 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     c->log2 = table_log2;
     c->cap = 1ULL << table_log2;
     CU(c, cudaSetDevice(device));
+    {
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ULL;
+        CU(c, cudaDeviceGetDefaultMemPool(&pool, device));
+        CU(c, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CU(c, cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     CU(c, cudaMalloc(&c->file_tab, c->cap * sizeof(Slot)));
@@ -390,7 +419,8 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaMallocHost(&c->st_host, sizeof(DevState)));
     CU(c, cudaEventCreate(&c->t0));
     CU(c, cudaEventCreate(&c->t1));
-    CU(c, cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+    CU(c, cudaFuncSetAttribute(scan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<256>::smem));
+    CU(c, cudaFuncSetAttribute(scan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<128>::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TRY(clear_table(c, c->total_tab));
     CU(c, cudaStreamSynchronize(c->compute));
@@ -405,7 +435,7 @@ void frb_destroy(frb_ctx* c) {
     for (auto& f : c->files) free_list(c, f);
     free_list(c, c->total);
     cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kHostStages; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]), cudaEventDestroy(c->stage_copied[i]), cudaEventDestroy(c->stage_done[i]);
         if (c->ring[i]) cudaFreeHost(c->ring[i]);
     }
@@ -533,7 +563,7 @@ int frb_scan_chunk_host(frb_ctx* c, const void* host, uint64_t nbytes, uint64_t 
             piece = static_cast<const unsigned char*>(nl) - p + 1;
         }
         const int s = c->stage_next;
-        c->stage_next = (s + 1) % kStages;
+        c->stage_next = (s + 1) % kHostStages;
         CU(c, cudaStreamWaitEvent(c->copy, c->stage_done[s], 0));  // kernel that last read this stage
         CU(c, cudaMemcpyAsync(c->stage[s], p, piece, cudaMemcpyHostToDevice, c->copy));
         CU(c, cudaEventRecord(c->stage_copied[s], c->copy));
@@ -622,9 +652,9 @@ int frb_total_load(frb_ctx* c, const uint64_t* keys, const uint64_t* counts, uin
     TRY(free_list(c, c->total));
     c->total.n = n;
     if (n) {
-        CU(c, cudaMalloc(&c->total.keys, n * 8));
-        CU(c, cudaMalloc(&c->total.counts, n * 8));
-        CU(c, cudaMalloc(&c->total.first, n * 8));
+        TRY(dmalloc(c, &c->total.keys, n * 8));
+        TRY(dmalloc(c, &c->total.counts, n * 8));
+        TRY(dmalloc(c, &c->total.first, n * 8));
         CU(c, cudaMemcpyAsync(c->total.keys, keys, n * 8, cudaMemcpyHostToDevice, c->compute));
         CU(c, cudaMemcpyAsync(c->total.counts, counts, n * 8, cudaMemcpyHostToDevice, c->compute));
         CU(c, cudaMemsetAsync(c->total.first, 0, n * 8, c->compute));
@@ -675,7 +705,7 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
                 uint64_t* n_unique, uint64_t* raw_bytes) {
     CU(c, cudaSetDevice(c->device));
     TRY(ensure_stages(c));
-    for (int i = 0; i < kStages; ++i)
+    for (int i = 0; i < kHostStages; ++i)
         if (!c->ring[i]) CU(c, cudaMallocHost(&c->ring[i], c->stage_cap));
     gzFile gz = gzopen(path, "rb");
     if (!gz) return fail(c, FRB_ERR_IO, "cannot open %s", path);
@@ -690,7 +720,7 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
     std::mutex mu;
     std::condition_variable cv;
     std::vector<Item> ready;
-    int free_slots = kStages;
+    int free_slots = kHostStages;
     bool stop = false;
     std::string io_err;
     uint64_t total_raw = 0;
@@ -753,7 +783,7 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
             }
             cv.notify_all();
             if (eof) return;
-            slot = (slot + 1) % kStages;
+            slot = (slot + 1) % kHostStages;
         }
     });
 
@@ -836,6 +866,7 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
     if (rc_mode && c->l2 == 0) return fail(c, FRB_ERR_ARG, "frb_match: rc_mode needs a dual-index sheet");
     const uint64_t n = c->total.n;
     if (n > c->match_cap) {
+        CU(c, cudaStreamSynchronize(c->compute));
         cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
         cudaFree(c->type), cudaFree(c->typerc);
         c->match_cap = 0;

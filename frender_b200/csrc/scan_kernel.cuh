@@ -20,16 +20,22 @@
 
 namespace frb {
 
-constexpr int kTile = 32768;
 constexpr int kHalo = 512;
-constexpr int kBuf = kTile + kHalo;
-constexpr int kThreads = 256;
-constexpr int kPerThread = kTile / kThreads;  // 128 bytes
-constexpr int kHdrCap = 1024;
+constexpr int kPerThread = 128;  // bytes of a tile owned by one thread
 constexpr unsigned kUnknown = 0xFFFFu;
 constexpr int kRuleOffsetsOnly = 2;  // internal: no key, record offsets only
-constexpr int kScanSmem = 2 * kBuf + 2 * kHdrCap * (int)sizeof(uint16_t);
-constexpr int kCtasPerSm = 3;
+constexpr int kStages = 3;           // shared-memory tile buffers per CTA
+
+// Geometry of one scan CTA: NT threads walk tiles of NT * 128 bytes.
+template <int NT>
+struct ScanCfg {
+    static constexpr int threads = NT;
+    static constexpr int tile = NT * kPerThread;
+    static constexpr int buf = tile + kHalo;
+    static constexpr int hdr_cap = NT * 4;
+    static constexpr int smem = kStages * buf + 2 * hdr_cap * (int)sizeof(uint16_t);
+    static constexpr int ctas_per_sm = (220 * 1024) / (smem + 2048) > 8 ? 8 : (220 * 1024) / (smem + 2048);
+};
 
 #define kFlagAgg (1ULL << 62)
 #define kFlagInc (2ULL << 62)
@@ -51,8 +57,9 @@ struct ScanArgs {
     unsigned int n_tiles;
     int use_carry;
     int rule;
-    unsigned* dbg;  // debug dump (tile 0) or null
-    int no_tma;  // debug / A-B: stage tiles with plain 16-byte loads instead of the bulk copy
+    unsigned long long* timing;  // optional: per-stage clock64 sums of thread 0 of every CTA
+    int dbg_flags;  // experiments: 1 = no table update, 2 = no atomicMin, 4 = no parse
+    int no_tma;     // debug / A-B: stage tiles with plain 16-byte loads instead of the bulk copy
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy ------------------------------------------------
@@ -212,15 +219,12 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
     return parse_serial(a.data + s_g, e_g - s_g, a.rule, key_out);
 }
 
-// Decoupled look-back over per-tile newline counts; returns the number of newlines before
-// tile t and publishes this tile's inclusive prefix.  Called by one full warp.
+// Decoupled look-back over per-tile newline counts.  The tile's own count was published by the
+// count stage (one pipeline step earlier, see scan_kernel); returns the number of newlines before
+// tile t and publishes the tile's inclusive prefix.  Called by one full warp.
 __device__ __forceinline__ unsigned long long tile_prefix(volatile unsigned long long* status, unsigned t,
                                                           unsigned total, int lane) {
-    if (t == 0) {
-        if (lane == 0) status[0] = kFlagInc | total;
-        return 0;
-    }
-    if (lane == 0) status[t] = kFlagAgg | total;
+    if (t == 0) return 0;  // published as inclusive by the count stage
     unsigned long long excl = 0;
     long long idx = static_cast<long long>(t) - 1;
     for (;;) {
@@ -248,14 +252,31 @@ __device__ __forceinline__ unsigned long long tile_prefix(volatile unsigned long
     return excl;
 }
 
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanArgs a) {
+// Software pipeline of one CTA over its tiles T0, T1, ... (claimed from a global counter), three
+// shared-memory buffers deep:
+//   iteration i:  claim Ti+2 and start its bulk copy          (lands during this iteration)
+//                 C  Ti+1 (copy started one iteration ago): newline masks, block scan, publish count
+//                 A  Ti: look-back over the published counts -> line number of its first newline
+//                 B  Ti: header positions, key extraction, table update
+// Stage C depends on nothing but the tile's bytes, so every tile's count is published about one
+// tile-time before any CTA looks back over it: the look-back never waits on a chain of CTAs.
+struct TileState {
+    unsigned long long lo, hi;  // newline mask of this thread's 128 bytes
+    unsigned before;            // newlines of the tile before this thread's bytes
+    unsigned total;             // newlines in the tile
+    unsigned valid;             // bytes in the tile
+    unsigned vnl;               // 1 if the chunk ends in this tile without a final '\n'
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(const ScanArgs a) {
+    constexpr int kThreads = NT, kTile = ScanCfg<NT>::tile, kBuf = ScanCfg<NT>::buf, kHdrCap = ScanCfg<NT>::hdr_cap;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* const bufs[2] = {smem, smem + kBuf};
-    uint16_t* const s_start = reinterpret_cast<uint16_t*>(smem + 2 * kBuf);
+    uint16_t* const s_start = reinterpret_cast<uint16_t*>(smem + kStages * kBuf);
     uint16_t* const s_end = s_start + kHdrCap;
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_bar[kStages];
     __shared__ unsigned long long s_prefix;
-    __shared__ unsigned s_tile[2];
+    __shared__ unsigned s_tile[kStages];
     __shared__ unsigned s_warp[kThreads / 32];
     __shared__ unsigned s_halo_start;
     __shared__ unsigned char s_lut[256];
@@ -264,8 +285,25 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
     const unsigned long long L0 =
         a.use_carry ? *reinterpret_cast<volatile unsigned long long*>(&a.st->line_carry) : a.line_base;
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
+    volatile unsigned long long* status = a.status + 1;
 
-    auto issue = [&](int b, unsigned t) {
+    // stage timing (thread 0 only, when a.timing is set): 0 wait, 1 count, 2 look-back, 3 positions,
+    // 4 parse+insert, 5 tail, 6 tiles
+    long long tmark = 0;
+    unsigned long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    auto tick = [&](int slot) {
+        if (a.timing && tid == 0) {
+            const long long now = clock64();
+            tacc[slot] += static_cast<unsigned long long>(now - tmark);
+            tmark = now;
+        }
+    };
+    if (a.timing && tid == 0) tmark = clock64();
+
+    auto claim_and_issue = [&](int b) {  // thread 0 only
+        const unsigned t = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
+        s_tile[b] = t;
+        if (t >= a.n_tiles) return;
         const unsigned long long off = static_cast<unsigned long long>(t) * kTile;
         const unsigned halo = t ? kHalo : 0;
         const unsigned long long left = a.nbytes - off;
@@ -273,44 +311,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
         const unsigned bulk = avail & ~15u;
         if (bulk && !a.no_tma) {
             mbar_expect_tx(&s_bar[b], bulk);
-            bulk_g2s(bufs[b] + (kHalo - halo), a.data + off - halo, bulk, &s_bar[b]);
+            bulk_g2s(smem + b * kBuf + (kHalo - halo), a.data + off - halo, bulk, &s_bar[b]);
         } else {
             mbar_arrive(&s_bar[b]);
         }
     };
 
-    s_lut[tid] = static_cast<unsigned char>(enc_read(tid));
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-        const unsigned t = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
-        s_tile[0] = t;
-        if (t < a.n_tiles) issue(0, t);
-    }
-    __syncthreads();
-
     unsigned parity = 0;  // bit b = phase parity of s_bar[b]
-    volatile unsigned long long* status = a.status + 1;
-    for (int b = 0;; b ^= 1) {
+
+    // stage C: newline masks + block scan of the tile staged in buffer b, publish its count
+    auto count_stage = [&](int b, TileState& ts) {
         const unsigned t = s_tile[b];
-        if (t >= a.n_tiles) break;
-        if (tid == 0) {
-            const unsigned nt = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
-            s_tile[b ^ 1] = nt;
-            if (nt < a.n_tiles) issue(b ^ 1, nt);
-        }
-        unsigned char* const buf = bufs[b];
+        if (t >= a.n_tiles) return;  // uniform
+        unsigned char* const buf = smem + b * kBuf;
         mbar_wait(&s_bar[b], (parity >> b) & 1u);
         parity ^= 1u << b;
-
+        tick(0);
         const unsigned long long tile_off = static_cast<unsigned long long>(t) * kTile;
         const unsigned long long left = a.nbytes - tile_off;
-        const unsigned valid = static_cast<unsigned>(left < kTile ? left : kTile);
-        const bool is_last = (t == a.n_tiles - 1);
+        ts.valid = static_cast<unsigned>(left < kTile ? left : kTile);
         {   // bytes past the last 16-byte multiple of the bulk copy (final tile only)
             const unsigned halo = t ? kHalo : 0;
-            const unsigned avail = valid + halo, bulk = avail & ~15u;
+            const unsigned avail = ts.valid + halo, bulk = avail & ~15u;
             if (a.no_tma) {
                 const uint4* src = reinterpret_cast<const uint4*>(a.data + tile_off - halo);
                 uint4* dst = reinterpret_cast<uint4*>(buf + (kHalo - halo));
@@ -323,26 +345,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
                 __syncthreads();
             }
         }
-
-        // ---- phase 1: 128-bit newline mask of this thread's 128 bytes ------------------------
         unsigned long long lo = 0, hi = 0;
-        {
-            const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + tid * (kPerThread / 16);
+        const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + tid * (kPerThread / 16);
 #pragma unroll
-            for (int j = 0; j < kPerThread / 16; ++j) {
-                const int seg = (j + tid) & 7;  // rotate so a quarter-warp hits 8 distinct bank groups
-                const unsigned long long m = newline_mask16(t4[seg]);
-                const int sh = (seg & 3) * 16;
-                if (seg < 4) lo |= m << sh;
-                else hi |= m << sh;
-            }
-            const int nv = static_cast<int>(valid) - tid * kPerThread;
-            if (nv < kPerThread) {
-                if (nv <= 0) lo = 0, hi = 0;
-                else if (nv < 64) lo &= (1ULL << nv) - 1, hi = 0;
-                else hi &= (1ULL << (nv - 64)) - 1;
-            }
+        for (int j = 0; j < kPerThread / 16; ++j) {
+            const int seg = (j + tid) & 7;  // rotate so a quarter-warp hits 8 distinct bank groups
+            const unsigned long long m = newline_mask16(t4[seg]);
+            const int sh = (seg & 3) * 16;
+            if (seg < 4) lo |= m << sh;
+            else hi |= m << sh;
         }
+        const int nv = static_cast<int>(ts.valid) - tid * kPerThread;
+        if (nv < kPerThread) {
+            if (nv <= 0) lo = 0, hi = 0;
+            else if (nv < 64) lo &= (1ULL << nv) - 1, hi = 0;
+            else hi &= (1ULL << (nv - 64)) - 1;
+        }
+        ts.lo = lo, ts.hi = hi;
         const unsigned cnt = __popcll(lo) + __popcll(hi);
         unsigned incl = cnt;
 #pragma unroll
@@ -359,25 +378,64 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
             if (w < warp) wbase += v;
             total += v;
         }
-        const unsigned before = wbase + incl - cnt;
-        if (a.dbg && t == 0) {
-            a.dbg[tid] = cnt;
-            a.dbg[256 + tid] = total;
-            a.dbg[512 + tid] = before;
-            a.dbg[768 + tid] = incl;
-            a.dbg[1024 + tid] = wbase;
-            a.dbg[1280 + tid] = static_cast<unsigned>(lo >> 32);
-            a.dbg[1536 + tid] = static_cast<unsigned>(hi);
-            a.dbg[1792 + tid] = static_cast<unsigned>(hi >> 32);
-        }
+        ts.before = wbase + incl - cnt;
+        ts.total = total;
+        if (tid == 0) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
         // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
-        const unsigned vnl = (is_last && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
+        ts.vnl = (t == a.n_tiles - 1 && ts.valid > 0 && buf[kHalo + ts.valid - 1] != '\n') ? 1u : 0u;
+        __syncthreads();  // s_warp is reused by the next count
+        tick(1);
+    };
 
+    s_lut[tid & 255] = static_cast<unsigned char>(enc_read(tid & 255));
+    if (kThreads < 256) s_lut[(tid + kThreads) & 255] = static_cast<unsigned char>(enc_read((tid + kThreads) & 255));
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
+        mbar_fence_init();
+        claim_and_issue(0);
+        claim_and_issue(1);
+    }
+    __syncthreads();
+    TileState cur{}, nxt{};
+    count_stage(0, cur);
+
+    // Deferred table update: the slot of a key is fetched when the key is extracted and examined
+    // one tile later, so the DRAM latency of the (random) probe is off the tile's critical path.
+    unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
+    unsigned p_cnt = 0;  // 0 = nothing pending
+    auto finish_pending = [&]() {
+        if (p_cnt) {
+            if (a.dbg_flags & 1) {
+            } else if (p_seen == p_key) {
+                atomicAdd(&a.table[p_slot].count, static_cast<unsigned long long>(p_cnt));
+                if (!(a.dbg_flags & 2)) atomicMin(&a.table[p_slot].first, p_pos);
+            } else {
+                table_add(a.table, a.table_mask, p_key, p_cnt, p_pos, &a.st->occupied, a.st);
+            }
+            p_cnt = 0;
+        }
+    };
+
+    int c = 0, n = 1, nn = 2;
+    for (;;) {
+        const unsigned t = s_tile[c];
+        if (t >= a.n_tiles) break;
+        if (tid == 0) claim_and_issue(nn);  // buffer nn was released at the end of the last iteration
+        __syncthreads();                    // s_tile[nn] visible; also orders the stages
+        tick(5);
+        count_stage(n, nxt);
+
+        unsigned char* const buf = smem + c * kBuf;
+        const unsigned long long tile_off = static_cast<unsigned long long>(t) * kTile;
+        const bool is_last = (t == a.n_tiles - 1);
+        const unsigned total = cur.total, vnl = cur.vnl, valid = cur.valid;
+
+        // ---- stage A: tile prefix (warp 0) and start of the straddling line (last warp) ---------
         if (warp == 0) {
             const unsigned long long excl = tile_prefix(status, t, total, lane);
             if (lane == 0) s_prefix = excl;
         } else if (warp == kThreads / 32 - 1) {
-            // where does the line that straddles the tile start begin? (last newline of the halo)
             if (t == 0) {
                 if (lane == 0) s_halo_start = kHalo;
             } else {
@@ -391,18 +449,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
             }
         }
         __syncthreads();
+        tick(2);
 
         const unsigned long long K0 = L0 + s_prefix;  // index of the first newline of the tile
         const unsigned long long o_first = (K0 + 3) >> 2;
         const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
         const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
 
+        // ---- stage B -----------------------------------------------------------------------------
         for (unsigned hbase = 0; hbase < n_owned; hbase += kHdrCap) {
-            // ---- phase 1b: line numbers -> header [start, end) positions ---------------------
-            {
-                unsigned long long k = K0 + before;
+            {   // line numbers -> header [start, end) positions
+                unsigned long long k = K0 + cur.before;
                 const unsigned long long obase = o_first + hbase;
-                unsigned long long m = lo;
+                unsigned long long m = cur.lo;
                 unsigned pos0 = kHalo + tid * kPerThread;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -419,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
                         }
                         ++k;
                     }
-                    m = hi;
+                    m = cur.hi;
                     pos0 += 64;
                 }
                 if (tid == 0) {
@@ -432,13 +491,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
                 }
             }
             __syncthreads();
+            tick(3);
 
-            // ---- phase 2 + 3: key extraction, warp-aggregated count ---------------------------
+            // key extraction, warp-aggregated count
             const unsigned npass = (n_owned - hbase < kHdrCap) ? (n_owned - hbase) : kHdrCap;
             for (unsigned h0 = 0; h0 < npass; h0 += kThreads) {
                 const unsigned h = h0 + tid;
                 const unsigned long long o = o_first + hbase + h;
-                bool have = (h < npass) && (o < a.read_limit);
+                bool have = (h < npass) && (o < a.read_limit) && !(a.dbg_flags & 4);
                 unsigned long long key = 0, start_g = 0;
                 if (have) {
                     const int rc = parse_header(buf, s_lut, s_start[h], s_end[h], a, tile_off, &key, &start_g);
@@ -448,11 +508,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
                     }
                 }
                 const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
+                finish_pending();
                 if (have) {
                     const unsigned same = __match_any_sync(grp, key);
-                    if (a.table && lane == __ffs(same) - 1)  // lowest lane = lowest read ordinal of the group
-                        table_add(a.table, a.table_mask, key, __popc(same), a.pos_base + o, &a.st->occupied,
-                                  a.st);
+                    if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal of the group
+                        p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
+                        p_slot = hash64(key) & a.table_mask;
+                        p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
+                    }
                     const unsigned long long slot = o - chunk_first_read;
                     if (slot < a.out_cap) {
                         if (a.keys_out) a.keys_out[slot] = key;
@@ -461,14 +524,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scan_kernel(const ScanAr
                 }
             }
             __syncthreads();
+            tick(4);
         }
 
         if (tid == 0) {
             const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
             if (c_hi > o_first) atomicAdd(&a.st->n_reads, c_hi - o_first);
             if (is_last) a.st->line_carry = K0 + total + vnl;
+            tacc[6] += 1;
         }
-        __syncthreads();
+        __syncthreads();  // everyone is done with buffer c and the header lists
+        cur = nxt;
+        const int old = c;
+        c = n, n = nn, nn = old;
+    }
+    finish_pending();
+    if (a.timing && tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) atomicAdd(&a.timing[i], tacc[i]);
     }
 }
 
