@@ -116,16 +116,24 @@ __device__ __forceinline__ unsigned newline_mask16(const uint4 v) {
            (gather4(eq_flags(v.z, 0x0A0A0A0Au)) << 8) | (gather4(eq_flags(v.w, 0x0A0A0A0Au)) << 12);
 }
 
-// occurrences of `ch` in buf[sb, eb), word-parallel over aligned shared-memory words
-__device__ __forceinline__ unsigned count_byte(const unsigned char* buf, unsigned sb, unsigned eb, unsigned pat) {
+// Number of ' ' in buf[sb, eb) for lines that end within 112 bytes of their 16-byte-aligned start,
+// else -1.  Fully unrolled and branch-free: seven independent 16-byte shared loads in flight.
+__device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsigned sb, unsigned eb) {
+    const unsigned a0 = sb & ~15u;
+    if (eb - a0 > 112u) return -1;
     unsigned cnt = 0;
-    for (unsigned p = sb & ~3u; p < eb; p += 4) {
-        unsigned y = eq_flags(*reinterpret_cast<const unsigned*>(buf + p), pat);
-        if (p < sb) y &= 0xFFFFFFFFu << (8 * (sb - p));
-        if (p + 4 > eb) y &= 0xFFFFFFFFu >> (8 * (p + 4 - eb));
-        cnt += __popc(y);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const unsigned p = a0 + 16u * i;
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + (p < eb ? p : a0));
+        unsigned m = gather4(eq_flags(v.x, 0x20202020u)) | (gather4(eq_flags(v.y, 0x20202020u)) << 4) |
+                     (gather4(eq_flags(v.z, 0x20202020u)) << 8) | (gather4(eq_flags(v.w, 0x20202020u)) << 12);
+        const unsigned lo_cut = sb > p ? sb - p : 0u;                  // bytes of this segment before the line
+        const unsigned hi_cut = eb > p ? (eb - p < 16u ? eb - p : 16u) : 0u;  // bytes of it inside [.., eb)
+        m &= (0xFFFFu << lo_cut) & ((1u << hi_cut) - 1u);
+        cnt += __popc(m);
     }
-    return cnt;
+    return static_cast<int>(cnt);
 }
 
 // Exact, byte-serial statement of both key rules over one header line (no trailing newline).
@@ -179,32 +187,34 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
     }
     if (sb != kUnknown) {
         *start_out = tile_off + sb - kHalo;
-        unsigned spaces = 1;
-        if (scan_rule) {
-            spaces = count_byte(buf, sb, eb, 0x20202020u);
-            if (spaces == 0) return FRB_ERR_BAD_HEADER;
-        }
-        if (spaces == 1) {
-            // exactly one space: the key is the text after the last ':' or ' ' of the line
-            unsigned long long k = 0;
-            bool open = true, bad = false;
+        // Fast path, branch-free and latency-flat.  With exactly one ' ' in the line the key is the
+        // text after the last ':' or ' ' (the 2nd space token runs to the end of the line).
+        const int spaces = scan_rule ? count_spaces_fast(buf, sb, eb) : 1;
+        unsigned ch[kMaxSyms + 1];
 #pragma unroll
-            for (int j = 0; j < kMaxSyms + 1; ++j) {
-                const int p = static_cast<int>(eb) - 1 - j;
-                const unsigned c = (p >= static_cast<int>(sb)) ? buf[p] : static_cast<unsigned>(':');
-                const bool delim = (c == ':') || (scan_rule && c == ' ');
-                open = open && !delim;
-                const unsigned code = lut[c];
-                if (open) {
-                    k = (k << 3) | code;
-                    bad |= (code == 0);
-                }
+        for (int j = 0; j < kMaxSyms + 1; ++j) {  // last 22 bytes of the line, closest to EOL first
+            const int p = static_cast<int>(eb) - 1 - j;
+            ch[j] = (p >= static_cast<int>(sb)) ? buf[p] : static_cast<unsigned>(':');
+        }
+        unsigned delim = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxSyms + 1; ++j)
+            delim |= ((ch[j] == ':') || (scan_rule && ch[j] == ' ') ? 1u : 0u) << j;
+        if (spaces == 0) return FRB_ERR_BAD_HEADER;
+        if (spaces == 1 && delim != 0) {
+            const int len = __ffs(delim) - 1;  // symbols in the key, <= 21
+            unsigned long long k = 0;
+            unsigned bad = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxSyms; ++j) {
+                const unsigned code = lut[ch[j]];
+                const bool in_key = j < len;
+                k |= in_key ? (static_cast<unsigned long long>(code) << (3 * (in_key ? len - 1 - j : 0))) : 0ULL;
+                bad |= (in_key && code == 0) ? 1u : 0u;
             }
-            if (!open) {
-                if (bad) return FRB_ERR_BAD_ALPHABET;
-                *key_out = k;
-                return 0;
-            }
+            if (bad) return FRB_ERR_BAD_ALPHABET;
+            *key_out = k;
+            return 0;
         }
     }
     const unsigned long long e_g = tile_off + eb - kHalo;
@@ -300,8 +310,13 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     };
     if (a.timing && tid == 0) tmark = clock64();
 
+    // Tile ids are claimed one step before they are needed so that the atomic's round trip to L2 is
+    // not on the critical path (thread 0 only).
+    unsigned claimed = 0;
+    if (tid == 0) claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
     auto claim_and_issue = [&](int b) {  // thread 0 only
-        const unsigned t = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
+        const unsigned t = claimed;
+        claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
         s_tile[b] = t;
         if (t >= a.n_tiles) return;
         const unsigned long long off = static_cast<unsigned long long>(t) * kTile;
