@@ -1,0 +1,531 @@
+"""Drop-in command line of frender (`frender.py scan ...`, `frender.py demux ...`).
+
+Flags, sample-sheet parsing, file discovery, output names, the scan-results CSV layout, the
+index-2-calls CSV, stdout messages and the per-sample fastq.gz outputs follow the reference
+(/root/reference/frender.py, "F:").  The per-read and per-unique-key work (read-name parse,
+unique-combination count, mismatch matching with reverse-complement orientation, record routing)
+runs in the CUDA library; this module is the host shell around it.
+"""
+import argparse
+import csv
+import gzip
+import os
+import re
+import zlib
+from datetime import datetime, timezone
+from math import floor
+from pathlib import Path
+
+import numpy as np
+
+from . import _lib
+from .engine import Context, FrbError, READ_TYPES, pack_keys, reverse_complement, unpack_keys
+
+STAMP = "%Y-%M-%d_%H%M_%Z"          # sic: minutes where the month should be (F:599, F:912)
+MIN_CHUNK = 1 << 20                  # smallest demux window (bytes per mate)
+
+
+# ---------------------------------------------------------------------------------------------
+# host, cold: cores, sample sheet, file discovery (F:9-151, F:685-716)
+# ---------------------------------------------------------------------------------------------
+def get_cores(cores):
+    """F:9-22.  The value now sizes host-side (de)compression helpers; the GPU does the rest."""
+    assert cores >= 0, "Number of cores is negative... what does that mean?"
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count()
+    if cores == 0:
+        return avail
+    if 0 < cores < 1:
+        return max(floor(cores * avail), 1)
+    return int(cores)
+
+
+def find_barcode_file(directory):
+    """Newest-sorting csv/txt whose path looks like a barcode table (F:25-49)."""
+    directory = Path(directory)
+    assert directory.is_dir(), "The specified directory does not exist"
+    hits = [p for p in directory.rglob("**/*")
+            if re.search("barcode.*association", str(p), re.I) or re.search("sample.*sheet", str(p), re.I)]
+    hits = sorted((p for p in hits if re.search(r"\.csv$|\.txt$", str(p), re.I)), reverse=True)
+    if not hits:
+        raise SystemExit(
+            "I couldn't find a barcode table in that directory. Please either specify one with the argment -b "
+            "or specify a directory including a barcode table. File names matching '.*barcode.*association.*' "
+            "or '.*sample.*sheet.*' (case insensitive) are accepted.")
+    print(f"Found barcode association file {os.path.basename(hits[0])}")
+    return hits[0]
+
+
+def get_indexes(barcode_file):
+    """{"id", "idx1", "idx2"} column lists of the sample sheet (F:52-116): an Illumina
+    [Header]..[Data] preamble is skipped, columns are found by regex on the header row.
+    Extension: a sheet without an index2 column yields idx2 = None (single index)."""
+    with open(barcode_file, "r") as handle:
+        rows = csv.reader(handle)
+        header = next(rows)
+        if re.search(r"\[Header\]", header[0]):
+            while not re.search(r"\[Data\]", next(rows)[0]):     # a blank row raises IndexError as in F:58
+                pass
+            header = next(rows)
+
+        def col(pattern, veto=None):
+            for i, name in enumerate(header):
+                if re.search(pattern, name, re.I) and not (veto and re.search(veto, name, re.I)):
+                    return i
+            raise ValueError(
+                f"""Couldn't find column matching "{pattern}"{' but not "' + veto + '"' if veto else ''} """
+                f"in csv header {header}")
+
+        try:
+            c_id, c_1 = col("id|name"), col("index", "id|2")
+        except ValueError as exc:
+            print("Error finding columns in provided barcode file:")
+            raise SystemExit(exc)
+        try:
+            c_2 = col("index.*2")
+        except ValueError as exc:
+            if os.environ.get("FRENDER_SINGLE_INDEX"):
+                c_2 = None
+            else:
+                print("Error finding columns in provided barcode file:")
+                raise SystemExit(exc)
+        out = {"id": [], "idx1": [], "idx2": [] if c_2 is not None else None}
+        for row in rows:
+            out["id"].append(row[c_id])
+            out["idx1"].append(row[c_1])
+            if c_2 is not None:
+                out["idx2"].append(row[c_2])
+        return out
+
+
+def parse_files(file_dict, just_r1):
+    """fastq.gz paths of a directory (optionally R1 only) or of an explicit list (F:119-151)."""
+    kind = list(file_dict.keys())[0]
+    paths = []
+    if kind == "dir":
+        print(f"Scanning {file_dict['dir']} for fastq files. "
+              f"{'Using read 1 files only for speed...' if just_r1 else ''}")
+        paths = [p for p in Path(file_dict["dir"]).rglob("**/*") if p.is_file()]
+    elif kind == "file":
+        given = file_dict["file"]
+        paths = [Path(a) for a in given if Path(a).is_file()] if isinstance(given, list) else [given]
+    keep = []
+    for p in paths:
+        if re.search(r"\.f[ast]*q\.gz$", str(p), re.I):
+            keep.append(p)
+        else:
+            print(f"Ignoring non-fastq file {os.path.basename(p)}")
+    if kind == "dir" and just_r1:
+        keep = [p for p in keep if re.search("R1", os.path.basename(p), re.I)]
+    return keep
+
+
+def is_read_mate(a, b):
+    """F:685-693: names differ in exactly one character and carry _R1_ / _R2_."""
+    if sum(1 for x, y in zip(a, b) if x != y) != 1:
+        return False
+    r = {int(re.search("_R[12]_", s)[0].strip("_").replace("R", "")) for s in (a, b)}
+    return r == {1, 2}
+
+
+def get_paired_files(files):
+    """[(R1, R2)] (F:696-716)."""
+    pairs = []
+    for r1 in (p for p in files if re.search("_R1_", str(p), re.I)):
+        mates = [q for q in files if is_read_mate(str(r1), str(q))]
+        if len(mates) > 1:
+            raise SystemExit(f"Found more than one potential read 2 file for {r1}")
+        if not mates:
+            raise SystemExit(f"Couldn't find a read 2 file for {r1}")
+        pairs.append((r1, mates[0]))
+    return pairs
+
+
+# ---------------------------------------------------------------------------------------------
+# scan (F:567-642)
+# ---------------------------------------------------------------------------------------------
+class ScanTables:
+    """Device results of the tally as arrays: total list + per-file lists (dict semantics of
+    barcode_counter: a repeated basename keeps its first position and the last file's counts)."""
+
+    def __init__(self, ctx, names):
+        self.keys, self.counts, _ = ctx.total_arrays()
+        slot = {}
+        for i, name in enumerate(names):
+            slot.setdefault(name, len(slot))
+        self.file_names = list(slot)
+        latest = {name: i for i, name in enumerate(names)}
+        self.files = [ctx.file_arrays(latest[name])[:2] for name in self.file_names]
+
+
+def demux_ok_flags(tables, read_type, sample_row, sheet_ids, prefix):
+    """demux_ok per unique key and the set of files holding a key they should not (F:504-564).
+    The class x file match matrix uses the reference's own regexes (sample name as a pattern)."""
+    files = tables.file_names
+    n = len(tables.keys)
+    fixed = [re.compile("undetermined", re.I), re.compile("undetermined|index-hop", re.I), None,
+             re.compile("undetermined|ambiguous", re.I)]
+    ok = np.ones(n, bool)
+    bad_files = set()
+    order = np.argsort(tables.keys, kind="stable")
+    sorted_keys = tables.keys[order]
+    name_match = {}
+    for f, fname in enumerate(files):
+        fkeys, fcounts = tables.files[f]
+        fkeys = fkeys[fcounts > 0]
+        idx = order[np.searchsorted(sorted_keys, fkeys)]
+        cls = read_type[idx]
+        match = np.zeros(len(idx), bool)
+        for t in (0, 1, 3):
+            match[cls == t] = bool(fixed[t].search(fname))
+        dem = np.flatnonzero(cls == 2)
+        for row in np.unique(sample_row[idx[dem]]):
+            name = sheet_ids[row]
+            if (name, fname) not in name_match:
+                name_match[(name, fname)] = bool(re.search(re.compile(name.removeprefix(prefix), re.I), fname))
+            match[dem[sample_row[idx[dem]] == row]] = name_match[(name, fname)]
+        ok[idx[~match]] = False
+        if (~match).any():
+            bad_files.add(fname)
+    return ok, bad_files
+
+
+def report_rc_call_info(rc_calls, indexes, out_csv_name):
+    """stdout table + index-2-calls CSV (F:429-479)."""
+    name = out_csv_name.replace("frender-scan-results_", "frender-index-2-calls_")
+    print("Based on the barcodes in the supplied fastq file, the following index 2 sequences will be used\n"
+          f"(also recorded in {name}):\n")
+    print("Sample Name", "Supplied Index 2", "Reads supporting (forward)", "Reverse complement Index 2",
+          "Reads supporting (rev comp)", "Final call", sep="\t")
+    rows = []
+    for sample, call in rc_calls.items():
+        supplied = indexes["idx2"][indexes["id"].index(sample)]
+        flipped = reverse_complement(supplied)
+        print(sample, supplied, call["reads_f"], flipped, call["reads_rc"],
+              "reverse complement" if call["call"] else "forward", sep="\t")
+        rows.append([sample, supplied, call["reads_f"], flipped, call["reads_rc"],
+                     "TRUE" if call["call"] else "FALSE"])
+    with open(name, "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["sample_name", "supplied_index_2", "reads_supplied_index_2", "rc_index_2",
+                    "reads_rc_index_2", "use_rc"])
+        w.writerows(rows)
+
+
+def frender_scan(args, ctx=None):
+    num_subs, rc_mode = args.n, args.rc
+    get_cores(args.c)
+    sample = args.s
+    infix = args.o if args.o else ""
+    prefix = args.p if args.p else ""
+    if args.b is None:
+        if len(args.files) != 1:
+            raise SystemExit("You have not specified a barcode table. Please either specify one with the argment -b "
+                             "or specify a directory including a barcode table")
+        barcode_file = find_barcode_file(Path(args.files[0]))
+    else:
+        barcode_file = Path(args.b)
+    indexes = get_indexes(barcode_file)
+
+    if len(args.files) == 1:                                                    # F:587-601
+        target = Path(args.files[0])
+        if target.is_dir():
+            files = {"dir": target}
+            out_csv_name = f"frender-scan-results_{num_subs}-mismatches_{infix}_{target.parts[-1]}.csv"
+        elif target.is_file():
+            files = {"file": target}
+            out_csv_name = f"frender-scan-results_{num_subs}-mismatches_{infix}_{target.name}.csv"
+        else:
+            raise SystemExit("Specified directory or file path doesn't seem to exist!")
+    else:
+        files = {"file": [Path(f) for f in args.files]}
+        stamp = datetime.strftime(datetime.now(timezone.utc), STAMP)
+        out_csv_name = f"frender-scan-results_{num_subs}-mismatches_{infix}_{stamp}.csv"
+    out_csv_name = out_csv_name.replace("__", "_")
+    files = parse_files(files, just_r1=True)
+
+    own_ctx = ctx is None
+    ctx = ctx or Context(int(os.environ.get("FRENDER_DEVICE", "0")),
+                         table_log2=int(os.environ.get("FRENDER_TABLE_LOG2", "24")))
+    try:
+        # ---- tally (F:183-207) -----------------------------------------------------------------
+        print(f"Scanning {len(files)} files on GPU {ctx.device}...")
+        if sample:
+            assert sample >= 1, "Number of reads to sample must be ≥ 1!"
+            print(f"Sampling {sample} reads from the head of each file...")
+        ctx.reset()
+        names = []
+        for ordinal, path in enumerate(files):
+            name = os.path.basename(str(path))
+            print(f"Tallying barcodes from {name}...", end="")
+            reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
+            print(f"found {uniq} new barcode{'' if uniq == 1 else 's'} in {reads} reads.")
+            names.append(name)
+        tables = ScanTables(ctx, names)
+        print("Scanning complete! Analyzing barcodes...")
+
+        # ---- matcher (F:610-630) ---------------------------------------------------------------
+        sheet = ctx.load_sheet(indexes)
+        if sheet.single and rc_mode:
+            raise SystemExit("-rc needs a dual-index sample sheet")
+        use = None
+        idx2_used = sheet.idx2
+        if rc_mode:
+            first = ctx.match(num_subs, True, None, want_outputs=False)
+            rc_calls = ctx.rc_calls(first)
+            print("First round of analysis complete.")
+            report_rc_call_info(rc_calls, indexes, out_csv_name)
+            use = np.array([rc_calls[name]["call"] for name in sheet.ids], np.uint8)
+            idx2_used = [b if u else a for a, b, u in zip(sheet.idx2, sheet.rc_idx2, use)]
+            print("\nRe-analyzing barcodes with corrected index 2 sequences...")
+        res = ctx.match(num_subs, False, use)
+
+        # ---- demux_ok + CSV (F:632-642) --------------------------------------------------------
+        ok, bad_files = demux_ok_flags(tables, res["type"], res["srow"], sheet.ids, prefix)
+        if bad_files:
+            print("Incorrectly demultiplexed barcodes found! Affected files:")
+            for f in sorted(bad_files):
+                print(f)
+        else:
+            print("It appears that all files are already correctly demultiplexed.")
+        print(f"Analysis complete! Writing results to {out_csv_name}")
+        write_scan_csv(out_csv_name, tables, res, sheet, idx2_used, ok)
+    finally:
+        if own_ctx:
+            ctx.close()
+    return out_csv_name
+
+
+def write_scan_csv(path, tables, res, sheet, idx2_used, ok):
+    """idx1,idx2,matched_idx1,matched_idx2,read_type,sample_name,reads,demux_ok -- the layout the
+    reference actually writes (dict insertion order, F:286-291, F:311, F:556; csv.DictWriter F:499)."""
+    keys = unpack_keys(tables.keys)
+    pick = lambda table, rows: [table[i] if i >= 0 else "" for i in rows.tolist()]
+    m1, m2 = pick(sheet.idx1, res["m1"]), pick(idx2_used, res["m2"])
+    if sheet.single:
+        m2 = [""] * len(keys)
+    kinds = [READ_TYPES[t] for t in res["type"].tolist()]
+    names = pick(sheet.ids, res["srow"])
+    with open(path, "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["idx1", "idx2", "matched_idx1", "matched_idx2", "read_type", "sample_name", "reads", "demux_ok"])
+        for key, a, b, kind, name, reads, good in zip(keys, m1, m2, kinds, names, tables.counts.tolist(),
+                                                      ok.tolist()):
+            parts = key.split("+")
+            w.writerow([parts[0], parts[1] if len(parts) > 1 else "", a, b, kind, name, reads, good])
+
+
+# ---------------------------------------------------------------------------------------------
+# demux (F:645-814)
+# ---------------------------------------------------------------------------------------------
+def parse_results_file(result_file):
+    """{key: (read_type, sample_id)} by column position 0,1,5,6; header assertion of F:649-657."""
+    with open(result_file, newline="") as fh:
+        rows = csv.reader(fh)
+        header = next(rows)
+        assert header[0:7] == ["idx1", "idx2", "reads", "matched_idx1", "matched_idx2", "read_type",
+                               "sample_name"], f"${result_file} does not appear to be a valid frender result file!"
+        return {r[0] + "+" + r[1]: (r[5], r[6]) for r in rows}
+
+
+class GzSink:
+    """One output file: gzip member stream fed with raw record bytes."""
+
+    def __init__(self, path, level):
+        self.fh = open(path, "wb")
+        self.z = zlib.compressobj(level, zlib.DEFLATED, 31)
+
+    def write(self, data):
+        if len(data):
+            self.fh.write(self.z.compress(data))
+
+    def close(self):
+        self.fh.write(self.z.flush())
+        self.fh.close()
+
+
+class TextChunks:
+    """Decompressed bytes of a fastq.gz with the newline translation of text mode (F:776)."""
+
+    def __init__(self, path, size):
+        self.fh = gzip.open(path, "rb")
+        self.size = size
+        self.buf = b""
+        self.eof = False
+
+    def fill(self):
+        while not self.eof and len(self.buf) < self.size:
+            piece = self.fh.read(self.size - len(self.buf))
+            if not piece:
+                self.eof = True
+                break
+            if b"\r" in piece or self.buf.endswith(b"\r"):
+                joined = (self.buf + piece)
+                tail = b"\r" if joined.endswith(b"\r") and not self.eof else b""
+                body = joined[:len(joined) - len(tail)]
+                self.buf = body.replace(b"\r\n", b"\n").replace(b"\r", b"\n") + tail
+            else:
+                self.buf += piece
+        if self.eof and self.buf.endswith(b"\r"):
+            self.buf = self.buf[:-1] + b"\n"
+
+    def take(self):
+        """Bytes up to the last complete line (everything at EOF)."""
+        if self.eof:
+            return len(self.buf)
+        cut = self.buf.rfind(b"\n")
+        return cut + 1
+
+
+def frender_demux(args, ctx=None):
+    index_hop, ambiguous = not args.no_index_hop, not args.no_ambiguous
+    undeter, samples = not args.no_undeter, not args.no_samples
+    undeter_name = f"Undetermined{'-ambiguous' if ambiguous else ''}{'-index-hop' if index_hop else ''}"
+    result_file = Path(args.r)
+    if not result_file.is_file():
+        raise SystemExit(f"File {result_file} not found")
+    table = parse_results_file(result_file)
+    ids = list(set(v[1] for v in table.values()) - {""})
+    if (not ids) and samples:
+        print("Warning: no demuxable sample ids found in the supplied frender result file!")
+
+    out_dir = args.d if args.d.endswith("/") else args.d + "/"
+    os.mkdir(args.d)                                                            # FileExistsError as in F:755
+    level = int(os.environ.get("FRENDER_GZIP_LEVEL", "6"))
+    infix = args.o + "_" if args.o else ""
+    sink_names = []                                                             # sink id -> name
+
+    def open_sink(name):
+        sink_names.append(name)
+        return len(sink_names) - 1
+
+    sample_sink = {sid: open_sink(sid) for sid in ids} if samples else {}
+    undeter_sink = open_sink(undeter_name) if undeter else None
+    hop_sink = open_sink("Index-hop") if index_hop else undeter_sink
+    amb_sink = open_sink("Ambiguous") if ambiguous else undeter_sink
+    sinks = [{r: GzSink(f"{out_dir}{name}_frender-demux_{infix}{r}.fq.gz", level) for r in ("R1", "R2")}
+             for name in sink_names]
+    n_sinks = len(sink_names)
+    reject = n_sinks                                                            # "Unrecognized read type" bucket
+
+    def route_of(kind, sid):                                                    # F:780-805
+        if kind == "demuxable" and sample_sink:
+            return sample_sink[sid]
+        if kind == "index_hop" and hop_sink is not None:
+            return hop_sink
+        if kind == "ambiguous" and amb_sink is not None:
+            return amb_sink
+        if kind == "undetermined" and undeter_sink is not None:
+            return undeter_sink
+        return reject
+
+    keys = pack_keys(list(table.keys()))
+    routes = np.array([route_of(*v) for v in table.values()], np.uint32)
+
+    if len(args.files) == 1:
+        target = Path(args.files[0])
+        if target.is_dir():
+            files = {"dir": target}
+        elif target.is_file():
+            files = {"file": target}
+        else:
+            raise SystemExit("Specified directory or file path doesn't seem to exist!")
+    else:
+        files = {"file": [Path(f) for f in args.files]}
+    pairs = get_paired_files(parse_files(files, just_r1=False))
+
+    own_ctx = ctx is None
+    ctx = ctx or Context(int(os.environ.get("FRENDER_DEVICE", "0")), table_log2=12)
+    chunk = max(int(os.environ.get("FRENDER_DEMUX_CHUNK_MB", "64")) << 20, MIN_CHUNK)
+    try:
+        ctx.route_load(keys, routes, n_sinks + 1)
+        for r1_path, r2_path in pairs:
+            print(f"Demultiplexing {r1_path.name}...")
+            a, b = TextChunks(r1_path, chunk), TextChunks(r2_path, chunk)
+            while True:
+                a.fill()
+                b.fill()
+                fa, fb = a.eof, b.eof                       # eof: the buffer holds all that is left
+                na, nb = a.take(), b.take()
+                o1, o2, off1, off2, done, used1, used2 = ctx.route_pair(
+                    a.buf[:na], b.buf[:nb], (1 if fa else 0) | (2 if fb else 0))
+                if off1[reject + 1] > off1[reject]:
+                    raise SystemExit("Unrecognized read type found in supplied frender result file!")
+                for s in range(n_sinks):
+                    sinks[s]["R1"].write(o1[off1[s]:off1[s + 1]])
+                    sinks[s]["R2"].write(o2[off2[s]:off2[s + 1]])
+                a.buf, b.buf = a.buf[used1:], b.buf[used2:]
+                if (fa and not a.buf) or (fb and not b.buf) or (fa and fb):
+                    break                                   # zip() ends with the shorter mate (F:777)
+                if done == 0:                               # a record longer than the window: widen it
+                    a.size += chunk
+                    b.size += chunk
+    except FrbError as exc:
+        if exc.code == _lib.ERR_KEY_NOT_FOUND:
+            raise SystemExit(exc.message)
+        raise
+    finally:
+        for s in sinks:
+            s["R1"].close()
+            s["R2"].close()
+        if own_ctx:
+            ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+def build_parser():
+    """The argparse surface of the reference, flag for flag (F:817-926)."""
+    parser = argparse.ArgumentParser(prog="frender.py")
+    sub = parser.add_subparsers()
+    scan = sub.add_parser("scan", help="Scan file(s) or directory and compare to a supplied barcode table")
+    scan.add_argument("-n", metavar="[int]", type=int, required=True,
+                      help="REQUIRED: Number of mismatches allowed between supplied barcodes and fastq file(s)")
+    scan.add_argument("-rc", action="store_true",
+                      help="Scan/demultiplex using reverse complement of index 2 as well as forward sequence "
+                           "(to check for mistakes with e.g. HiSeq 4000 and other systems)")
+    scan.add_argument("-c", metavar="cores", type=float, default=1,
+                      help="Number of cores to use for analysis, default = 1. Use 0 for all available, a number "
+                           "between 0 and 1 for a fraction of all available cores, or a number >= 1 for a specified "
+                           "number of cores")
+    scan.add_argument("-s", metavar="sample", type=int,
+                      help="If set, sample an absolute number of reads from the head of each file (s >= 1)")
+    scan.add_argument("-o", metavar="output_name", help="name infix for output files")
+    scan.add_argument("-p", metavar="fix_prefix",
+                      help="When matching sample ids to filenames, remove this prefix from the sample id")
+    scan.add_argument("-b", metavar="barcode_table",
+                      help=".csv formatted file containing barcode associations with ids. REQUIRED unless you "
+                           "specify a directory already containing such a file.")
+    scan.add_argument("files", nargs="+",
+                      help="Fastq file, list of fastq files, or directory path containing fastq files "
+                           "(subdirectories will be searched as well)")
+    scan.set_defaults(func=frender_scan)
+
+    demux = sub.add_parser("demux", help="Demultiplex reads into sample and undetermined files according to "
+                                         "supplied frender scan results file")
+    demux.add_argument("-i", "--no-index-hop", action="store_true",
+                       help="don't split index hop reads into their own file (will be included in undetermined "
+                            "file unless -u is set)")
+    demux.add_argument("-a", "--no-ambiguous", action="store_true",
+                       help="don't split ambiguous reads into their own file (will be included in undetermined "
+                            "file unless -u is set)")
+    demux.add_argument("-u", "--no-undeter", action="store_true", help="do NOT produce undetermined files")
+    demux.add_argument("-s", "--no-samples", action="store_true", help="do NOT produce individual sample files")
+    demux.add_argument("-o", metavar="output_name", help="name infix for output files")
+    demux.add_argument("-d", metavar="output_dir",
+                       default=f"./frender-demux-output_{datetime.strftime(datetime.now(timezone.utc), STAMP)}/",
+                       help="output directory (default: ./frender-demux-output_{date_time}/)")
+    demux.add_argument("-r", metavar="result_file", required=True,
+                       help="REQUIRED: frender scan result file (typically named "
+                            "'frender-scan-result_n-mismatches_{output infix or file/directory name}.csv')")
+    demux.add_argument("files", nargs="+",
+                       help="Fastq file, list of fastq files, or directory path containing fastq files "
+                            "(subdirectories will be searched as well)")
+    demux.set_defaults(func=frender_demux)
+    return parser
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    args.func(args)

@@ -101,7 +101,7 @@ int frb_route_pair(frb_ctx* c, const void* r1, uint64_t r1_bytes, const void* r2
     TRY(route_parse(c, b.in1, r1_bytes, kRuleOffsetsOnly, nullptr, b.off1, &n1, &lines1));
     // zip() of the 4-line groupers stops at the shorter mate (F:777); a trailing partial record
     // only exists at the end of a file (F:719-723)
-    const uint64_t e1 = final_chunk ? n1 : lines1 / 4, e2 = final_chunk ? n2 : lines2 / 4;
+    const uint64_t e1 = (final_chunk & 1) ? n1 : lines1 / 4, e2 = (final_chunk & 2) ? n2 : lines2 / 4;
     const uint64_t n = std::min(e1, e2);
     *n_pairs = n;
     unsigned long long c1 = 0, c2 = 0;

@@ -267,6 +267,28 @@ class Context:
         results, _ = self.process(None, indexes, num_subs, False, use_rc_rows=use)
         return results, calls, oriented
 
+    # ---- hot path C -------------------------------------------------------------------------
+    def route_load(self, keys, sink_ids, n_sinks):
+        """Results table for the demux router: packed key -> sink id (unique keys)."""
+        keys = np.ascontiguousarray(keys, np.uint64)
+        sink_ids = np.ascontiguousarray(sink_ids, np.uint32)
+        self._ck(lib.frb_route_load(self._h, _ptr(keys), _ptr(sink_ids), len(keys), n_sinks))
+        self._n_sinks = n_sinks
+
+    def route_pair(self, r1, r2, final=3):
+        """Partition one record-aligned chunk pair by sink (frb_route_pair).  Returns
+        (out_r1, out_r2, off_r1, off_r2, pairs, consumed_r1, consumed_r2); sink s of mate m is
+        out_m[off_m[s]:off_m[s+1]]."""
+        a = np.frombuffer(r1, np.uint8)
+        b = np.frombuffer(r2, np.uint8)
+        o1, o2 = np.empty(max(a.size, 1), np.uint8), np.empty(max(b.size, 1), np.uint8)
+        off1, off2 = np.zeros(self._n_sinks + 1, np.uint64), np.zeros(self._n_sinks + 1, np.uint64)
+        pairs, u1, u2, bad = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(lib.frb_route_pair(self._h, _ptr(a), a.size, _ptr(b), b.size, int(final), _ptr(o1), _ptr(o2),
+                                    _ptr(off1), _ptr(off2), C.byref(pairs), C.byref(u1), C.byref(u2), C.byref(bad)))
+        return (o1[:u1.value].tobytes(), o2[:u2.value].tobytes(), off1.astype(np.int64), off2.astype(np.int64),
+                pairs.value, u1.value, u2.value)
+
     # ---- measurement ------------------------------------------------------------------------
     def launches(self):
         return lib.frb_launch_count(self._h)

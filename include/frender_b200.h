@@ -146,8 +146,9 @@ int frb_match(frb_ctx* ctx, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_
  *                    out_r1 / out_r2 (host, >= the input sizes); sink s of mate m occupies
  *                    [off_m[s], off_m[s+1]) (n_sinks+1 offsets).  Stops at the shorter mate
  *                    (F:777): *n_pairs pairs were routed and consumed_r1/2 bytes of each input
- *                    used; the caller carries the rest into the next call.  Only when
- *                    final_chunk != 0 does a trailing partial record count (F:719-723).
+ *                    used; the caller carries the rest into the next call.  final_chunk bit 0 /
+ *                    bit 1: the R1 / R2 chunk reaches the end of its file, so a trailing
+ *                    partial record of that mate counts as a record (F:719-723).
  */
 int frb_route_load(frb_ctx* ctx, const uint64_t* keys, const uint32_t* sink_ids, uint64_t n, uint32_t n_sinks);
 int frb_route_pair(frb_ctx* ctx, const void* r1, uint64_t r1_bytes, const void* r2, uint64_t r2_bytes,
