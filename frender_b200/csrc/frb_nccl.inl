@@ -91,7 +91,7 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
     ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
     const int R = c->n_ranks;
     unsigned long long* d_sizes = nullptr;
-    CU(c, cudaMalloc(&d_sizes, (R + 1) * 8));
+    TRY(dmalloc(c, &d_sizes, (R + 1) * 8));
     unsigned long long mine = c->total.n;
     CU(c, cudaMemcpyAsync(d_sizes + R, &mine, 8, cudaMemcpyHostToDevice, c->compute));
     NC(c, api, api->AllGather(d_sizes + R, d_sizes, 1, ncclUint64, comm, c->compute));
@@ -102,8 +102,8 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
     for (auto s : sizes) mx = std::max(mx, s);
     // one padded buffer per field: [R][mx]
     unsigned long long *send = nullptr, *recv = nullptr;
-    CU(c, cudaMalloc(&send, 3 * mx * 8));
-    CU(c, cudaMalloc(&recv, 3ULL * R * mx * 8));
+    TRY(dmalloc(c, &send, 3 * mx * 8));
+    TRY(dmalloc(c, &recv, 3ULL * R * mx * 8));
     CU(c, cudaMemsetAsync(send, 0, 3 * mx * 8, c->compute));
     if (mine) {
         CU(c, cudaMemcpyAsync(send, c->total.keys, mine * 8, cudaMemcpyDeviceToDevice, c->compute));
@@ -122,10 +122,9 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
         c->launches++;
     }
     CU(c, cudaGetLastError());
-    CU(c, cudaStreamSynchronize(c->compute));
-    CU(c, cudaFree(send));
-    CU(c, cudaFree(recv));
-    CU(c, cudaFree(d_sizes));
+    TRY(dfree(c, send));
+    TRY(dfree(c, recv));
+    TRY(dfree(c, d_sizes));
     c->total_ready = false;
     return frb_total_finish(c, n_unique);
 }

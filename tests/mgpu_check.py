@@ -1,0 +1,54 @@
+"""Run under torchrun with N ranks (one per GPU): every rank scans its own shard of a synthetic
+lane, the per-rank tables are merged over NCCL (frb_allmerge) and every rank must end with the
+oracle's tally of the whole lane, in the oracle's order, and the oracle's classifications."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    import torch.distributed as dist
+
+    import frender_oracle as O
+    from frender_b200 import _lib as L
+    from frender_b200 import synth
+    from frender_b200.engine import C, Context, unpack_keys
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = Context(int(os.environ["LOCAL_RANK"]), table_log2=18)
+    spec = synth.make_spec("C2", n_samples=64)
+    per = 30_000
+    shard = synth.generate(spec, rank * per, (rank + 1) * per)          # chunk sharding: rank r owns chunk r
+    ident = (C.c_char * 128)()
+    if rank == 0:
+        ctx._ck(L.lib.frb_nccl_unique_id(ident))
+    box = [bytes(ident)]
+    dist.broadcast_object_list(box, src=0)
+    ctx._ck(L.lib.frb_nccl_init(ctx._h, box[0], rank, world))
+    ctx.reset()
+    ctx.scan_bytes(shard, ordinal=rank)                                  # first_pos = (chunk ordinal, read ordinal)
+    n = C.c_uint64()
+    ctx._ck(L.lib.frb_allmerge(ctx._h, C.byref(n)))
+    keys, counts, _ = ctx.total_arrays()
+    whole = synth.generate(spec, 0, world * per)
+    want, visited = O.tally_text(whole.decode().splitlines(keepends=True))
+    got = dict(zip(unpack_keys(keys), counts.tolist()))
+    assert visited == world * per
+    assert list(got.items()) == list(want.items()), f"rank {rank}: merged tally differs from the oracle"
+    res, calls, _ = ctx.analyze(spec.indexes(), 1, True)
+    want_res, want_calls, _ = O.scan_analysis(1, {"total": want}, spec.indexes(), 1, True)
+    assert res == want_res and calls == want_calls, f"rank {rank}: matcher differs from the oracle"
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu ok: {world} ranks, {len(got)} unique keys, merged == oracle on every rank")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""Multi-rank paths.  CPU: the rank-count invariance of the merge on gloo, world size 2 (host logic
+only, oracle tallies stand in for the device tables).  GPU: NCCL merge against the oracle when the
+box has >= 2 GPUs (tests/mgpu_check.py under torchrun)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+import torch.distributed as dist
+import frender_oracle as O
+from frender_b200 import synth
+from frender_b200.shard import assign, merge_lists
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+spec = synth.make_spec("C1", n_samples=12)
+chunks = [(i, i * 500, (i + 1) * 500) for i in range(7)]            # (ordinal, g0, g1): 7 chunks, 2 ranks
+mine = assign(chunks, rank, world)
+local = []
+for ordinal, g0, g1 in mine:
+    counter, _ = O.tally_text(synth.generate(spec, g0, g1).decode().splitlines(keepends=True))
+    firsts = {{}}
+    for pos, key in enumerate(synth.keys_of(spec, g0, g1)):
+        firsts.setdefault(key, (ordinal << 40) | pos)
+    local.append([(k, n, firsts[k]) for k, n in counter.items()])
+gathered = [None] * world
+dist.all_gather_object(gathered, local)
+merged = merge_lists([lst for per_rank in gathered for lst in per_rank])
+want, _ = O.tally_text(synth.generate(spec, 0, 3500).decode().splitlines(keepends=True))
+assert list(merged.items()) == list(want.items()), "merged tally differs from the single-process oracle"
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_merge_is_rank_count_invariant_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_assign_covers_everything_once():
+    from frender_b200.shard import assign
+    items = list(range(23))
+    for world in (1, 2, 3, 8):
+        parts = [assign(items, r, world) for r in range(world)]
+        assert sorted(x for p in parts for x in p) == items
+
+
+@pytest.mark.gpu
+def test_nccl_merge_matches_oracle():
+    import ctypes
+    n = ctypes.c_int()
+    from frender_b200._lib import lib
+    lib.frb_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(n.value, 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "mgpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "mgpu ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
