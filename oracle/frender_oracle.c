@@ -1,0 +1,161 @@
+/* CPU oracle in plain C for the frender scan hot path -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A restatement of the reference's algorithms (/root/reference/frender.py, "F:") that is fast
+ * enough to check the CUDA path at millions of reads.  It is checked against the Python oracle
+ * (itself pinned by fixtures the reference wrote, tests/golden) in tests/test_oracle_c.py.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it; the product never
+ * does.  Build: `make -C oracle` -> oracle/_build/liboracle.so.
+ *
+ *   oracle_tally     every 4th line -> key -> count, in first-appearance order    (F:154-181)
+ *   oracle_classify  Hamming match + classification of one key list              (F:214-351)
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KEY_MAX 63
+
+typedef struct {
+    char (*keys)[KEY_MAX + 1]; /* first-appearance order */
+    uint64_t* counts;
+    uint64_t n, cap, reads;
+    uint64_t* slots;           /* open addressing: index + 1 into keys, 0 = empty */
+    uint64_t nslots;
+} tally_t;
+
+static uint64_t fnv(const char* s, size_t n) {
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)s[i]) * 1099511628211ULL;
+    return h;
+}
+
+static void grow(tally_t* t) {
+    uint64_t ns = t->nslots ? t->nslots * 2 : 1024;
+    free(t->slots);
+    t->slots = calloc(ns, sizeof(uint64_t));
+    t->nslots = ns;
+    for (uint64_t i = 0; i < t->n; ++i) {
+        uint64_t h = fnv(t->keys[i], strlen(t->keys[i])) & (ns - 1);
+        while (t->slots[h]) h = (h + 1) & (ns - 1);
+        t->slots[h] = i + 1;
+    }
+}
+
+static void add(tally_t* t, const char* key, size_t len) {
+    if (t->n * 2 >= t->nslots) grow(t);
+    uint64_t h = fnv(key, len) & (t->nslots - 1);
+    while (t->slots[h]) {
+        const char* k = t->keys[t->slots[h] - 1];
+        if (strlen(k) == len && memcmp(k, key, len) == 0) {
+            t->counts[t->slots[h] - 1]++;
+            return;
+        }
+        h = (h + 1) & (t->nslots - 1);
+    }
+    if (t->n == t->cap) {
+        t->cap = t->cap ? t->cap * 2 : 1024;
+        t->keys = realloc(t->keys, t->cap * sizeof(*t->keys));
+        t->counts = realloc(t->counts, t->cap * sizeof(uint64_t));
+    }
+    memcpy(t->keys[t->n], key, len);
+    t->keys[t->n][len] = 0;
+    t->counts[t->n] = 1;
+    t->slots[h] = ++t->n;
+}
+
+/* rule 0: line.rstrip("\n").split(" ")[1].split(":")[-1]   (F:169)
+ * rule 1: line.split(":")[-1].rstrip("\n")                 (F:778)
+ * returns 0, -1 = header without a second token (IndexError), -2 = key longer than KEY_MAX */
+static int key_of(const unsigned char* s, size_t len, int rule, const unsigned char** k, size_t* klen) {
+    const unsigned char *a = s, *e = s + len;
+    if (rule == 0) {
+        const unsigned char* sp = memchr(s, ' ', len);
+        if (!sp) return -1;
+        a = sp + 1;
+        const unsigned char* sp2 = memchr(a, ' ', (size_t)(e - a));
+        if (sp2) e = sp2;
+    }
+    for (const unsigned char* p = e; p > a; --p)
+        if (p[-1] == ':') {
+            a = p;
+            break;
+        }
+    if ((size_t)(e - a) > KEY_MAX) return -2;
+    *k = a;
+    *klen = (size_t)(e - a);
+    return 0;
+}
+
+void* oracle_tally(const unsigned char* data, uint64_t nbytes, int rule, uint64_t sample, int* err) {
+    tally_t* t = calloc(1, sizeof(tally_t));
+    uint64_t pos = 0, line = 0;
+    *err = 0;
+    while (pos < nbytes) {
+        const unsigned char* nl = memchr(data + pos, '\n', nbytes - pos);
+        uint64_t end = nl ? (uint64_t)(nl - data) : nbytes;
+        if ((line & 3) == 0) {
+            if (sample && t->reads >= sample) break; /* F:163-165 */
+            t->reads++;
+            const unsigned char* k;
+            size_t klen;
+            int rc = key_of(data + pos, end - pos, rule, &k, &klen);
+            if (rc) {
+                *err = rc;
+                return t;
+            }
+            add(t, (const char*)k, klen);
+        }
+        pos = end + 1;
+        line++;
+    }
+    return t;
+}
+uint64_t oracle_tally_size(void* h) { return ((tally_t*)h)->n; }
+uint64_t oracle_tally_reads(void* h) { return ((tally_t*)h)->reads; }
+const char* oracle_tally_key(void* h, uint64_t i) { return ((tally_t*)h)->keys[i]; }
+uint64_t oracle_tally_count(void* h, uint64_t i) { return ((tally_t*)h)->counts[i]; }
+void oracle_tally_free(void* h) {
+    tally_t* t = h;
+    free(t->keys), free(t->counts), free(t->slots), free(t);
+}
+
+static int lower(int c) { return (c >= 'A' && c <= 'Z') ? c + 32 : c; }
+static int within(const char* q, const char* c, int len, int max_subs) { /* F:226-230 */
+    int d = 0;
+    for (int i = 0; i < len; ++i) d += lower(q[i]) != lower(c[i]);
+    return d <= max_subs;
+}
+
+/* One key ("idx1+idx2[+...]") against the sheet (rows of fixed-width strings l1 / l2).
+ * out[0] = first idx1 match row or -1, out[1] = first idx2 match row or -1,
+ * out[2] = read type (0 undetermined, 1 index_hop, 2 demuxable, 3 ambiguous), out[3] = sample row.
+ * returns 0, -1 when a length differs from the sheet (AssertionError F:227) or no '+' (F:306). */
+int oracle_classify(const char* key, const char* idx1, const char* idx2, int rows, int l1, int l2, int max_subs,
+                    int* out) {
+    const char* plus = strchr(key, '+');
+    if (!plus || (int)(plus - key) != l1) return -1;
+    const char* b = plus + 1;
+    const char* plus2 = strchr(b, '+');
+    int blen = plus2 ? (int)(plus2 - b) : (int)strlen(b);
+    if (blen != l2) return -1;
+    int first1 = -1, first2 = -1, both = 0, both_row = -1;
+    for (int r = 0; r < rows; ++r) {
+        int m1 = within(key, idx1 + (size_t)r * l1, l1, max_subs);
+        int m2 = within(b, idx2 + (size_t)r * l2, l2, max_subs);
+        if (m1 && first1 < 0) first1 = r;
+        if (m2 && first2 < 0) first2 = r;
+        if (m1 && m2) {
+            both++;
+            if (both_row < 0) both_row = r;
+        }
+    }
+    if (first1 >= 0 && first2 >= 0) { /* F:259-278 */
+        out[0] = first1, out[1] = first2;
+        out[2] = both == 0 ? 1 : (both == 1 ? 2 : 3);
+        out[3] = both == 1 ? both_row : -1;
+    } else { /* F:280-284 */
+        out[0] = out[1] = out[3] = -1;
+        out[2] = 0;
+    }
+    return 0;
+}
