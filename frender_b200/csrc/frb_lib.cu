@@ -324,8 +324,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.dbg_flags = getenv("FRB_DBG_FLAGS") ? atoi(getenv("FRB_DBG_FLAGS")) : 0;
     static unsigned long long* timing = nullptr;
     if (getenv("FRB_SCAN_TIMING")) {
-        if (!timing) cudaMalloc(&timing, 64);
-        cudaMemsetAsync(timing, 0, 64, c->compute);
+        if (!timing) cudaMalloc(&timing, 80);
+        cudaMemsetAsync(timing, 0, 80, c->compute);
         a.timing = timing;
     }
     {
@@ -343,14 +343,15 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     }
     CU(c, cudaGetLastError());
     if (a.timing) {
-        unsigned long long h[8];
+        unsigned long long h[10];
         cudaStreamSynchronize(c->compute);
-        cudaMemcpy(h, a.timing, 64, cudaMemcpyDeviceToHost);
-        const char* names[6] = {"wait", "count", "lookback", "positions", "parse+insert", "tail"};
+        cudaMemcpy(h, a.timing, 80, cudaMemcpyDeviceToHost);
+        const char* names[9] = {"wait", "count", "lookback", "positions", "parse", "insert", "tile-end", "claim-bar", "issue"};
         double sum = 0;
-        for (int i = 0; i < 6; ++i) sum += static_cast<double>(h[i]);
-        fprintf(stderr, "SCAN TIMING tiles %llu cycles/tile %.0f:", h[6], sum / (h[6] ? h[6] : 1));
-        for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f (%.0f%%)", names[i], (double)h[i] / (h[6] ? h[6] : 1), 100.0 * h[i] / sum);
+        for (int i = 0; i < 9; ++i) sum += static_cast<double>(h[i]);
+        const double tiles = h[9] ? static_cast<double>(h[9]) : 1.0;
+        fprintf(stderr, "SCAN TIMING tiles %llu cycles/tile %.0f:", h[9], sum / tiles);
+        for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.0f", names[i], (double)h[i] / tiles);
         fprintf(stderr, "\n");
     }
     return FRB_OK;

@@ -232,9 +232,14 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
 // Decoupled look-back over per-tile newline counts.  The tile's own count was published by the
 // count stage (one pipeline step earlier, see scan_kernel); returns the number of newlines before
 // tile t and publishes the tile's inclusive prefix.  Called by one full warp.
-__device__ __forceinline__ unsigned long long tile_prefix(volatile unsigned long long* status, unsigned t,
-                                                          unsigned total, int lane) {
-    if (t == 0) return 0;  // published as inclusive by the count stage
+// kBlocking = false: a single pass that gives up (returns false) as soon as a needed count is not
+// published yet -- used to take the look-back off the critical path without ever stalling a CTA on
+// another CTA's progress.
+template <bool kBlocking>
+__device__ __forceinline__ bool tile_prefix(volatile unsigned long long* status, unsigned t, unsigned total,
+                                            int lane, unsigned long long* out) {
+    *out = 0;
+    if (t == 0) return true;  // published as inclusive by the count stage
     unsigned long long excl = 0;
     long long idx = static_cast<long long>(t) - 1;
     for (;;) {
@@ -254,12 +259,14 @@ __device__ __forceinline__ unsigned long long tile_prefix(volatile unsigned long
                 done = first_inc < 32;
                 break;
             }
+            if (!kBlocking) return false;
         }
         if (done) break;
         idx -= 32;
     }
     if (lane == 0) status[t] = kFlagInc | (excl + total);
-    return excl;
+    *out = excl;
+    return true;
 }
 
 // Software pipeline of one CTA over its tiles T0, T1, ... (claimed from a global counter), three
@@ -285,7 +292,8 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     uint16_t* const s_start = reinterpret_cast<uint16_t*>(smem + kStages * kBuf);
     uint16_t* const s_end = s_start + kHdrCap;
     __shared__ __align__(8) unsigned long long s_bar[kStages];
-    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_prefix[2];
+    __shared__ unsigned s_have_prefix[2];  // early look-back of the tile parsed in iteration (i & 1) succeeded
     __shared__ unsigned s_tile[kStages];
     __shared__ unsigned s_warp[kThreads / 32];
     __shared__ unsigned s_halo_start;
@@ -298,9 +306,9 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     volatile unsigned long long* status = a.status + 1;
 
     // stage timing (thread 0 only, when a.timing is set): 0 wait, 1 count, 2 look-back, 3 positions,
-    // 4 parse+insert, 5 tail, 6 tiles
+    // 4 parse, 5 insert+sync, 6 end-of-tile atomics+sync, 7 claim+issue+sync, 9 tiles
     long long tmark = 0;
-    unsigned long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto tick = [&](int slot) {
         if (a.timing && tid == 0) {
             const long long now = clock64();
@@ -310,13 +318,13 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     };
     if (a.timing && tid == 0) tmark = clock64();
 
-    // Tile ids are claimed one step before they are needed so that the atomic's round trip to L2 is
-    // not on the critical path (thread 0 only).
+    // Tile tickets.  __syncthreads() waits for the arriving thread's outstanding global atomics, so the
+    // ticket for the tile after next is drawn at the start of the barrier-free key-extraction phase
+    // (claim_next) and only consumed one iteration later (issue): its L2 round trip is never exposed.
     unsigned claimed = 0;
-    if (tid == 0) claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
-    auto claim_and_issue = [&](int b) {  // thread 0 only
+    auto claim_next = [&]() { claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL)); };  // thread 0
+    auto issue = [&](int b) {  // thread 0 only: start the bulk copy of tile `claimed` into buffer b
         const unsigned t = claimed;
-        claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL));
         s_tile[b] = t;
         if (t >= a.n_tiles) return;
         const unsigned long long off = static_cast<unsigned long long>(t) * kTile;
@@ -408,23 +416,52 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
 #pragma unroll
         for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
         mbar_fence_init();
-        claim_and_issue(0);
-        claim_and_issue(1);
+        claim_next();
+        issue(0);
+        claim_next();
+        issue(1);
+        claim_next();
     }
     __syncthreads();
     TileState cur{}, nxt{};
     count_stage(0, cur);
+    // look-back of the first tile; later tiles are looked back one iteration ahead (see stage B)
+    if (warp == kThreads / 32 - 1 && lane == 0) s_have_prefix[0] = 0, s_have_prefix[1] = 0;
+    __syncthreads();
 
-    // Deferred table update: the slot of a key is fetched when the key is extracted and examined
-    // one tile later, so the DRAM latency of the (random) probe is off the tile's critical path.
-    unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
-    unsigned p_cnt = 0;  // 0 = nothing pending
+    // Deferred table update, three steps, each consuming a memory result issued one tile earlier so
+    // that no DRAM / L2 round trip of the (random) probe sits on the tile's critical path:
+    //   step 1 (tile i)    key extracted -> load of its home slot issued
+    //   step 2 (tile i+1)  slot holds the key -> RED.ADD/RED.MIN;  slot empty -> CAS issued
+    //   step 3 (tile i+2)  CAS won (or another thread inserted the same key) -> RED.ADD/RED.MIN
+    // anything else (collision) falls back to the synchronous probing loop.
+    unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;  // step-1 state
+    unsigned p_cnt = 0;                                               // 0 = nothing pending
+    unsigned long long q_key = 0, q_pos = 0, q_slot = 0, q_old = 0;   // step-2 state (CAS in flight)
+    unsigned q_cnt = 0;
+    auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
+        atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
+        if (!(a.dbg_flags & 2)) atomicMin(&a.table[slot].first, pos);
+    };
     auto finish_pending = [&]() {
-        if (p_cnt) {
+        if (q_cnt) {  // step 3
+            if (q_old == kEmpty) {
+                atomicAdd(&a.st->occupied, 1ULL);
+                bump(q_slot, q_cnt, q_pos);
+            } else if (q_old == q_key) {
+                bump(q_slot, q_cnt, q_pos);
+            } else {
+                table_add(a.table, a.table_mask, q_key, q_cnt, q_pos, &a.st->occupied, a.st);
+            }
+            q_cnt = 0;
+        }
+        if (p_cnt) {  // step 2
             if (a.dbg_flags & 1) {
             } else if (p_seen == p_key) {
-                atomicAdd(&a.table[p_slot].count, static_cast<unsigned long long>(p_cnt));
-                if (!(a.dbg_flags & 2)) atomicMin(&a.table[p_slot].first, p_pos);
+                bump(p_slot, p_cnt, p_pos);
+            } else if (p_seen == kEmpty) {
+                q_key = p_key, q_pos = p_pos, q_slot = p_slot, q_cnt = p_cnt;
+                q_old = atomicCAS(&a.table[p_slot].key, kEmpty, p_key);
             } else {
                 table_add(a.table, a.table_mask, p_key, p_cnt, p_pos, &a.st->occupied, a.st);
             }
@@ -433,12 +470,14 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     };
 
     int c = 0, n = 1, nn = 2;
-    for (;;) {
+    unsigned long long my_reads = 0;  // thread 0: reads tallied by this CTA
+    for (unsigned iter = 0;; ++iter) {
         const unsigned t = s_tile[c];
         if (t >= a.n_tiles) break;
-        if (tid == 0) claim_and_issue(nn);  // buffer nn was released at the end of the last iteration
-        __syncthreads();                    // s_tile[nn] visible; also orders the stages
-        tick(5);
+        if (tid == 0) issue(nn);  // buffer nn was released at the end of the last iteration
+        tick(8);
+        __syncthreads();          // s_tile[nn] visible; also orders the stages
+        tick(7);
         count_stage(n, nxt);
 
         unsigned char* const buf = smem + c * kBuf;
@@ -446,11 +485,14 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
         const bool is_last = (t == a.n_tiles - 1);
         const unsigned total = cur.total, vnl = cur.vnl, valid = cur.valid;
 
-        // ---- stage A: tile prefix (warp 0) and start of the straddling line (last warp) ---------
-        if (warp == 0) {
-            const unsigned long long excl = tile_prefix(status, t, total, lane);
-            if (lane == 0) s_prefix = excl;
-        } else if (warp == kThreads / 32 - 1) {
+        // ---- stage A: tile prefix unless the early attempt of the previous iteration already has it
+        //      (warp 0), start of the line that straddles the tile start (last warp) -----------------
+        if (warp == 0 && !s_have_prefix[iter & 1]) {
+            unsigned long long excl;
+            tile_prefix<true>(status, t, total, lane, &excl);
+            if (lane == 0) s_prefix[iter & 1] = excl;
+        }
+        if (warp == kThreads / 32 - 1) {
             if (t == 0) {
                 if (lane == 0) s_halo_start = kHalo;
             } else {
@@ -466,10 +508,26 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
         __syncthreads();
         tick(2);
 
-        const unsigned long long K0 = L0 + s_prefix;  // index of the first newline of the tile
+        const unsigned long long K0 = L0 + s_prefix[iter & 1];  // index of the first newline of the tile
         const unsigned long long o_first = (K0 + 3) >> 2;
         const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
         const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
+
+        // Work that issues global atomics or spins on other CTAs runs once per tile at the start of the
+        // longest barrier-free stretch (key extraction), so that no __syncthreads() waits for an L2
+        // round trip: last tile's table updates, the ticket for the tile after next, and the look-back
+        // of the NEXT tile (its count was published by this iteration's stage C) on the last warp, which
+        // has no headers to parse in ordinary tiles.
+        auto between_barriers = [&]() {
+            finish_pending();
+            if (tid == 0) claim_next();
+            if (warp == kThreads / 32 - 1) {
+                unsigned long long excl = 0;
+                const bool ok = s_tile[n] < a.n_tiles && tile_prefix<false>(status, s_tile[n], nxt.total, lane, &excl);
+                if (lane == 0) s_prefix[(iter + 1) & 1] = excl, s_have_prefix[(iter + 1) & 1] = ok ? 1u : 0u;
+            }
+        };
+        if (n_owned == 0) between_barriers();
 
         // ---- stage B -----------------------------------------------------------------------------
         for (unsigned hbase = 0; hbase < n_owned; hbase += kHdrCap) {
@@ -508,6 +566,9 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
             __syncthreads();
             tick(3);
 
+            if (hbase == 0) between_barriers();
+            else finish_pending();
+
             // key extraction, warp-aggregated count
             const unsigned npass = (n_owned - hbase < kHdrCap) ? (n_owned - hbase) : kHdrCap;
             for (unsigned h0 = 0; h0 < npass; h0 += kThreads) {
@@ -523,10 +584,11 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
                     }
                 }
                 const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
-                finish_pending();
+                tick(4);
+                if (h0) finish_pending();  // more than one header per thread: make room for the next key
                 if (have) {
                     const unsigned same = __match_any_sync(grp, key);
-                    if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal of the group
+                    if (a.table && !(a.dbg_flags & 8) && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
                         p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
                         p_slot = hash64(key) & a.table_mask;
                         p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
@@ -539,24 +601,27 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
                 }
             }
             __syncthreads();
-            tick(4);
+            tick(5);
         }
 
         if (tid == 0) {
             const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
-            if (c_hi > o_first) atomicAdd(&a.st->n_reads, c_hi - o_first);
+            if (c_hi > o_first) my_reads += c_hi - o_first;
             if (is_last) a.st->line_carry = K0 + total + vnl;
-            tacc[6] += 1;
+            tacc[9] += 1;
         }
         __syncthreads();  // everyone is done with buffer c and the header lists
+        tick(6);
         cur = nxt;
         const int old = c;
         c = n, n = nn, nn = old;
     }
     finish_pending();
+    finish_pending();  // a CAS issued by the call above
+    if (tid == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
     if (a.timing && tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) atomicAdd(&a.timing[i], tacc[i]);
+        for (int i = 0; i < 10; ++i) atomicAdd(&a.timing[i], tacc[i]);
     }
 }
 
