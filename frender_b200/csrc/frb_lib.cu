@@ -22,6 +22,7 @@
 #include "match_kernel.cuh"
 #include "route_kernel.cuh"
 #include "scan_kernel.cuh"
+#include "scan_ws_kernel.cuh"
 #include "synth_kernel.cuh"
 #include "table_kernels.cuh"
 
@@ -292,6 +293,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     if (nbytes == 0) return FRB_OK;
     if (reinterpret_cast<uintptr_t>(dev) & 15) return fail(c, FRB_ERR_ARG, "chunk pointer must be 16-byte aligned");
     static const int nt = getenv("FRB_SCAN_THREADS") ? atoi(getenv("FRB_SCAN_THREADS")) : 256;
+    // default: warp-specialised kernel; FRB_SCAN_KERNEL=std selects the barrier-synchronous pipeline
+    static const bool ws = getenv("FRB_SCAN_KERNEL") ? strcmp(getenv("FRB_SCAN_KERNEL"), "std") != 0 : true;
     const uint64_t tile = static_cast<uint64_t>(nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile);
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
@@ -330,7 +333,10 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     }
     {
         ProfScope ps(c, FRB_K_SCAN);
-        if (nt == 128) {
+        if (ws) {
+            const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * 2));
+            scan_ws_kernel<<<grid, kWsThreads, kWsSmem, c->compute>>>(a);
+        } else if (nt == 128) {
             using Cfg = ScanCfg<128>;
             const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
             scan_kernel<128><<<grid, Cfg::threads, Cfg::smem, c->compute>>>(a);
@@ -346,7 +352,9 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         unsigned long long h[10];
         cudaStreamSynchronize(c->compute);
         cudaMemcpy(h, a.timing, 80, cudaMemcpyDeviceToHost);
-        const char* names[9] = {"wait", "count", "lookback", "positions", "parse", "insert", "tile-end", "claim-bar", "issue"};
+        const char* names_std[9] = {"wait", "count", "lookback", "positions", "parse", "insert", "tile-end", "claim-bar", "issue"};
+        const char* names_ws[9] = {"C:wait-bytes", "C:count", "P:wait-counted", "P:lookback", "P:endsync", "P:early-lb", "P:finish-pending", "P:parse_header", "P:match+issue"};
+        const char** names = ws ? names_ws : names_std;
         double sum = 0;
         for (int i = 0; i < 9; ++i) sum += static_cast<double>(h[i]);
         const double tiles = h[9] ? static_cast<double>(h[9]) : 1.0;
@@ -422,6 +430,7 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaEventCreate(&c->t1));
     CU(c, cudaFuncSetAttribute(scan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<256>::smem));
     CU(c, cudaFuncSetAttribute(scan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<128>::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TRY(clear_table(c, c->total_tab));
     CU(c, cudaStreamSynchronize(c->compute));

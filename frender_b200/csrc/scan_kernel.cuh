@@ -32,8 +32,8 @@ struct ScanCfg {
     static constexpr int threads = NT;
     static constexpr int tile = NT * kPerThread;
     static constexpr int buf = tile + kHalo;
-    static constexpr int hdr_cap = NT * 4;
-    static constexpr int smem = kStages * buf + 2 * hdr_cap * (int)sizeof(uint16_t);
+    static constexpr int nl_cap = NT * 8;  // newline positions kept per tile (more: serial fallback)
+    static constexpr int smem = kStages * buf + 2 * nl_cap * (int)sizeof(uint16_t);
     static constexpr int ctas_per_sm = (220 * 1024) / (smem + 2048) > 8 ? 8 : (220 * 1024) / (smem + 2048);
 };
 
@@ -95,6 +95,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     // not __syncwarp(): nvcc sees straight-line code here and drops it
     asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
 }
+// non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// single-thread wait (no warp reconvergence: the caller is one elected lane)
+__device__ __forceinline__ void mbar_wait_one(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FRB_WAIT1_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FRB_DONE1_%=;\n\t"
+        "bra FRB_WAIT1_%=;\n\t"
+        "FRB_DONE1_%=:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_addr(dst)),
@@ -109,12 +133,16 @@ __device__ __forceinline__ unsigned eq_flags(unsigned w, unsigned pat) {
     unsigned t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return ~(t | x) & 0x80808080u;
 }
-// flags at bits 7/15/23/31 -> 4 adjacent bits (byte 0 -> bit 0)
-__device__ __forceinline__ unsigned gather4(unsigned y) { return (((y >> 7) * 0x00204081u) >> 21) & 0xFu; }
-__device__ __forceinline__ unsigned newline_mask16(const uint4 v) {
-    return gather4(eq_flags(v.x, 0x0A0A0A0Au)) | (gather4(eq_flags(v.y, 0x0A0A0A0Au)) << 4) |
-           (gather4(eq_flags(v.z, 0x0A0A0A0Au)) << 8) | (gather4(eq_flags(v.w, 0x0A0A0A0Au)) << 12);
+// 16-bit mask (bit i = byte i) of the bytes of v equal to the byte replicated in `pat`.
+// One multiply moves a word's four flags (bits 7/15/23/31) into the top nibble of the product in
+// byte order: y * 0x204081 has flag b at bit 28 + b and nothing else up there (all partial
+// products land on distinct bits, so no carries).
+__device__ __forceinline__ unsigned eq_mask16(const uint4 v, unsigned pat) {
+    const unsigned p0 = eq_flags(v.x, pat) * 0x00204081u, p1 = eq_flags(v.y, pat) * 0x00204081u;
+    const unsigned p2 = eq_flags(v.z, pat) * 0x00204081u, p3 = eq_flags(v.w, pat) * 0x00204081u;
+    return (p0 >> 28) | ((p1 >> 24) & 0xF0u) | ((p2 >> 20) & 0xF00u) | ((p3 >> 16) & 0xF000u);
 }
+__device__ __forceinline__ unsigned newline_mask16(const uint4 v) { return eq_mask16(v, 0x0A0A0A0Au); }
 
 // Number of ' ' in buf[sb, eb) for lines that end within 112 bytes of their 16-byte-aligned start,
 // else -1.  Fully unrolled and branch-free: seven independent 16-byte shared loads in flight.
@@ -126,8 +154,7 @@ __device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsig
     for (int i = 0; i < 7; ++i) {
         const unsigned p = a0 + 16u * i;
         const uint4 v = *reinterpret_cast<const uint4*>(buf + (p < eb ? p : a0));
-        unsigned m = gather4(eq_flags(v.x, 0x20202020u)) | (gather4(eq_flags(v.y, 0x20202020u)) << 4) |
-                     (gather4(eq_flags(v.z, 0x20202020u)) << 8) | (gather4(eq_flags(v.w, 0x20202020u)) << 12);
+        unsigned m = eq_mask16(v, 0x20202020u);
         const unsigned lo_cut = sb > p ? sb - p : 0u;                  // bytes of this segment before the line
         const unsigned hi_cut = eb > p ? (eb - p < 16u ? eb - p : 16u) : 0u;  // bytes of it inside [.., eb)
         m &= (0xFFFFu << lo_cut) & ((1u << hi_cut) - 1u);
@@ -278,8 +305,6 @@ __device__ __forceinline__ bool tile_prefix(volatile unsigned long long* status,
 // Stage C depends on nothing but the tile's bytes, so every tile's count is published about one
 // tile-time before any CTA looks back over it: the look-back never waits on a chain of CTAs.
 struct TileState {
-    unsigned long long lo, hi;  // newline mask of this thread's 128 bytes
-    unsigned before;            // newlines of the tile before this thread's bytes
     unsigned total;             // newlines in the tile
     unsigned valid;             // bytes in the tile
     unsigned vnl;               // 1 if the chunk ends in this tile without a final '\n'
@@ -287,10 +312,11 @@ struct TileState {
 
 template <int NT>
 __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(const ScanArgs a) {
-    constexpr int kThreads = NT, kTile = ScanCfg<NT>::tile, kBuf = ScanCfg<NT>::buf, kHdrCap = ScanCfg<NT>::hdr_cap;
+    constexpr int kThreads = NT, kTile = ScanCfg<NT>::tile, kBuf = ScanCfg<NT>::buf, kNlCap = ScanCfg<NT>::nl_cap;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint16_t* const s_start = reinterpret_cast<uint16_t*>(smem + kStages * kBuf);
-    uint16_t* const s_end = s_start + kHdrCap;
+    // positions (buffer offsets) of the newlines of a tile, in order; two lists: the tile being parsed
+    // and the tile counted one stage ahead
+    uint16_t* const s_nl = reinterpret_cast<uint16_t*>(smem + kStages * kBuf);
     __shared__ __align__(8) unsigned long long s_bar[kStages];
     __shared__ unsigned long long s_prefix[2];
     __shared__ unsigned s_have_prefix[2];  // early look-back of the tile parsed in iteration (i & 1) succeeded
@@ -343,7 +369,7 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     unsigned parity = 0;  // bit b = phase parity of s_bar[b]
 
     // stage C: newline masks + block scan of the tile staged in buffer b, publish its count
-    auto count_stage = [&](int b, TileState& ts) {
+    auto count_stage = [&](int b, TileState& ts, unsigned lsel) {
         const unsigned t = s_tile[b];
         if (t >= a.n_tiles) return;  // uniform
         unsigned char* const buf = smem + b * kBuf;
@@ -384,7 +410,6 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
             else if (nv < 64) lo &= (1ULL << nv) - 1, hi = 0;
             else hi &= (1ULL << (nv - 64)) - 1;
         }
-        ts.lo = lo, ts.hi = hi;
         const unsigned cnt = __popcll(lo) + __popcll(hi);
         unsigned incl = cnt;
 #pragma unroll
@@ -401,11 +426,27 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
             if (w < warp) wbase += v;
             total += v;
         }
-        ts.before = wbase + incl - cnt;
         ts.total = total;
         if (tid == 0) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
         // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
         ts.vnl = (t == a.n_tiles - 1 && ts.valid > 0 && buf[kHalo + ts.valid - 1] != '\n') ? 1u : 0u;
+        {   // ordered list of newline positions; the line numbers come later, from the look-back
+            uint16_t* const nl = s_nl + lsel * kNlCap;
+            unsigned idx = wbase + incl - cnt;
+            unsigned pos0 = kHalo + tid * kPerThread;
+            unsigned long long m = lo;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                while (m) {
+                    if (idx < kNlCap) nl[idx] = static_cast<uint16_t>(pos0 + (__ffsll(static_cast<long long>(m)) - 1));
+                    m &= m - 1;
+                    ++idx;
+                }
+                m = hi;
+                pos0 += 64;
+            }
+            if (tid == 0 && ts.vnl && total < kNlCap) nl[total] = static_cast<uint16_t>(kHalo + ts.valid);
+        }
         __syncthreads();  // s_warp is reused by the next count
         tick(1);
     };
@@ -424,7 +465,7 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
     }
     __syncthreads();
     TileState cur{}, nxt{};
-    count_stage(0, cur);
+    count_stage(0, cur, 0);
     // look-back of the first tile; later tiles are looked back one iteration ahead (see stage B)
     if (warp == kThreads / 32 - 1 && lane == 0) s_have_prefix[0] = 0, s_have_prefix[1] = 0;
     __syncthreads();
@@ -478,7 +519,7 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
         tick(8);
         __syncthreads();          // s_tile[nn] visible; also orders the stages
         tick(7);
-        count_stage(n, nxt);
+        count_stage(n, nxt, (iter + 1) & 1);
 
         unsigned char* const buf = smem + c * kBuf;
         const unsigned long long tile_off = static_cast<unsigned long long>(t) * kTile;
@@ -512,72 +553,41 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
         const unsigned long long o_first = (K0 + 3) >> 2;
         const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
         const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
+        const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);  // list index of the first header end
+        const uint16_t* const nl = s_nl + (iter & 1) * kNlCap;
 
-        // Work that issues global atomics or spins on other CTAs runs once per tile at the start of the
+        // Work that issues global atomics or polls other CTAs runs once per tile at the start of the
         // longest barrier-free stretch (key extraction), so that no __syncthreads() waits for an L2
-        // round trip: last tile's table updates, the ticket for the tile after next, and the look-back
-        // of the NEXT tile (its count was published by this iteration's stage C) on the last warp, which
-        // has no headers to parse in ordinary tiles.
-        auto between_barriers = [&]() {
-            finish_pending();
-            if (tid == 0) claim_next();
-            if (warp == kThreads / 32 - 1) {
-                unsigned long long excl = 0;
-                const bool ok = s_tile[n] < a.n_tiles && tile_prefix<false>(status, s_tile[n], nxt.total, lane, &excl);
-                if (lane == 0) s_prefix[(iter + 1) & 1] = excl, s_have_prefix[(iter + 1) & 1] = ok ? 1u : 0u;
+        // round trip: last tile's table updates, the ticket for the tile after next, and a non-blocking
+        // look-back attempt for the NEXT tile (its count was published by this iteration's stage C) on
+        // the last warp, which has no headers to parse in ordinary tiles.
+        finish_pending();
+        if (tid == 0) claim_next();
+        if (warp == kThreads / 32 - 1) {
+            unsigned long long excl = 0;
+            const bool ok = s_tile[n] < a.n_tiles && tile_prefix<false>(status, s_tile[n], nxt.total, lane, &excl);
+            if (lane == 0) s_prefix[(iter + 1) & 1] = excl, s_have_prefix[(iter + 1) & 1] = ok ? 1u : 0u;
+        }
+
+        // ---- stage B: one thread per header line owned by the tile ---------------------------------
+        // header h ends at list entry j0 + 4h and starts right after entry j0 + 4h - 1 (or in the halo)
+        auto emit = [&](unsigned long long o, unsigned long long key, unsigned long long start_g) {
+            const unsigned long long slot = o - chunk_first_read;
+            if (slot < a.out_cap) {
+                if (a.keys_out) a.keys_out[slot] = key;
+                if (a.rec_off_out) a.rec_off_out[slot] = start_g;
             }
         };
-        if (n_owned == 0) between_barriers();
-
-        // ---- stage B -----------------------------------------------------------------------------
-        for (unsigned hbase = 0; hbase < n_owned; hbase += kHdrCap) {
-            {   // line numbers -> header [start, end) positions
-                unsigned long long k = K0 + cur.before;
-                const unsigned long long obase = o_first + hbase;
-                unsigned long long m = cur.lo;
-                unsigned pos0 = kHalo + tid * kPerThread;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    while (m) {
-                        const unsigned p = pos0 + (__ffsll(static_cast<long long>(m)) - 1);
-                        m &= m - 1;
-                        const unsigned r = static_cast<unsigned>(k) & 3u;
-                        if (r == 0) {  // newline 4o ends header line 4o
-                            const unsigned long long rel = (k >> 2) - obase;
-                            if (rel < kHdrCap) s_end[rel] = static_cast<uint16_t>(p);
-                        } else if (r == 3) {  // newline 4o-1: header line 4o starts right after
-                            const unsigned long long rel = ((k + 1) >> 2) - obase;
-                            if (rel < kHdrCap) s_start[rel] = static_cast<uint16_t>(p + 1);
-                        }
-                        ++k;
-                    }
-                    m = cur.hi;
-                    pos0 += 64;
-                }
-                if (tid == 0) {
-                    if (hbase == 0 && (K0 & 3) == 0) s_start[0] = static_cast<uint16_t>(s_halo_start);
-                    if (vnl) {
-                        const unsigned long long kv = K0 + total;
-                        const unsigned long long rel = (kv >> 2) - obase;
-                        if ((kv & 3) == 0 && rel < kHdrCap) s_end[rel] = static_cast<uint16_t>(kHalo + valid);
-                    }
-                }
-            }
-            __syncthreads();
-            tick(3);
-
-            if (hbase == 0) between_barriers();
-            else finish_pending();
-
-            // key extraction, warp-aggregated count
-            const unsigned npass = (n_owned - hbase < kHdrCap) ? (n_owned - hbase) : kHdrCap;
-            for (unsigned h0 = 0; h0 < npass; h0 += kThreads) {
+        if (total + vnl <= static_cast<unsigned>(kNlCap)) {
+            for (unsigned h0 = 0; h0 < n_owned; h0 += kThreads) {
                 const unsigned h = h0 + tid;
-                const unsigned long long o = o_first + hbase + h;
-                bool have = (h < npass) && (o < a.read_limit) && !(a.dbg_flags & 4);
+                const unsigned long long o = o_first + h;
+                bool have = (h < n_owned) && (o < a.read_limit) && !(a.dbg_flags & 4);
                 unsigned long long key = 0, start_g = 0;
                 if (have) {
-                    const int rc = parse_header(buf, s_lut, s_start[h], s_end[h], a, tile_off, &key, &start_g);
+                    const unsigned j = j0 + 4 * h;
+                    const unsigned sb = j ? nl[j - 1] + 1u : s_halo_start;
+                    const int rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
                     if (rc) {
                         raise_error(a.st, rc, o);
                         have = false;
@@ -588,21 +598,36 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
                 if (h0) finish_pending();  // more than one header per thread: make room for the next key
                 if (have) {
                     const unsigned same = __match_any_sync(grp, key);
-                    if (a.table && !(a.dbg_flags & 8) && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
+                    if (a.table && !(a.dbg_flags & 8) && lane == __ffs(same) - 1) {  // lowest lane = lowest ordinal
                         p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
                         p_slot = hash64(key) & a.table_mask;
                         p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
                     }
-                    const unsigned long long slot = o - chunk_first_read;
-                    if (slot < a.out_cap) {
-                        if (a.keys_out) a.keys_out[slot] = key;
-                        if (a.rec_off_out) a.rec_off_out[slot] = start_g;
-                    }
+                    emit(o, key, start_g);
                 }
             }
-            __syncthreads();
-            tick(5);
+        } else if (tid == 0) {
+            // More newlines than the list holds (lines shorter than 16 bytes on average): exact but serial.
+            unsigned long long k = K0;
+            unsigned prev = s_halo_start;
+            for (unsigned p = 0; p <= valid; ++p) {
+                const bool is_end = (p < valid) ? (buf[kHalo + p] == '\n') : (vnl != 0);
+                if (!is_end) continue;
+                if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
+                    unsigned long long key = 0, start_g = 0;
+                    const int rc = parse_header(buf, s_lut, prev, kHalo + p, a, tile_off, &key, &start_g);
+                    if (rc) raise_error(a.st, rc, k >> 2);
+                    else {
+                        if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
+                        emit(k >> 2, key, start_g);
+                    }
+                }
+                prev = kHalo + p + 1;
+                ++k;
+            }
         }
+        __syncthreads();
+        tick(5);
 
         if (tid == 0) {
             const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;

@@ -1,0 +1,366 @@
+// Warp-specialised form of the scan kernel (hot path A).  Same arithmetic, same results and the
+// same helpers as scan_kernel.cuh; the difference is the schedule inside a CTA.
+//
+//   warps 0-3  COUNTERS  for tile i: wait for its bytes (TMA mbarrier), 256 bytes per thread ->
+//                        newline mask, group scan, ordered newline-position list in shared memory,
+//                        publish the tile's newline count, signal `counted[stage]`.
+//                        Thread 0 also draws tile tickets and starts the bulk copy of tile i+2 as
+//                        soon as the parsers have released that stage.
+//   warps 4-7  PARSERS   for tile i: wait `counted[stage]`, look-back over the published counts
+//                        (line number of the tile's first newline), one thread per header line:
+//                        key extraction, warp fold, deferred table update; signal `free[stage]`.
+//
+// The two groups only meet through shared-memory mbarriers (full -> counted -> free per stage) and
+// synchronise internally with named barriers, so counting tile i+1 overlaps parsing tile i and a
+// parser that waits on another CTA's count never stops its own CTA's counters.
+#pragma once
+#include "scan_kernel.cuh"
+
+namespace frb {
+
+constexpr int kWsThreads = 256;
+constexpr int kWsGroup = 128;                 // threads per role
+constexpr int kWsTile = 32768;
+constexpr int kWsBuf = kWsTile + kHalo;
+constexpr int kWsNlCap = 2048;
+constexpr int kWsPerThread = kWsTile / kWsGroup;  // 256 bytes per counter thread
+constexpr int kWsSmem = kStages * kWsBuf + kStages * kWsNlCap * (int)sizeof(uint16_t);
+constexpr unsigned kNoTile = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void group_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kWsGroup) : "memory");
+}
+
+__global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint16_t* const s_nl = reinterpret_cast<uint16_t*>(smem + kStages * kWsBuf);
+    __shared__ __align__(8) unsigned long long s_full[kStages], s_counted[kStages];
+    __shared__ unsigned s_tile[kStages], s_total[kStages], s_valid[kStages], s_vnl[kStages];
+    __shared__ unsigned s_cwarp[kWsGroup / 32];
+    __shared__ unsigned long long s_prefix[2];
+    __shared__ unsigned s_have_prefix[2];
+    __shared__ unsigned s_halo_start;
+    __shared__ unsigned char s_lut[256];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long L0 =
+        a.use_carry ? *reinterpret_cast<volatile unsigned long long*>(&a.st->line_carry) : a.line_base;
+    const unsigned long long chunk_first_read = (L0 + 3) >> 2;
+    volatile unsigned long long* status = a.status + 1;
+
+    s_lut[tid] = static_cast<unsigned char>(enc_read(tid));
+    if (tid == 0) {
+        s_have_prefix[0] = 0, s_have_prefix[1] = 0;
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_counted[i], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < kWsGroup / 32) {
+        // =============================== COUNTERS ================================================
+        const int ct = tid;
+        unsigned full_parity = 0;  // bit s
+        long long tm = (a.timing && ct == 0) ? clock64() : 0;
+        unsigned long long t_wait = 0, t_work = 0;
+        for (unsigned i = 0;; ++i) {
+            const int s = i % kStages;
+            mbar_wait(&s_full[s], (full_parity >> s) & 1u);
+            full_parity ^= 1u << s;
+            if (a.timing && ct == 0) { const long long now = clock64(); t_wait += now - tm; tm = now; }
+            const unsigned t = s_tile[s];
+            if (t == kNoTile) {
+                if (ct == 0) mbar_arrive(&s_counted[s]);
+                break;
+            }
+            unsigned char* const buf = smem + s * kWsBuf;
+            const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
+            const unsigned long long left = a.nbytes - tile_off;
+            const unsigned valid = static_cast<unsigned>(left < kWsTile ? left : kWsTile);
+            {   // bytes past the last 16-byte multiple of the bulk copy (final tile only)
+                const unsigned halo = t ? kHalo : 0;
+                const unsigned avail = valid + halo, bulk = avail & ~15u;
+                if (avail != bulk) {
+                    if (ct < static_cast<int>(avail - bulk))
+                        buf[(kHalo - halo) + bulk + ct] = a.data[tile_off - halo + bulk + ct];
+                    group_sync(1);
+                }
+            }
+            // newline mask of this thread's 256 bytes: m[h][0/1] = bytes 128h + 0..63 / 64..127
+            unsigned long long m00 = 0, m01 = 0, m10 = 0, m11 = 0;
+            const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * (kWsPerThread / 16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = (j + ct) & 7;  // rotate so a quarter-warp hits 8 distinct bank groups
+                const unsigned long long ma = newline_mask16(t4[r]);
+                const unsigned long long mb = newline_mask16(t4[8 + r]);
+                const int sh = (r & 3) * 16;
+                if (r < 4) m00 |= ma << sh, m10 |= mb << sh;
+                else m01 |= ma << sh, m11 |= mb << sh;
+            }
+            {
+                const int nv = static_cast<int>(valid) - ct * kWsPerThread;
+                if (nv < kWsPerThread) {
+                    auto keep = [](unsigned long long m, int n) -> unsigned long long {
+                        return n <= 0 ? 0ULL : (n >= 64 ? m : (m & ((1ULL << n) - 1)));
+                    };
+                    m00 = keep(m00, nv), m01 = keep(m01, nv - 64), m10 = keep(m10, nv - 128), m11 = keep(m11, nv - 192);
+                }
+            }
+            const unsigned cnt = __popcll(m00) + __popcll(m01) + __popcll(m10) + __popcll(m11);
+            unsigned incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += n;
+            }
+            if (lane == 31) s_cwarp[warp] = incl;
+            group_sync(1);
+            unsigned wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kWsGroup / 32; ++w) {
+                const unsigned v = s_cwarp[w];
+                if (w < warp) wbase += v;
+                total += v;
+            }
+            // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
+            const unsigned vnl = (t == a.n_tiles - 1 && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
+            {   // ordered list of newline positions; line numbers come later, from the look-back
+                uint16_t* const nl = s_nl + s * kWsNlCap;
+                unsigned idx = wbase + incl - cnt;
+                unsigned pos0 = kHalo + ct * kWsPerThread;
+                const unsigned long long ms[4] = {m00, m01, m10, m11};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned long long m = ms[q];
+                    while (m) {
+                        if (idx < kWsNlCap) nl[idx] = static_cast<uint16_t>(pos0 + (__ffsll(static_cast<long long>(m)) - 1));
+                        m &= m - 1;
+                        ++idx;
+                    }
+                    pos0 += 64;
+                }
+                if (ct == 0 && vnl && total < kWsNlCap) nl[total] = static_cast<uint16_t>(kHalo + valid);
+            }
+            if (ct == 0) {
+                s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
+                status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
+            }
+            group_sync(1);  // list + meta complete (also protects s_cwarp)
+            if (ct == 0) mbar_arrive(&s_counted[s]);
+            if (a.timing && ct == 0) { const long long now = clock64(); t_work += now - tm; tm = now; }
+        }
+        if (a.timing && ct == 0) atomicAdd(&a.timing[0], t_wait), atomicAdd(&a.timing[1], t_work);
+    } else {
+        // =============================== PARSERS =================================================
+        const int pt = tid - kWsGroup;
+        const int pwarp = warp - kWsGroup / 32;
+        // deferred table update, three steps (see scan_kernel.cuh)
+        unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
+        unsigned p_cnt = 0;
+        unsigned long long q_key = 0, q_pos = 0, q_slot = 0, q_old = 0;
+        unsigned q_cnt = 0;
+        auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
+            atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
+            atomicMin(&a.table[slot].first, pos);
+        };
+        auto finish_pending = [&]() {
+            if (q_cnt) {
+                if (q_old == kEmpty) {
+                    atomicAdd(&a.st->occupied, 1ULL);
+                    bump(q_slot, q_cnt, q_pos);
+                } else if (q_old == q_key) {
+                    bump(q_slot, q_cnt, q_pos);
+                } else {
+                    table_add(a.table, a.table_mask, q_key, q_cnt, q_pos, &a.st->occupied, a.st);
+                }
+                q_cnt = 0;
+            }
+            if (p_cnt) {
+                if (p_seen == p_key) {
+                    bump(p_slot, p_cnt, p_pos);
+                } else if (p_seen == kEmpty) {
+                    q_key = p_key, q_pos = p_pos, q_slot = p_slot, q_cnt = p_cnt;
+                    q_old = atomicCAS(&a.table[p_slot].key, kEmpty, p_key);
+                } else {
+                    table_add(a.table, a.table_mask, p_key, p_cnt, p_pos, &a.st->occupied, a.st);
+                }
+                p_cnt = 0;
+            }
+        };
+        auto emit = [&](unsigned long long o, unsigned long long key, unsigned long long start_g) {
+            const unsigned long long slot = o - chunk_first_read;
+            if (slot < a.out_cap) {
+                if (a.keys_out) a.keys_out[slot] = key;
+                if (a.rec_off_out) a.rec_off_out[slot] = start_g;
+            }
+        };
+        // Tickets and bulk copies are driven by parser thread 0: a stage is refilled the moment the
+        // parsers are done with it, and the ticket for it was drawn one tile earlier.  The counters never
+        // wait for anything but bytes.
+        unsigned claimed = 0;
+        auto claim_next = [&]() { claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL)); };
+        auto issue = [&](int s) {  // ticket -> stage s, start its bulk copy
+            const unsigned t = claimed < a.n_tiles ? claimed : kNoTile;
+            s_tile[s] = t;
+            if (t == kNoTile) {
+                mbar_arrive(&s_full[s]);
+                return;
+            }
+            const unsigned long long off = static_cast<unsigned long long>(t) * kWsTile;
+            const unsigned halo = t ? kHalo : 0;
+            const unsigned long long left = a.nbytes - off;
+            const unsigned avail = static_cast<unsigned>(left < kWsTile ? left : kWsTile) + halo;
+            const unsigned bulk = avail & ~15u;
+            if (bulk) {
+                mbar_expect_tx(&s_full[s], bulk);
+                bulk_g2s(smem + s * kWsBuf + (kHalo - halo), a.data + off - halo, bulk, &s_full[s]);
+            } else {
+                mbar_arrive(&s_full[s]);
+            }
+        };
+        if (pt == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                claim_next();
+                issue(s);
+            }
+            claim_next();
+        }
+        unsigned counted_parity = 0;
+        unsigned long long my_reads = 0;
+        long long tm = (a.timing && pt == 0) ? clock64() : 0;
+        unsigned long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        auto tick = [&](int k) {
+            if (a.timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
+        };
+        for (unsigned i = 0;; ++i) {
+            const int s = i % kStages;
+            mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
+            counted_parity ^= 1u << s;
+            tick(0);
+            const unsigned t = s_tile[s];
+            if (t == kNoTile) break;
+            unsigned char* const buf = smem + s * kWsBuf;
+            const unsigned total = s_total[s], valid = s_valid[s], vnl = s_vnl[s];
+            const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
+            const uint16_t* const nl = s_nl + s * kWsNlCap;
+
+            if (pwarp == 0) {
+                if (!s_have_prefix[i & 1]) {  // the early attempt of the previous tile did not complete
+                    unsigned long long excl;
+                    tile_prefix<true>(status, t, total, lane, &excl);
+                    if (lane == 0) s_prefix[i & 1] = excl;
+                }
+            } else if (pwarp == kWsGroup / 32 - 1) {
+                if (t == 0) {
+                    if (lane == 0) s_halo_start = kHalo;
+                } else {
+                    const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane]);
+                    const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+                    if (any == 0) {
+                        if (lane == 0) s_halo_start = kUnknown;
+                    } else if (lane == 31 - __clz(any)) {
+                        s_halo_start = lane * 16 + (31 - __clz(m)) + 1;
+                    }
+                }
+            }
+            group_sync(2);
+            tick(1);
+            const unsigned long long K0 = L0 + s_prefix[i & 1];
+            const unsigned halo_start = s_halo_start;
+            // Look-back of the NEXT tile in the shadow of this tile's key extraction: only if its count
+            // is already in (non-blocking probe) and without ever waiting on another CTA.
+            if (pwarp == kWsGroup / 32 - 1) {
+                const int sn = (i + 1) % kStages;
+                unsigned long long excl = 0;
+                bool ok = false;
+                if (mbar_test(&s_counted[sn], (counted_parity >> sn) & 1u)) {
+                    const unsigned tn = s_tile[sn];
+                    ok = tn != kNoTile && tile_prefix<false>(status, tn, s_total[sn], lane, &excl);
+                }
+                if (lane == 0) s_prefix[(i + 1) & 1] = excl, s_have_prefix[(i + 1) & 1] = ok ? 1u : 0u;
+            }
+            const unsigned long long o_first = (K0 + 3) >> 2;
+            const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
+            const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
+            const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
+
+            tick(4);
+            finish_pending();  // issued far from the next barrier: its atomics never stall one
+            tick(5);
+            if (total + vnl <= static_cast<unsigned>(kWsNlCap)) {
+                for (unsigned h0 = 0; h0 < n_owned; h0 += kWsGroup) {
+                    const unsigned h = h0 + pt;
+                    const unsigned long long o = o_first + h;
+                    bool have = (h < n_owned) && (o < a.read_limit);
+                    unsigned long long key = 0, start_g = 0;
+                    if (have) {
+                        const unsigned j = j0 + 4 * h;
+                        const unsigned sb = j ? nl[j - 1] + 1u : halo_start;
+                        const int rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
+                        if (rc) {
+                            raise_error(a.st, rc, o);
+                            have = false;
+                        }
+                    }
+                    const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
+                    tick(6);
+                    if (h0) finish_pending();
+                    if (have) {
+                        const unsigned same = __match_any_sync(grp, key);
+                        if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
+                            p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
+                            p_slot = hash64(key) & a.table_mask;
+                            p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
+                        }
+                        emit(o, key, start_g);
+                    }
+                }
+            } else if (pt == 0) {
+                // more newlines than the list holds (lines < 16 bytes on average): exact but serial
+                unsigned long long k = K0;
+                unsigned prev = halo_start;
+                for (unsigned p = 0; p <= valid; ++p) {
+                    const bool is_end = (p < valid) ? (buf[kHalo + p] == '\n') : (vnl != 0);
+                    if (!is_end) continue;
+                    if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
+                        unsigned long long key = 0, start_g = 0;
+                        const int rc = parse_header(buf, s_lut, prev, kHalo + p, a, tile_off, &key, &start_g);
+                        if (rc) raise_error(a.st, rc, k >> 2);
+                        else {
+                            if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
+                            emit(k >> 2, key, start_g);
+                        }
+                    }
+                    prev = kHalo + p + 1;
+                    ++k;
+                }
+            }
+            tick(7);
+            group_sync(2);  // everyone is done reading stage s
+            tick(2);
+            if (pt == 0) {
+                issue(s);      // the stage is free: refill it with the ticket drawn one tile ago
+                claim_next();  // consumed one tile from now; the next barrier is a whole tile away
+                const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
+                if (c_hi > o_first) my_reads += c_hi - o_first;
+                if (t == a.n_tiles - 1) a.st->line_carry = K0 + total + vnl;
+                tp[3] += 1;
+            }
+        }
+        if (a.timing && pt == 0) {
+            atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[3], tp[1]), atomicAdd(&a.timing[4], tp[2]);
+            atomicAdd(&a.timing[5], tp[4]), atomicAdd(&a.timing[6], tp[5]), atomicAdd(&a.timing[7], tp[6]);
+            atomicAdd(&a.timing[8], tp[7]);
+            atomicAdd(&a.timing[9], tp[3]);
+        }
+        finish_pending();
+        finish_pending();
+        if (pt == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
+    }
+}
+
+}  // namespace frb

@@ -150,3 +150,21 @@ def test_keys_per_read_and_offsets(ctx):
     assert unpack_keys(keys) == synth.keys_of(spec, 0, n)
     starts = np.flatnonzero(arr == 10)[3::4][:-1] + 1
     assert offs[0] == 0 and (offs[1:] == starts).all()
+
+
+def test_short_lines_serial_fallback(ctx):
+    """Records so short that a tile holds more newlines than the kernel's position list: the exact
+    serial fallback must give the oracle's tally (and per-read keys) too."""
+    import random
+
+    import frender_oracle as O
+    rnd = random.Random(7)
+    keys = ["".join(rnd.choice("ACGTN") for _ in range(2)) + "+" + "".join(rnd.choice("ACGT") for _ in range(2))
+            for _ in range(40)]
+    recs = "".join(f"@r 1:N:0:{rnd.choice(keys)}\nA\n+\nF\n" for _ in range(20000))
+    want, visited = O.tally_text(recs.splitlines(keepends=True))
+    for chunk in (None, 50_000):
+        ctx.reset()
+        reads, uniq = ctx.scan_bytes(recs.encode(), chunk=chunk)
+        assert reads == visited == 20000 and uniq == len(want)
+        assert list(ctx.counter()["total"].items()) == list(want.items())
