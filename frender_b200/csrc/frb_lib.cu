@@ -67,6 +67,8 @@ struct frb_ctx {
     std::vector<KeyList> files;
     KeyList total;
     bool total_ready = false, in_file = false;
+    size_t merged_upto = 0;        // file lists already folded into total_tab
+    bool total_tab_clean = true;   // total_tab holds no keys
     uint32_t cur_ordinal = 0;
     uint64_t cur_limit = ~0ULL;
     // sheet
@@ -78,7 +80,13 @@ struct frb_ctx {
     // matcher outputs (device, grown on demand)
     int *m1 = nullptr, *m2 = nullptr, *srow = nullptr, *m2rc = nullptr, *srowrc = nullptr;
     unsigned char *type = nullptr, *typerc = nullptr;
+    unsigned* work = nullptr;             // keys with an idx1 match (matcher work list)
+    unsigned long long* work_n = nullptr;
     uint64_t match_cap = 0;
+    uint64_t total_gen = 0, sheet_gen = 0;            // bumped whenever the total list / sheet changes
+    uint64_t m1_total_gen = ~0ULL, m1_sheet_gen = ~0ULL;  // what c->m1 currently describes
+    uint32_t m1_n_subs = ~0u;
+    bool m1_from_rc = false;                              // ... and it came from an rc_mode pass
     // temp for sort
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
@@ -452,7 +460,7 @@ void frb_destroy(frb_ctx* c) {
     cudaFree(c->sheet_fwd), cudaFree(c->sheet_rc), cudaFree(c->sheet_group), cudaFree(c->sheet_use_rc);
     cudaFree(c->f_sum), cudaFree(c->rc_sum);
     cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
-    cudaFree(c->type), cudaFree(c->typerc), cudaFree(c->cub_tmp), cudaFree(c->route_tab);
+    cudaFree(c->type), cudaFree(c->typerc), cudaFree(c->work), cudaFree(c->work_n), cudaFree(c->cub_tmp), cudaFree(c->route_tab);
     route_free(c->rb);
     cudaFree(c->synth_i7), cudaFree(c->synth_i5), cudaFree(c->synth_cdf), cudaFree(c->synth_len), cudaFree(c->synth_off);
     for (auto& p : c->prof_pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
@@ -599,14 +607,6 @@ int frb_scan_end(frb_ctx* c, uint64_t* n_reads, uint64_t* n_unique) {
     fl.reads = c->st_host->n_reads;
     fl.ordinal = c->cur_ordinal;
     TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl));
-    if (fl.n) {  // fold into "total" (F:199-203); first = (file ordinal, read ordinal)
-        ProfScope ps(c, FRB_K_EXPORT);
-        merge_list_kernel<<<static_cast<unsigned>((fl.n + 255) / 256), 256, 0, c->compute>>>(
-            c->total_tab, c->cap - 1, fl.keys, fl.counts, fl.first, fl.n,
-            static_cast<unsigned long long>(fl.ordinal) << 40, &c->st->occupied_total, c->st);
-        c->launches++;
-        CU(c, cudaGetLastError());
-    }
     c->files.push_back(fl);
     c->total_ready = false;
     if (n_reads) *n_reads = fl.reads;
@@ -640,15 +640,51 @@ int frb_file_export(frb_ctx* c, uint32_t i, uint64_t* keys, uint64_t* counts, ui
     return export_list(c, c->files[i], keys, counts, first_read, cap);
 }
 
+static int merge_pending_files(frb_ctx* c) {  // fold file lists into total_tab (F:199-203)
+    for (; c->merged_upto < c->files.size(); ++c->merged_upto) {
+        const KeyList& fl = c->files[c->merged_upto];
+        if (!fl.n) continue;
+        ProfScope ps(c, FRB_K_EXPORT);
+        merge_list_kernel<<<static_cast<unsigned>((fl.n + 255) / 256), 256, 0, c->compute>>>(
+            c->total_tab, c->cap - 1, fl.keys, fl.counts, fl.first, fl.n,
+            static_cast<unsigned long long>(fl.ordinal) << 40, &c->st->occupied_total, c->st);
+        c->launches++;
+        c->total_tab_clean = false;
+        CU(c, cudaGetLastError());
+    }
+    return FRB_OK;
+}
+
 int frb_total_finish(frb_ctx* c, uint64_t* n_unique) {
     CU(c, cudaSetDevice(c->device));
     if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_total_finish: a file is still open");
     if (!c->total_ready) {
-        CU(c, cudaStreamSynchronize(c->compute));
-        TRY(device_error_check(c));
         TRY(free_list(c, c->total));
-        TRY(table_to_sorted_list(c, c->total_tab, c->st_host->occupied_total, &c->total));
+        if (c->files.size() == 1 && c->merged_upto == 0) {
+            // one file: "total" is that file's list (F:199-203 degenerates to a copy); only `first`
+            // gets the file ordinal in its high bits
+            const KeyList& fl = c->files[0];
+            c->total.n = fl.n;
+            if (fl.n) {
+                TRY(dmalloc(c, &c->total.keys, fl.n * 8));
+                TRY(dmalloc(c, &c->total.counts, fl.n * 8));
+                TRY(dmalloc(c, &c->total.first, fl.n * 8));
+                ProfScope ps(c, FRB_K_EXPORT);
+                CU(c, cudaMemcpyAsync(c->total.keys, fl.keys, fl.n * 8, cudaMemcpyDeviceToDevice, c->compute));
+                CU(c, cudaMemcpyAsync(c->total.counts, fl.counts, fl.n * 8, cudaMemcpyDeviceToDevice, c->compute));
+                add_offset_kernel<<<static_cast<unsigned>((fl.n + 255) / 256), 256, 0, c->compute>>>(
+                    fl.first, c->total.first, fl.n, static_cast<unsigned long long>(fl.ordinal) << 40);
+                c->launches++;
+                CU(c, cudaGetLastError());
+            }
+        } else {
+            TRY(merge_pending_files(c));
+            CU(c, cudaStreamSynchronize(c->compute));
+            TRY(device_error_check(c));
+            TRY(table_to_sorted_list(c, c->total_tab, c->st_host->occupied_total, &c->total));
+        }
         c->total_ready = true;
+        c->total_gen++;
     }
     if (n_unique) *n_unique = c->total.n;
     return FRB_OK;
@@ -671,6 +707,7 @@ int frb_total_load(frb_ctx* c, const uint64_t* keys, const uint64_t* counts, uin
         CU(c, cudaStreamSynchronize(c->compute));
     }
     c->total_ready = true;
+    c->total_gen++;
     return FRB_OK;
 }
 int frb_reset(frb_ctx* c) {
@@ -682,7 +719,11 @@ int frb_reset(frb_ctx* c) {
     c->total_ready = false;
     c->in_file = false;
     CU(c, cudaMemsetAsync(c->st, 0, sizeof(DevState), c->compute));
-    TRY(clear_table(c, c->total_tab));
+    c->merged_upto = 0;
+    if (!c->total_tab_clean) {
+        TRY(clear_table(c, c->total_tab));
+        c->total_tab_clean = true;
+    }
     return FRB_OK;
 }
 
@@ -864,6 +905,7 @@ int frb_sheet_load(frb_ctx* c, const uint64_t* fwd, const uint64_t* rc, const in
         CU(c, cudaMemcpy(c->sheet_group, group, n_rows * 4, cudaMemcpyHostToDevice));
     }
     c->rows = n_rows, c->l1 = l1, c->l2 = l2;
+    c->sheet_gen++;
     return FRB_OK;
 }
 
@@ -878,7 +920,7 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
     if (n > c->match_cap) {
         CU(c, cudaStreamSynchronize(c->compute));
         cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
-        cudaFree(c->type), cudaFree(c->typerc);
+        cudaFree(c->type), cudaFree(c->typerc), cudaFree(c->work), cudaFree(c->work_n);
         c->match_cap = 0;
         CU(c, cudaMalloc(&c->m1, n * 4));
         CU(c, cudaMalloc(&c->m2, n * 4));
@@ -887,7 +929,10 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
         CU(c, cudaMalloc(&c->srowrc, n * 4));
         CU(c, cudaMalloc(&c->type, n));
         CU(c, cudaMalloc(&c->typerc, n));
+        CU(c, cudaMalloc(&c->work, n * 4));
+        CU(c, cudaMalloc(&c->work_n, 8));
         c->match_cap = n;
+        c->m1_total_gen = ~0ULL;
     }
     const size_t rows1 = std::max<uint32_t>(c->rows, 1);
     if (use_rc_rows && c->rows)
@@ -903,8 +948,26 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
         a.m1 = c->m1, a.m2 = c->m2, a.srow = c->srow, a.type = c->type;
         a.m2rc = c->m2rc, a.srowrc = c->srowrc, a.typerc = c->typerc;
         a.f_sum = c->f_sum, a.rc_sum = c->rc_sum, a.st = c->st;
-        const size_t smem = static_cast<size_t>(c->rows) * (4 * 8 + 4) + 16;
+        a.work = c->work, a.work_n = c->work_n;
+        // An rc pass tried both orientations of every row, so its idx1 verdicts (and its work list) carry
+        // over to any per-row choice of orientation over the same keys / sheet / n (F:618-630).
+        const bool reuse = !rc_mode && c->m1_from_rc && c->m1_total_gen == c->total_gen &&
+                           c->m1_sheet_gen == c->sheet_gen && c->m1_n_subs == n_subs;
+        c->m1_total_gen = c->total_gen, c->m1_sheet_gen = c->sheet_gen, c->m1_n_subs = n_subs;
+        c->m1_from_rc = rc_mode != 0;
         ProfScope ps(c, FRB_K_MATCH);
+        if (!reuse) {
+            CU(c, cudaMemsetAsync(c->work_n, 0, 8, c->compute));
+            match_idx1_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads,
+                                static_cast<size_t>(c->rows) * 8 + 16, c->compute>>>(a);
+            c->launches++;
+        } else {
+            // keys off the work list stay undetermined; m1 is already -1 for them
+            CU(c, cudaMemsetAsync(c->m2, 0xFF, n * 4, c->compute));
+            CU(c, cudaMemsetAsync(c->srow, 0xFF, n * 4, c->compute));
+            CU(c, cudaMemsetAsync(c->type, 0, n, c->compute));
+        }
+        const size_t smem = static_cast<size_t>(c->rows) * (4 * 8 + 4) + 16;
         match_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads, smem, c->compute>>>(a);
         c->launches++;
         CU(c, cudaGetLastError());

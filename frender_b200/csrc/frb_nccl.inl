@@ -113,6 +113,8 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
     NC(c, api, api->AllGather(send, recv, 3 * mx, ncclUint64, comm, c->compute));
     CU(c, cudaMemsetAsync(&c->st->occupied_total, 0, 8, c->compute));
     TRY(clear_table(c, c->total_tab));
+    c->total_tab_clean = false;
+    c->merged_upto = c->files.size();
     for (int r = 0; r < R; ++r) {
         if (!sizes[r]) continue;
         const unsigned long long* base = recv + 3ULL * r * mx;
@@ -125,8 +127,15 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
     TRY(dfree(c, send));
     TRY(dfree(c, recv));
     TRY(dfree(c, d_sizes));
-    c->total_ready = false;
-    return frb_total_finish(c, n_unique);
+    // the merged table replaces the local one: rebuild the sorted list from it
+    CU(c, cudaStreamSynchronize(c->compute));
+    TRY(device_error_check(c));
+    TRY(free_list(c, c->total));
+    TRY(table_to_sorted_list(c, c->total_tab, c->st_host->occupied_total, &c->total));
+    c->total_ready = true;
+    c->total_gen++;
+    if (n_unique) *n_unique = c->total.n;
+    return FRB_OK;
 }
 
 }  // extern "C"

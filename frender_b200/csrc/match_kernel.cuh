@@ -27,6 +27,8 @@ struct MatchArgs {
     int *m1, *m2, *srow, *m2rc, *srowrc;  // per-key outputs (device, may be null)
     unsigned char *type, *typerc;
     unsigned long long *f_sum, *rc_sum;   // [rows] per group (rc_mode only)
+    unsigned* work;                       // [n] indices of the keys with an idx1 match
+    unsigned long long* work_n;           // entries in work[]
     DevState* st;
 };
 
@@ -46,6 +48,74 @@ __device__ __forceinline__ void classify_one(int first1, int first2, unsigned bo
     }
 }
 
+// ---- kernel 1: idx1 sweep over ALL unique keys, fully convergent --------------------------------
+// A key whose idx1 matches no row is undetermined whatever its idx2 does (F:259, F:280-284) -- the fate
+// of almost every unique key of a real lane (random index pairs dominate the unique set).  Those keys
+// are finished here; the others go to a compact work list so that the expensive idx2 / reverse-
+// complement sweep (kernel 2) runs with full warps instead of a few live lanes per warp.
+__global__ void __launch_bounds__(kMatchThreads) match_idx1_kernel(const MatchArgs a) {
+    extern __shared__ __align__(16) unsigned char msmem[];
+    unsigned long long* s_a = reinterpret_cast<unsigned long long*>(msmem);
+    for (unsigned r = threadIdx.x; r < a.rows; r += blockDim.x) s_a[r] = a.sheet_fwd[r];
+    __syncthreads();
+    const unsigned long long B1 = ((1ULL << (3 * a.l1)) - 1) & kFoldLsb;
+    const unsigned n_subs = a.n_subs;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    const unsigned long long n_up = (a.n + 31) & ~31ULL;
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n_up;
+         i += stride) {
+        int first1 = -1;
+        if (i < a.n) {
+            const unsigned long long key = a.keys[i];
+            // shape check: idx1 of l1 symbols in 1..5, then '+' and idx2 of l2 symbols in 1..5, then end
+            // or another '+' (extra parts ignored, F:306); single index: l1 symbols then end.
+            if (a.rows) {
+                bool ok = true;
+                const unsigned total = a.l2 ? a.l1 + 1 + a.l2 : a.l1;
+                for (unsigned s = 0; s < total; ++s) {
+                    const unsigned sym = static_cast<unsigned>(key >> (3 * s)) & 7u;
+                    if (a.l2 && s == a.l1) ok &= (sym == 6);
+                    else ok &= (sym >= 1 && sym <= 5);
+                }
+                if (total < kMaxSyms) {
+                    const unsigned nxt = static_cast<unsigned>(key >> (3 * total)) & 7u;
+                    ok &= a.l2 ? (nxt == 0 || nxt == 6) : (nxt == 0);
+                }
+                if (!ok) raise_error(a.st, FRB_ERR_BAD_LENGTH, key);
+            }
+            if (a.l1 <= 10) {  // idx1 fits 30 bits: 32-bit compare, one LOP3 folds the three bit planes
+                const unsigned m = (1u << (3 * a.l1)) - 1u;
+                const unsigned k1 = static_cast<unsigned>(key) & m, b1 = static_cast<unsigned>(B1);
+                for (unsigned r = 0; r < a.rows; ++r) {
+                    const unsigned d = k1 ^ (static_cast<unsigned>(s_a[r]) & m);
+                    const bool h1 = static_cast<unsigned>(__popc((d | (d >> 1) | (d >> 2)) & b1)) <= n_subs;
+                    if (h1 && first1 < 0) first1 = r;
+                }
+            } else {
+                for (unsigned r = 0; r < a.rows; ++r) {
+                    const bool h1 = static_cast<unsigned>(__popcll(fold3(key ^ s_a[r]) & B1)) <= n_subs;
+                    if (h1 && first1 < 0) first1 = r;
+                }
+            }
+            a.m1[i] = first1;
+            if (first1 < 0) {
+                a.m2[i] = -1, a.srow[i] = -1, a.type[i] = FRB_TYPE_UNDETERMINED;
+                if (a.rc_mode) a.m2rc[i] = -1, a.srowrc[i] = -1, a.typerc[i] = FRB_TYPE_UNDETERMINED;
+            }
+        }
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, first1 >= 0);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(a.work_n, static_cast<unsigned long long>(__popc(need)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (first1 >= 0) a.work[base + __popc(need & ((1u << lane) - 1u))] = static_cast<unsigned>(i);
+        }
+    }
+}
+
+// ---- kernel 2: full classification of the keys on the work list ---------------------------------
 __global__ void __launch_bounds__(kMatchThreads) match_kernel(const MatchArgs a) {
     extern __shared__ __align__(16) unsigned char msmem[];
     unsigned long long* s_a = reinterpret_cast<unsigned long long*>(msmem);  // idx2 as supplied / oriented
@@ -67,46 +137,37 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(const MatchArgs a)
     const unsigned long long B1 = ((1ULL << (3 * a.l1)) - 1) & kFoldLsb;
     const unsigned long long B2 = a.l2 ? ((((1ULL << (3 * a.l2)) - 1) & kFoldLsb) << (3 * (a.l1 + 1))) : 0ULL;
     const unsigned n_subs = a.n_subs;
+    const unsigned long long n_work = *a.work_n;
 
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < a.n;
-         i += stride) {
+    for (unsigned long long j = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; j < n_work;
+         j += stride) {
+        const unsigned long long i = a.work[j];
         const unsigned long long key = a.keys[i];
-        // shape check: idx1 of l1 symbols in 1..5, then '+' and idx2 of l2 symbols in 1..5, then
-        // end or another '+' (extra parts ignored, F:306); single index: l1 symbols then end.
-        if (a.rows) {
-            bool ok = true;
-            const unsigned total = a.l2 ? a.l1 + 1 + a.l2 : a.l1;
-            for (unsigned s = 0; s < total; ++s) {
-                const unsigned sym = static_cast<unsigned>(key >> (3 * s)) & 7u;
-                if (a.l2 && s == a.l1) ok &= (sym == 6);
-                else ok &= (sym >= 1 && sym <= 5);
-            }
-            if (total < kMaxSyms) {
-                const unsigned nxt = static_cast<unsigned>(key >> (3 * total)) & 7u;
-                ok &= a.l2 ? (nxt == 0 || nxt == 6) : (nxt == 0);
-            }
-            if (!ok) raise_error(a.st, FRB_ERR_BAD_LENGTH, key);
-        }
-        int first1 = -1, firstf = -1, firstr = -1, rowf = -1, rowr = -1;
+        // first idx1 row: from kernel 1, or from the rc pass when this is the oriented second pass of a
+        // scan (F:628) -- orientation only changes idx2, and a key the rc pass left without an
+        // idx1+idx2 match in either orientation cannot get one from a per-row choice between the two.
+        const int first1 = a.m1[i];
+        int firstf = -1, firstr = -1, rowf = -1, rowr = -1;
         unsigned nf = 0, nr = 0;
-        for (unsigned r = 0; r < a.rows; ++r) {
-            const unsigned long long df = fold3(key ^ s_a[r]);
-            const bool h1 = static_cast<unsigned>(__popcll(df & B1)) <= n_subs;
-            const bool h2 = a.l2 ? (static_cast<unsigned>(__popcll(df & B2)) <= n_subs) : true;
-            if (h1 && first1 < 0) first1 = r;
-            if (h2 && firstf < 0) firstf = r;
-            if (h1 && h2) {
-                ++nf;
-                if (rowf < 0) rowf = r;
-            }
-            if (a.rc_mode) {
-                const unsigned long long dr = fold3(key ^ s_b[r]);
-                const bool h3 = static_cast<unsigned>(__popcll(dr & B2)) <= n_subs;
-                if (h3 && firstr < 0) firstr = r;
-                if (h1 && h3) {
-                    ++nr;
-                    if (rowr < 0) rowr = r;
+        if (first1 >= 0) {
+            for (unsigned r = 0; r < a.rows; ++r) {
+                const unsigned long long df = fold3(key ^ s_a[r]);
+                const bool h1 = static_cast<unsigned>(__popcll(df & B1)) <= n_subs;
+                const bool h2 = a.l2 ? (static_cast<unsigned>(__popcll(df & B2)) <= n_subs) : true;
+                if (h2 && firstf < 0) firstf = r;
+                if (h1 && h2) {
+                    ++nf;
+                    if (rowf < 0) rowf = r;
+                }
+                if (a.rc_mode) {
+                    const unsigned long long dr = fold3(key ^ s_b[r]);
+                    const bool h3 = static_cast<unsigned>(__popcll(dr & B2)) <= n_subs;
+                    if (h3 && firstr < 0) firstr = r;
+                    if (h1 && h3) {
+                        ++nr;
+                        if (rowr < 0) rowr = r;
+                    }
                 }
             }
         }
@@ -123,14 +184,14 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(const MatchArgs a)
             const unsigned long long c = a.counts[i];
             if (srow >= 0) atomicAdd(&s_f[s_g[srow]], c);      // F:370-371
             if (srowr >= 0) atomicAdd(&s_r[s_g[srowr]], c);    // F:372-373
-            if (a.m2rc) a.m2rc[i] = m2r;
-            if (a.typerc) a.typerc[i] = static_cast<unsigned char>(typer);
-            if (a.srowrc) a.srowrc[i] = srowr;
+            a.m2rc[i] = m2r;
+            a.typerc[i] = static_cast<unsigned char>(typer);
+            a.srowrc[i] = srowr;
         }
-        if (a.m1) a.m1[i] = m1;
-        if (a.m2) a.m2[i] = m2;
-        if (a.type) a.type[i] = static_cast<unsigned char>(type);
-        if (a.srow) a.srow[i] = srow;
+        a.m1[i] = m1;
+        a.m2[i] = m2;
+        a.type[i] = static_cast<unsigned char>(type);
+        a.srow[i] = srow;
     }
     if (a.rc_mode) {
         __syncthreads();

@@ -64,6 +64,13 @@ __global__ void __launch_bounds__(256) gather2_kernel(const unsigned* __restrict
     }
 }
 
+__global__ void __launch_bounds__(256) add_offset_kernel(const unsigned long long* __restrict__ in,
+                                                         unsigned long long* __restrict__ out, unsigned long long n,
+                                                         unsigned long long off) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = in[i] + off;
+}
+
 // dst[key] += counts, first = min(first, pos_base + first_in)
 __global__ void __launch_bounds__(256) merge_list_kernel(Slot* dst, unsigned long long mask,
                                                          const unsigned long long* __restrict__ keys,
