@@ -63,7 +63,10 @@ __device__ __forceinline__ void raise_error(DevState* st, int code, unsigned lon
 }
 
 // count += cnt, first = min(first, pos) for `key`, inserting it if new.  Linear probing.
-__device__ __forceinline__ void table_add(Slot* __restrict__ tab, unsigned long long mask,
+// Cold path (collisions, first insertions that lost a race): out of line, so that the many places that
+// may need it do not each carry a copy of the probing loop (the scan kernels' SASS has to stay near the
+// instruction cache size).
+__device__ __noinline__ void table_add(Slot* __restrict__ tab, unsigned long long mask,
                                           unsigned long long key, unsigned long long cnt,
                                           unsigned long long pos, unsigned long long* occupied,
                                           DevState* st) {

@@ -126,6 +126,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 }
 
+#define kFoldLsb3 0x1249249249249249ULL  // bit 0 of every 3-bit group
+
 // ---- byte-compare primitives ---------------------------------------------------------------
 // bit 7 of every byte of w that equals the byte replicated in `pat`; exact (no borrow leaks).
 __device__ __forceinline__ unsigned eq_flags(unsigned w, unsigned pat) {
@@ -153,6 +155,7 @@ __device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsig
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const unsigned p = a0 + 16u * i;
+        if (i >= 4 && p >= eb) break;  // ordinary header lines span 5 segments; the loads stay batched
         const uint4 v = *reinterpret_cast<const uint4*>(buf + (p < eb ? p : a0));
         unsigned m = eq_mask16(v, 0x20202020u);
         const unsigned lo_cut = sb > p ? sb - p : 0u;                  // bytes of this segment before the line
@@ -161,6 +164,11 @@ __device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsig
         cnt += __popc(m);
     }
     return static_cast<int>(cnt);
+}
+
+// shared-memory LUT entry of byte c for parse_header (code | delimiter flags)
+__device__ __forceinline__ unsigned char lut_entry(unsigned c) {
+    return static_cast<unsigned char>(enc_read(c) | (c == ':' ? 0x18u : 0u) | (c == ' ' ? 0x08u : 0u));
 }
 
 // Exact, byte-serial statement of both key rules over one header line (no trailing newline).
@@ -216,31 +224,34 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
         *start_out = tile_off + sb - kHalo;
         // Fast path, branch-free and latency-flat.  With exactly one ' ' in the line the key is the
         // text after the last ':' or ' ' (the 2nd space token runs to the end of the line).
+        // lut[c]: bits 0-2 symbol code, bit 3 = delimiter under the scan rule, bit 4 = under the demux rule.
         const int spaces = scan_rule ? count_spaces_fast(buf, sb, eb) : 1;
-        unsigned ch[kMaxSyms + 1];
+        const unsigned dbit = scan_rule ? 3u : 4u;
+        unsigned delim = 0, zero = 0, lo = 0, hi = 0, top = 0;
 #pragma unroll
         for (int j = 0; j < kMaxSyms + 1; ++j) {  // last 22 bytes of the line, closest to EOL first
             const int p = static_cast<int>(eb) - 1 - j;
-            ch[j] = (p >= static_cast<int>(sb)) ? buf[p] : static_cast<unsigned>(':');
+            const unsigned c = (p >= static_cast<int>(sb)) ? buf[p] : static_cast<unsigned>(':');
+            const unsigned v = lut[c];
+            const unsigned code = v & 7u;
+            delim |= ((v >> dbit) & 1u) << j;
+            zero |= (code == 0 ? 1u : 0u) << j;
+            if (j < 10) lo |= code << (3 * j);
+            else if (j < 20) hi |= code << (3 * (j - 10));
+            else if (j == 20) top = code;
         }
-        unsigned delim = 0;
-#pragma unroll
-        for (int j = 0; j < kMaxSyms + 1; ++j)
-            delim |= ((ch[j] == ':') || (scan_rule && ch[j] == ' ') ? 1u : 0u) << j;
         if (spaces == 0) return FRB_ERR_BAD_HEADER;
         if (spaces == 1 && delim != 0) {
             const int len = __ffs(delim) - 1;  // symbols in the key, <= 21
-            unsigned long long k = 0;
-            unsigned bad = 0;
-#pragma unroll
-            for (int j = 0; j < kMaxSyms; ++j) {
-                const unsigned code = lut[ch[j]];
-                const bool in_key = j < len;
-                k |= in_key ? (static_cast<unsigned long long>(code) << (3 * (in_key ? len - 1 - j : 0))) : 0ULL;
-                bad |= (in_key && code == 0) ? 1u : 0u;
-            }
-            if (bad) return FRB_ERR_BAD_ALPHABET;
-            *key_out = k;
+            if (zero & ((1u << len) - 1u)) return FRB_ERR_BAD_ALPHABET;
+            // krev holds the key backwards (symbol j = j-th char from the end); reverse the order of the
+            // 3-bit groups: bit-reverse the word, then put the bits of every group back in order
+            const unsigned long long krev = static_cast<unsigned long long>(lo) |
+                                            (static_cast<unsigned long long>(hi) << 30) |
+                                            (static_cast<unsigned long long>(top) << 60);
+            const unsigned long long r = __brevll(krev) >> 1;  // group j now at group index 20 - j, bits mirrored
+            const unsigned long long g = ((r & kFoldLsb3) << 2) | (r & (kFoldLsb3 << 1)) | ((r >> 2) & kFoldLsb3);
+            *key_out = len ? (g >> (3 * (kMaxSyms - len))) : 0ULL;
             return 0;
         }
     }
@@ -451,8 +462,8 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
         tick(1);
     };
 
-    s_lut[tid & 255] = static_cast<unsigned char>(enc_read(tid & 255));
-    if (kThreads < 256) s_lut[(tid + kThreads) & 255] = static_cast<unsigned char>(enc_read((tid + kThreads) & 255));
+    s_lut[tid & 255] = lut_entry(tid & 255);
+    if (kThreads < 256) s_lut[(tid + kThreads) & 255] = lut_entry((tid + kThreads) & 255);
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     volatile unsigned long long* status = a.status + 1;
 
-    s_lut[tid] = static_cast<unsigned char>(enc_read(tid));
+    s_lut[tid] = lut_entry(tid);
     if (tid == 0) {
         s_have_prefix[0] = 0, s_have_prefix[1] = 0;
 #pragma unroll
@@ -271,28 +271,38 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
             tick(1);
             const unsigned long long K0 = L0 + s_prefix[i & 1];
             const unsigned halo_start = s_halo_start;
-            // Look-back of the NEXT tile in the shadow of this tile's key extraction: only if its count
-            // is already in (non-blocking probe) and without ever waiting on another CTA.
-            if (pwarp == kWsGroup / 32 - 1) {
-                const int sn = (i + 1) % kStages;
-                unsigned long long excl = 0;
-                bool ok = false;
-                if (mbar_test(&s_counted[sn], (counted_parity >> sn) & 1u)) {
-                    const unsigned tn = s_tile[sn];
-                    ok = tn != kNoTile && tile_prefix<false>(status, tn, s_total[sn], lane, &excl);
-                }
-                if (lane == 0) s_prefix[(i + 1) & 1] = excl, s_have_prefix[(i + 1) & 1] = ok ? 1u : 0u;
-            }
             const unsigned long long o_first = (K0 + 3) >> 2;
             const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
             const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
             const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
-
+            // Look-back of the NEXT tile in the shadow of this tile's key extraction: only if its count
+            // is already in (non-blocking probe) and without ever waiting on another CTA.
+            if (pwarp == kWsGroup / 32 - 1) {
+                // this warp has no header lines in ordinary tiles: it keeps probing (bounded, never
+                // blocking on another CTA) while the other parser warps extract keys
+                const int sn = (i + 1) % kStages;
+                unsigned long long excl = 0;
+                bool ok = false;
+                const bool idle = n_owned <= static_cast<unsigned>(kWsGroup - 32);
+                for (int attempt = 0; attempt < 1 && !ok; ++attempt) {
+                    if (mbar_test(&s_counted[sn], (counted_parity >> sn) & 1u)) {
+                        const unsigned tn = s_tile[sn];
+                        if (tn == kNoTile) break;
+                        ok = tile_prefix<false>(status, tn, s_total[sn], lane, &excl);
+                    }
+                    if (!ok && idle) __nanosleep(100);
+                }
+                if (lane == 0) s_prefix[(i + 1) & 1] = excl, s_have_prefix[(i + 1) & 1] = ok ? 1u : 0u;
+            }
             tick(4);
-            finish_pending();  // issued far from the next barrier: its atomics never stall one
+            if (n_owned == 0) finish_pending();
             tick(5);
             if (total + vnl <= static_cast<unsigned>(kWsNlCap)) {
+#pragma unroll 1
                 for (unsigned h0 = 0; h0 < n_owned; h0 += kWsGroup) {
+                    // table updates of the previous tile (or pass): issued here, far from the next
+                    // barrier, so that their atomics never stall one
+                    finish_pending();
                     const unsigned h = h0 + pt;
                     const unsigned long long o = o_first + h;
                     bool have = (h < n_owned) && (o < a.read_limit);
@@ -308,7 +318,6 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                     }
                     const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
                     tick(6);
-                    if (h0) finish_pending();
                     if (have) {
                         const unsigned same = __match_any_sync(grp, key);
                         if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
@@ -357,8 +366,8 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
             atomicAdd(&a.timing[8], tp[7]);
             atomicAdd(&a.timing[9], tp[3]);
         }
-        finish_pending();
-        finish_pending();
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) finish_pending();  // the second call retires a CAS issued by the first
         if (pt == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
     }
 }
