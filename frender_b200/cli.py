@@ -147,17 +147,76 @@ def get_paired_files(files):
 # scan (F:567-642)
 # ---------------------------------------------------------------------------------------------
 class ScanTables:
-    """Device results of the tally as arrays: total list + per-file lists (dict semantics of
+    """Results of the tally as arrays: total list + per-file lists (dict semantics of
     barcode_counter: a repeated basename keeps its first position and the last file's counts)."""
 
-    def __init__(self, ctx, names):
-        self.keys, self.counts, _ = ctx.total_arrays()
+    def __init__(self, names, total, per_file):
+        self.keys, self.counts = total
         slot = {}
         for i, name in enumerate(names):
             slot.setdefault(name, len(slot))
         self.file_names = list(slot)
         latest = {name: i for i, name in enumerate(names)}
-        self.files = [ctx.file_arrays(latest[name])[:2] for name in self.file_names]
+        self.files = [per_file[latest[name]] for name in self.file_names]
+
+    @classmethod
+    def from_ctx(cls, ctx, names):
+        keys, counts, _ = ctx.total_arrays()
+        return cls(names, (keys, counts), [ctx.file_arrays(i)[:2] for i in range(len(names))])
+
+
+def _scan_worker(rank, n_ranks, device, ident, jobs, sample, table_log2, conn):
+    """One process per GPU (FRENDER_GPUS > 1): scan this rank's files, merge the per-rank tables over
+    NCCL, send the per-file lists (and, from rank 0, the merged total) to the parent."""
+    try:
+        ctx = Context(device, table_log2=table_log2)
+        ctx.nccl_init(ident, rank, n_ranks)
+        ctx.reset()
+        out = []
+        for k, (ordinal, path) in enumerate(jobs):
+            reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
+            fk, fc, _ = ctx.file_arrays(k)
+            out.append((ordinal, reads, uniq, fk, fc))
+        ctx.allmerge()
+        total = ctx.total_arrays()[:2] if rank == 0 else None
+        conn.send(("ok", out, total))
+        ctx.close()
+    except BaseException as exc:            # forwarded: the parent re-raises
+        conn.send(("error", repr(exc), None))
+    finally:
+        conn.close()
+
+
+def scan_files_multi_gpu(files, sample, n_gpus, table_log2):
+    """File-level sharding over n_gpus GPUs: file i goes to rank i % n_gpus."""
+    import multiprocessing as mp
+
+    from .shard import assign
+    mpc = mp.get_context("spawn")
+    ident = Context.nccl_unique_id()
+    jobs = list(enumerate(files))
+    procs, pipes = [], []
+    for rank in range(n_gpus):
+        parent, child = mpc.Pipe(duplex=False)
+        p = mpc.Process(target=_scan_worker, args=(rank, n_gpus, rank, ident, assign(jobs, rank, n_gpus), sample,
+                                                   table_log2, child))
+        p.start()
+        procs.append(p)
+        pipes.append(parent)
+    per_file, total = {}, None
+    for rank, conn in enumerate(pipes):
+        status, payload, tot = conn.recv()
+        if status != "ok":
+            for p in procs:
+                p.terminate()
+            raise SystemExit(f"GPU worker {rank} failed: {payload}")
+        for ordinal, reads, uniq, fk, fc in payload:
+            per_file[ordinal] = (reads, uniq, fk, fc)
+        if tot is not None:
+            total = tot
+    for p in procs:
+        p.join()
+    return per_file, total
 
 
 def demux_ok_flags(tables, read_type, sample_row, sheet_ids, prefix):
@@ -256,14 +315,22 @@ def frender_scan(args, ctx=None):
             assert sample >= 1, "Number of reads to sample must be ≥ 1!"
             print(f"Sampling {sample} reads from the head of each file...")
         ctx.reset()
-        names = []
-        for ordinal, path in enumerate(files):
-            name = os.path.basename(str(path))
-            print(f"Tallying barcodes from {name}...", end="")
-            reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
-            print(f"found {uniq} new barcode{'' if uniq == 1 else 's'} in {reads} reads.")
-            names.append(name)
-        tables = ScanTables(ctx, names)
+        names = [os.path.basename(str(path)) for path in files]
+        n_gpus = min(int(os.environ.get("FRENDER_GPUS", "1")), max(len(files), 1))
+        if n_gpus > 1:
+            per_file, total = scan_files_multi_gpu(files, sample, n_gpus, ctx.table_log2)
+            for ordinal, name in enumerate(names):
+                reads, uniq = per_file[ordinal][:2]
+                print(f"Tallying barcodes from {name}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
+                      f"in {reads} reads.")
+            tables = ScanTables(names, total, [per_file[i][2:] for i in range(len(names))])
+            ctx.load_total_arrays(*total)
+        else:
+            for ordinal, path in enumerate(files):
+                print(f"Tallying barcodes from {names[ordinal]}...", end="")
+                reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
+                print(f"found {uniq} new barcode{'' if uniq == 1 else 's'} in {reads} reads.")
+            tables = ScanTables.from_ctx(ctx, names)
         print("Scanning complete! Analyzing barcodes...")
 
         # ---- matcher (F:610-630) ---------------------------------------------------------------

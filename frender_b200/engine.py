@@ -199,6 +199,30 @@ class Context:
         counts = np.fromiter(counter.values(), dtype=np.uint64, count=len(counter))
         self._ck(lib.frb_total_load(self._h, _ptr(keys), _ptr(counts), len(keys)))
 
+    def load_total_arrays(self, keys, counts):
+        """Use packed key / count arrays as the unique-key list (already in first-appearance order)."""
+        keys = np.ascontiguousarray(keys, np.uint64)
+        counts = np.ascontiguousarray(counts, np.uint64)
+        self._ck(lib.frb_total_load(self._h, _ptr(keys), _ptr(counts), len(keys)))
+
+    # ---- multi-GPU ----------------------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        ident = (C.c_char * 128)()
+        rc = lib.frb_nccl_unique_id(ident)
+        if rc != _lib.OK:
+            raise FrbError(rc, (lib.frb_last_error(None) or b"").decode())
+        return bytes(ident)
+
+    def nccl_init(self, ident, rank, n_ranks):
+        self._ck(lib.frb_nccl_init(self._h, ident, rank, n_ranks))
+
+    def allmerge(self):
+        """Merge the per-rank totals over NCCL; every rank ends with the same total list."""
+        n = C.c_uint64()
+        self._ck(lib.frb_allmerge(self._h, C.byref(n)))
+        return n.value
+
     def match(self, n_subs, rc_mode, use_rc_rows=None, want_outputs=True):
         """Raw matcher call over the context's total list.  Returns a dict of numpy arrays."""
         uniq = C.c_uint64()

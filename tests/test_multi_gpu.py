@@ -69,3 +69,30 @@ def test_nccl_merge_matches_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "mgpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "mgpu ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_cli_scan_file_sharding_two_gpus(tmp_path, monkeypatch):
+    """FRENDER_GPUS=2: files sharded over two GPUs, tables merged over NCCL, CSV byte-identical to the
+    reference's output for the same three files."""
+    import ctypes
+    import json
+    from conftest import GOLDEN_DIR, unb64
+    from frender_b200._lib import lib
+    n = ctypes.c_int()
+    lib.frb_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs >= 2 GPUs")
+    case = json.load(open(os.path.join(GOLDEN_DIR, "golden.json")))["scan"]["multi"]
+    files = []
+    for fname in case["files"]:
+        dst = tmp_path / fname
+        dst.write_bytes(open(os.path.join(GOLDEN_DIR, f"multi__{fname}"), "rb").read())
+        files.append(str(dst))
+    (tmp_path / "SampleSheet.csv").write_text(case["sheet_csv"])
+    monkeypatch.setenv("FRENDER_GPUS", "2")
+    monkeypatch.chdir(tmp_path)
+    from frender_b200.cli import main
+    main(["scan", "-n", "1", "-rc", "-p", case["prefix"], "-o", "m", "-b", str(tmp_path / "SampleSheet.csv")] + files)
+    out = [f for f in os.listdir(tmp_path) if f.startswith("frender-scan-results_")][0]
+    assert (tmp_path / out).read_bytes() == unb64(case["scan_csv"])
