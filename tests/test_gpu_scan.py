@@ -168,3 +168,33 @@ def test_short_lines_serial_fallback(ctx):
         reads, uniq = ctx.scan_bytes(recs.encode(), chunk=chunk)
         assert reads == visited == 20000 and uniq == len(want)
         assert list(ctx.counter()["total"].items()) == list(want.items())
+
+
+def test_single_index_c5(ctx, tmp_path):
+    """Config 5 shape: 6 bp single index.  The tally is pinned by the oracle (the reference can run it,
+    F:154-207); the matcher for single-index sheets is an extension (the reference cannot: F:104-107,
+    F:306) checked against the oracle's statement of it (parity unpinned)."""
+    import frender_oracle as O
+    from frender_b200 import synth
+    from frender_b200.engine import tally_barcodes
+    spec = synth.make_spec("C5")
+    files = []
+    for i in range(3):
+        p = tmp_path / f"S{i}_L001_R1_001.fastq.gz"
+        p.write_bytes(gzip.compress(synth.generate(spec, i * 4000, (i + 1) * 4000), 1))
+        files.append(p)
+    want = O.tally_barcodes(1, files)
+    got = tally_barcodes(1, files, ctx=ctx)
+    assert {k: list(v.items()) for k, v in got.items()} == {k: list(v.items()) for k, v in want.items()}
+    idx = spec.indexes()
+    assert idx["idx2"] is None
+    res, _ = ctx.process(None, idx, 0, False)
+    for key, rec in res.items():
+        exp = O.match_single_index(key, idx["idx1"], idx["id"], 0)
+        assert (rec["matched_idx1"], rec["read_type"], rec["sample_name"]) == \
+               (exp["matched_idx1"], exp["read_type"], exp["sample_name"]), key
+    res1, _ = ctx.process(None, idx, 1, False)
+    for key, rec in list(res1.items())[:500]:
+        exp = O.match_single_index(key, idx["idx1"], idx["id"], 1)
+        assert (rec["matched_idx1"], rec["read_type"], rec["sample_name"]) == \
+               (exp["matched_idx1"], exp["read_type"], exp["sample_name"]), key
