@@ -50,6 +50,7 @@ SIGNATURES = {
     "frb_total_finish": (C.c_int, [vp, P(u64)]),
     "frb_total_export": (C.c_int, [vp, vp, vp, vp, u64]),
     "frb_total_load": (C.c_int, [vp, vp, vp, u64]),
+    "frb_total_merge": (C.c_int, [vp, vp, vp, vp, u64]),
     "frb_reset": (C.c_int, [vp]),
     "frb_sheet_load": (C.c_int, [vp, vp, vp, vp, u32, u32, u32]),
     "frb_match": (C.c_int, [vp, u32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -187,6 +187,48 @@ def _scan_worker(rank, n_ranks, device, ident, jobs, sample, table_log2, conn):
         conn.close()
 
 
+def scan_files_concurrent(files, sample, streams, device, table_log2, main_ctx):
+    """`-c N` on one GPU: N files are inflated and scanned at the same time, each on its own context
+    (own tables, streams and zlib thread; ctypes releases the GIL), which is the reference's file-level
+    pool (F:189-193) with the GPU behind it.  The per-file lists are folded into main_ctx's total on
+    the device (F:199-203)."""
+    import queue
+    import threading
+    jobs = queue.Queue()
+    for item in enumerate(files):
+        jobs.put(item)
+    per_file, errors = {}, []
+
+    def worker():
+        try:
+            ctx = Context(device, table_log2=table_log2)
+            while True:
+                try:
+                    ordinal, path = jobs.get_nowait()
+                except queue.Empty:
+                    break
+                ctx.reset()
+                reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
+                fk, fc, ff = ctx.file_arrays(0)
+                per_file[ordinal] = (reads, uniq, fk, fc, ff)
+            ctx.close()
+        except BaseException as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker) for _ in range(streams)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    main_ctx.reset()
+    for ordinal in range(len(files)):
+        _, _, fk, fc, ff = per_file[ordinal]
+        main_ctx.merge_list(fk, fc, ff + (np.uint64(ordinal) << np.uint64(40)))
+    return per_file, main_ctx.total_arrays()[:2]
+
+
 def scan_files_multi_gpu(files, sample, n_gpus, table_log2):
     """File-level sharding over n_gpus GPUs: file i goes to rank i % n_gpus."""
     import multiprocessing as mp
@@ -275,7 +317,7 @@ def report_rc_call_info(rc_calls, indexes, out_csv_name):
 
 def frender_scan(args, ctx=None):
     num_subs, rc_mode = args.n, args.rc
-    get_cores(args.c)
+    cores = get_cores(args.c)
     sample = args.s
     infix = args.o if args.o else ""
     prefix = args.p if args.p else ""
@@ -310,7 +352,7 @@ def frender_scan(args, ctx=None):
                          table_log2=int(os.environ.get("FRENDER_TABLE_LOG2", "24")))
     try:
         # ---- tally (F:183-207) -----------------------------------------------------------------
-        print(f"Scanning {len(files)} files on GPU {ctx.device}...")
+        print(f"Scanning {len(files)} files on GPU {ctx.device} with {cores} inflate stream{'' if cores == 1 else 's'}...")
         if sample:
             assert sample >= 1, "Number of reads to sample must be ≥ 1!"
             print(f"Sampling {sample} reads from the head of each file...")
@@ -325,6 +367,14 @@ def frender_scan(args, ctx=None):
                       f"in {reads} reads.")
             tables = ScanTables(names, total, [per_file[i][2:] for i in range(len(names))])
             ctx.load_total_arrays(*total)
+        elif cores > 1 and len(files) > 1:
+            streams = min(cores, len(files), int(os.environ.get("FRENDER_MAX_STREAMS", "16")))
+            per_file, total = scan_files_concurrent(files, sample, streams, ctx.device, ctx.table_log2, ctx)
+            for ordinal, name in enumerate(names):
+                reads, uniq = per_file[ordinal][:2]
+                print(f"Tallying barcodes from {name}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
+                      f"in {reads} reads.")
+            tables = ScanTables(names, total, [per_file[i][2:4] for i in range(len(names))])
         else:
             for ordinal, path in enumerate(files):
                 print(f"Tallying barcodes from {names[ordinal]}...", end="")

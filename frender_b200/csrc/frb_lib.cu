@@ -68,6 +68,7 @@ struct frb_ctx {
     KeyList total;
     bool total_ready = false, in_file = false;
     size_t merged_upto = 0;        // file lists already folded into total_tab
+    bool ext_merged = false;       // lists from other contexts were folded in (frb_total_merge)
     bool total_tab_clean = true;   // total_tab holds no keys
     uint32_t cur_ordinal = 0;
     uint64_t cur_limit = ~0ULL;
@@ -660,7 +661,7 @@ int frb_total_finish(frb_ctx* c, uint64_t* n_unique) {
     if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_total_finish: a file is still open");
     if (!c->total_ready) {
         TRY(free_list(c, c->total));
-        if (c->files.size() == 1 && c->merged_upto == 0) {
+        if (c->files.size() == 1 && c->merged_upto == 0 && !c->ext_merged) {
             // one file: "total" is that file's list (F:199-203 degenerates to a copy); only `first`
             // gets the file ordinal in its high bits
             const KeyList& fl = c->files[0];
@@ -710,6 +711,34 @@ int frb_total_load(frb_ctx* c, const uint64_t* keys, const uint64_t* counts, uin
     c->total_gen++;
     return FRB_OK;
 }
+int frb_total_merge(frb_ctx* c, const uint64_t* keys, const uint64_t* counts, const uint64_t* first_pos, uint64_t n) {
+    CU(c, cudaSetDevice(c->device));
+    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_total_merge: a file is still open");
+    if (n) {
+        unsigned long long *dk = nullptr, *dc = nullptr, *df = nullptr;
+        TRY(dmalloc(c, &dk, n * 8));
+        TRY(dmalloc(c, &dc, n * 8));
+        TRY(dmalloc(c, &df, n * 8));
+        CU(c, cudaMemcpyAsync(dk, keys, n * 8, cudaMemcpyHostToDevice, c->compute));
+        CU(c, cudaMemcpyAsync(dc, counts, n * 8, cudaMemcpyHostToDevice, c->compute));
+        CU(c, cudaMemcpyAsync(df, first_pos, n * 8, cudaMemcpyHostToDevice, c->compute));
+        {
+            ProfScope ps(c, FRB_K_EXPORT);
+            merge_list_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(
+                c->total_tab, c->cap - 1, dk, dc, df, n, 0ULL, &c->st->occupied_total, c->st);
+            c->launches++;
+        }
+        CU(c, cudaGetLastError());
+        CU(c, cudaStreamSynchronize(c->compute));  // the host arrays may be reused by the caller
+        TRY(dfree(c, dk));
+        TRY(dfree(c, dc));
+        TRY(dfree(c, df));
+        c->total_tab_clean = false;
+    }
+    c->ext_merged = true;
+    c->total_ready = false;
+    return FRB_OK;
+}
 int frb_reset(frb_ctx* c) {
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->compute));
@@ -720,6 +749,7 @@ int frb_reset(frb_ctx* c) {
     c->in_file = false;
     CU(c, cudaMemsetAsync(c->st, 0, sizeof(DevState), c->compute));
     c->merged_upto = 0;
+    c->ext_merged = false;
     if (!c->total_tab_clean) {
         TRY(clear_table(c, c->total_tab));
         c->total_tab_clean = true;

@@ -205,6 +205,11 @@ class Context:
         counts = np.ascontiguousarray(counts, np.uint64)
         self._ck(lib.frb_total_load(self._h, _ptr(keys), _ptr(counts), len(keys)))
 
+    def merge_list(self, keys, counts, first_pos):
+        """Fold a (key, count, global first_pos) list from another context into this context's total."""
+        keys, counts, first_pos = (np.ascontiguousarray(x, np.uint64) for x in (keys, counts, first_pos))
+        self._ck(lib.frb_total_merge(self._h, _ptr(keys), _ptr(counts), _ptr(first_pos), len(keys)))
+
     # ---- multi-GPU ----------------------------------------------------------------------------
     @staticmethod
     def nccl_unique_id():

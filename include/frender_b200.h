@@ -113,6 +113,10 @@ int frb_total_finish(frb_ctx* ctx, uint64_t* n_unique); /* sort total by first a
 int frb_total_export(frb_ctx* ctx, uint64_t* keys, uint64_t* counts, uint64_t* first_pos, uint64_t cap);
 /* Load a (key,count) list as the total instead of scanning (process() on a caller's dict).  */
 int frb_total_load(frb_ctx* ctx, const uint64_t* keys, const uint64_t* counts, uint64_t n);
+/* Fold a (key,count,first_pos) list produced elsewhere (another context scanning other files of
+ * the same run, F:199-203) into this context's total; first_pos must already be global.          */
+int frb_total_merge(frb_ctx* ctx, const uint64_t* keys, const uint64_t* counts, const uint64_t* first_pos,
+                    uint64_t n);
 int frb_reset(frb_ctx* ctx); /* forget all files and the total                                 */
 
 /* ---- hot path B: mismatch matcher + index-2 orientation ------------------------------------

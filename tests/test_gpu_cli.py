@@ -62,7 +62,9 @@ def test_cli_scan_csv_bytes(golden, golden_dir, tmp_path, name):
         assert (tmp_path / calls).read_bytes() == unb64(case["rc_calls_csv"])
 
 
-def test_cli_scan_multi_file_prefix(golden, golden_dir, tmp_path):
+@pytest.mark.parametrize("cores", ["1", "3"])
+def test_cli_scan_multi_file_prefix(golden, golden_dir, tmp_path, cores):
+    """Three files, `-p` prefix; `-c 3` scans them concurrently on three contexts of the same GPU."""
     case = golden["scan"]["multi"]
     files = []
     for fname in case["files"]:
@@ -70,8 +72,8 @@ def test_cli_scan_multi_file_prefix(golden, golden_dir, tmp_path):
         dst.write_bytes(open(os.path.join(golden_dir, f"multi__{fname}"), "rb").read())
         files.append(str(dst))
     (tmp_path / "SampleSheet.csv").write_text(case["sheet_csv"])
-    run_cli(["scan", "-n", "1", "-rc", "-p", case["prefix"], "-o", "m", "-b", str(tmp_path / "SampleSheet.csv")]
-            + files, tmp_path)
+    run_cli(["scan", "-n", "1", "-rc", "-c", cores, "-p", case["prefix"], "-o", "m", "-b",
+             str(tmp_path / "SampleSheet.csv")] + files, tmp_path)
     out = [f for f in os.listdir(tmp_path) if f.startswith("frender-scan-results_")][0]
     assert (tmp_path / out).read_bytes() == unb64(case["scan_csv"])
 
