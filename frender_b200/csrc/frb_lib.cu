@@ -304,7 +304,9 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     static const int nt = getenv("FRB_SCAN_THREADS") ? atoi(getenv("FRB_SCAN_THREADS")) : 256;
     // default: warp-specialised kernel; FRB_SCAN_KERNEL=std selects the barrier-synchronous pipeline
     static const bool ws = getenv("FRB_SCAN_KERNEL") ? strcmp(getenv("FRB_SCAN_KERNEL"), "std") != 0 : true;
-    const uint64_t tile = static_cast<uint64_t>(nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile);
+    static const bool dense = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "dense") == 0 : false;
+    const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : WsWide::tile)
+                                                   : (nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile));
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
     if (n_tiles + 1 > c->status_cap) {
@@ -343,8 +345,13 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     {
         ProfScope ps(c, FRB_K_SCAN);
         if (ws) {
-            const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * 2));
-            scan_ws_kernel<<<grid, kWsThreads, kWsSmem, c->compute>>>(a);
+            if (dense) {
+                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsDense::ctas));
+                scan_ws_kernel<WsDense><<<grid, WsDense::threads, WsDense::smem, c->compute>>>(a);
+            } else {
+                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsWide::ctas));
+                scan_ws_kernel<WsWide><<<grid, WsWide::threads, WsWide::smem, c->compute>>>(a);
+            }
         } else if (nt == 128) {
             using Cfg = ScanCfg<128>;
             const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
@@ -439,7 +446,8 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaEventCreate(&c->t1));
     CU(c, cudaFuncSetAttribute(scan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<256>::smem));
     CU(c, cudaFuncSetAttribute(scan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<128>::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsWide::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsDense::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TRY(clear_table(c, c->total_tab));
     CU(c, cudaStreamSynchronize(c->compute));

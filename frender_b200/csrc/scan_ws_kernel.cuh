@@ -18,20 +18,40 @@
 
 namespace frb {
 
-constexpr int kWsThreads = 256;
-constexpr int kWsGroup = 128;                 // threads per role
-constexpr int kWsTile = 32768;
-constexpr int kWsBuf = kWsTile + kHalo;
-constexpr int kWsNlCap = 2048;
-constexpr int kWsPerThread = kWsTile / kWsGroup;  // 256 bytes per counter thread
-constexpr int kWsSmem = kStages * kWsBuf + kStages * kWsNlCap * (int)sizeof(uint16_t);
+constexpr int kWsGroup = 128;                 // counter threads
 constexpr unsigned kNoTile = 0xFFFFFFFFu;
 
+// Tile geometry.  SEG = 16-byte segments per counter thread, PW = parser warps, CTAS = resident CTAs
+// per SM the shared memory and registers are budgeted for.
+template <int SEG, int PW, int CTAS, int NLCAP>
+struct WsGeom {
+    static constexpr int seg = SEG;
+    static constexpr int per_thread = SEG * 16;
+    static constexpr int tile = kWsGroup * per_thread;
+    static constexpr int buf = tile + kHalo;
+    static constexpr int nl_cap = NLCAP;
+    static constexpr int pwarps = PW;
+    static constexpr int pgroup = PW * 32;
+    static constexpr int threads = kWsGroup + pgroup;
+    static constexpr int ctas = CTAS;
+    static constexpr int maxreg = (65536 / (CTAS * threads)) / 8 * 8;  // per-thread budget that keeps CTAS resident
+    static constexpr int smem = kStages * buf + kStages * nl_cap * (int)sizeof(uint16_t);
+};
+using WsWide = WsGeom<16, 4, 2, 2048>;   // 32 KiB tiles, 2 x 8 warps per SM
+using WsDense = WsGeom<10, 3, 3, 1024>;  // 20 KiB tiles, 3 x 7 warps per SM
+constexpr int kWsTile = WsWide::tile;
+constexpr int kWsThreads = WsWide::threads;
+constexpr int kWsSmem = WsWide::smem;
+
+template <int N>
 __device__ __forceinline__ void group_sync(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kWsGroup) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
 }
 
-__global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a) {
+template <class G>
+__global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
+    constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
+    constexpr int kPGroup = G::pgroup, kPWarps = G::pwarps;
     extern __shared__ __align__(128) unsigned char smem[];
     uint16_t* const s_nl = reinterpret_cast<uint16_t*>(smem + kStages * kWsBuf);
     __shared__ __align__(8) unsigned long long s_full[kStages], s_counted[kStages];
@@ -48,7 +68,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     volatile unsigned long long* status = a.status + 1;
 
-    s_lut[tid] = lut_entry(tid);
+    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i);
     if (tid == 0) {
         s_have_prefix[0] = 0, s_have_prefix[1] = 0;
 #pragma unroll
@@ -86,31 +106,60 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                 if (avail != bulk) {
                     if (ct < static_cast<int>(avail - bulk))
                         buf[(kHalo - halo) + bulk + ct] = a.data[tile_off - halo + bulk + ct];
-                    group_sync(1);
+                    group_sync<kWsGroup>(1);
                 }
             }
-            // newline mask of this thread's 256 bytes: m[h][0/1] = bytes 128h + 0..63 / 64..127
-            unsigned long long m00 = 0, m01 = 0, m10 = 0, m11 = 0;
-            const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * (kWsPerThread / 16);
+            // newline masks of this thread's bytes as 32-bit words in byte order (bit k of word q = byte
+            // 32q + k); segments are read rotated so that the eight lanes of a 16-byte load phase hit
+            // eight different bank groups.
+            constexpr int kWords = kWsPerThread / 32;
+            unsigned w[kWords];
+            const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * G::seg;
+            if constexpr (G::seg == 16) {
+                unsigned long long m00 = 0, m01 = 0, m10 = 0, m11 = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = (j + ct) & 7;  // rotate so a quarter-warp hits 8 distinct bank groups
-                const unsigned long long ma = newline_mask16(t4[r]);
-                const unsigned long long mb = newline_mask16(t4[8 + r]);
-                const int sh = (r & 3) * 16;
-                if (r < 4) m00 |= ma << sh, m10 |= mb << sh;
-                else m01 |= ma << sh, m11 |= mb << sh;
+                for (int j = 0; j < 8; ++j) {
+                    const int r = (j + ct) & 7;
+                    const unsigned long long ma = newline_mask16(t4[r]);
+                    const unsigned long long mb = newline_mask16(t4[8 + r]);
+                    const int sh = (r & 3) * 16;
+                    if (r < 4) m00 |= ma << sh, m10 |= mb << sh;
+                    else m01 |= ma << sh, m11 |= mb << sh;
+                }
+                w[0] = static_cast<unsigned>(m00), w[1] = static_cast<unsigned>(m00 >> 32);
+                w[2] = static_cast<unsigned>(m01), w[3] = static_cast<unsigned>(m01 >> 32);
+                w[4] = static_cast<unsigned>(m10), w[5] = static_cast<unsigned>(m10 >> 32);
+                w[6] = static_cast<unsigned>(m11), w[7] = static_cast<unsigned>(m11 >> 32);
+            } else {
+                // thread stride 160 bytes = 10 bank groups: lanes 4-7 of a phase start one segment later
+                static_assert(G::seg == 10, "rotation below is written for 10 segments per thread");
+                const bool rot = (ct >> 2) & 1;
+                unsigned m[G::seg];
+#pragma unroll
+                for (int j = 0; j < G::seg; ++j) {
+                    const int r = (j == G::seg - 1) ? (rot ? 0 : j) : j + (rot ? 1 : 0);
+                    m[j] = newline_mask16(t4[r]);
+                }
+#pragma unroll
+                for (int q = 0; q < kWords; ++q) {
+                    const unsigned lo = rot ? m[(2 * q + G::seg - 1) % G::seg] : m[2 * q];
+                    const unsigned hi = rot ? m[2 * q] : m[2 * q + 1];
+                    w[q] = lo | (hi << 16);
+                }
             }
             {
                 const int nv = static_cast<int>(valid) - ct * kWsPerThread;
                 if (nv < kWsPerThread) {
-                    auto keep = [](unsigned long long m, int n) -> unsigned long long {
-                        return n <= 0 ? 0ULL : (n >= 64 ? m : (m & ((1ULL << n) - 1)));
-                    };
-                    m00 = keep(m00, nv), m01 = keep(m01, nv - 64), m10 = keep(m10, nv - 128), m11 = keep(m11, nv - 192);
+#pragma unroll
+                    for (int q = 0; q < kWords; ++q) {
+                        const int n = nv - 32 * q;
+                        w[q] = n <= 0 ? 0u : (n >= 32 ? w[q] : (w[q] & ((1u << n) - 1u)));
+                    }
                 }
             }
-            const unsigned cnt = __popcll(m00) + __popcll(m01) + __popcll(m10) + __popcll(m11);
+            unsigned cnt = 0;
+#pragma unroll
+            for (int q = 0; q < kWords; ++q) cnt += __popc(w[q]);
             unsigned incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -118,12 +167,12 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                 if (lane >= d) incl += n;
             }
             if (lane == 31) s_cwarp[warp] = incl;
-            group_sync(1);
+            group_sync<kWsGroup>(1);
             unsigned wbase = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < kWsGroup / 32; ++w) {
-                const unsigned v = s_cwarp[w];
-                if (w < warp) wbase += v;
+            for (int k = 0; k < kWsGroup / 32; ++k) {
+                const unsigned v = s_cwarp[k];
+                if (k < warp) wbase += v;
                 total += v;
             }
             // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
@@ -132,24 +181,23 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                 uint16_t* const nl = s_nl + s * kWsNlCap;
                 unsigned idx = wbase + incl - cnt;
                 unsigned pos0 = kHalo + ct * kWsPerThread;
-                const unsigned long long ms[4] = {m00, m01, m10, m11};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    unsigned long long m = ms[q];
+                for (int q = 0; q < kWords; ++q) {
+                    unsigned m = w[q];
                     while (m) {
-                        if (idx < kWsNlCap) nl[idx] = static_cast<uint16_t>(pos0 + (__ffsll(static_cast<long long>(m)) - 1));
+                        if (idx < static_cast<unsigned>(kWsNlCap)) nl[idx] = static_cast<uint16_t>(pos0 + (__ffs(m) - 1));
                         m &= m - 1;
                         ++idx;
                     }
-                    pos0 += 64;
+                    pos0 += 32;
                 }
-                if (ct == 0 && vnl && total < kWsNlCap) nl[total] = static_cast<uint16_t>(kHalo + valid);
+                if (ct == 0 && vnl && total < static_cast<unsigned>(kWsNlCap)) nl[total] = static_cast<uint16_t>(kHalo + valid);
             }
             if (ct == 0) {
                 s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
                 status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
             }
-            group_sync(1);  // list + meta complete (also protects s_cwarp)
+            group_sync<kWsGroup>(1);  // list + meta complete (also protects s_cwarp)
             if (ct == 0) mbar_arrive(&s_counted[s]);
             if (a.timing && ct == 0) { const long long now = clock64(); t_work += now - tm; tm = now; }
         }
@@ -158,6 +206,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
         // =============================== PARSERS =================================================
         const int pt = tid - kWsGroup;
         const int pwarp = warp - kWsGroup / 32;
+        constexpr int kLast = kPWarps - 1;  // helper warp: halo scan, early look-back
         // deferred table update, three steps (see scan_kernel.cuh)
         unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
         unsigned p_cnt = 0;
@@ -254,7 +303,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                     tile_prefix<true>(status, t, total, lane, &excl);
                     if (lane == 0) s_prefix[i & 1] = excl;
                 }
-            } else if (pwarp == kWsGroup / 32 - 1) {
+            } else if (pwarp == kLast) {
                 if (t == 0) {
                     if (lane == 0) s_halo_start = kHalo;
                 } else {
@@ -267,7 +316,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                     }
                 }
             }
-            group_sync(2);
+            group_sync<kPGroup>(2);
             tick(1);
             const unsigned long long K0 = L0 + s_prefix[i & 1];
             const unsigned halo_start = s_halo_start;
@@ -277,13 +326,13 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
             const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
             // Look-back of the NEXT tile in the shadow of this tile's key extraction: only if its count
             // is already in (non-blocking probe) and without ever waiting on another CTA.
-            if (pwarp == kWsGroup / 32 - 1) {
+            if (pwarp == kLast) {
                 // this warp has no header lines in ordinary tiles: it keeps probing (bounded, never
                 // blocking on another CTA) while the other parser warps extract keys
                 const int sn = (i + 1) % kStages;
                 unsigned long long excl = 0;
                 bool ok = false;
-                const bool idle = n_owned <= static_cast<unsigned>(kWsGroup - 32);
+                const bool idle = n_owned <= static_cast<unsigned>(kPGroup - 32);
                 for (int attempt = 0; attempt < 1 && !ok; ++attempt) {
                     if (mbar_test(&s_counted[sn], (counted_parity >> sn) & 1u)) {
                         const unsigned tn = s_tile[sn];
@@ -299,7 +348,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
             tick(5);
             if (total + vnl <= static_cast<unsigned>(kWsNlCap)) {
 #pragma unroll 1
-                for (unsigned h0 = 0; h0 < n_owned; h0 += kWsGroup) {
+                for (unsigned h0 = 0; h0 < n_owned; h0 += kPGroup) {
                     // table updates of the previous tile (or pass): issued here, far from the next
                     // barrier, so that their atomics never stall one
                     finish_pending();
@@ -349,7 +398,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) scan_ws_kernel(const ScanArgs a
                 }
             }
             tick(7);
-            group_sync(2);  // everyone is done reading stage s
+            group_sync<kPGroup>(2);  // everyone is done reading stage s
             tick(2);
             if (pt == 0) {
                 issue(s);      // the stage is free: refill it with the ticket drawn one tile ago
