@@ -166,9 +166,11 @@ __device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsig
     return static_cast<int>(cnt);
 }
 
-// shared-memory LUT entry of byte c for parse_header (code | delimiter flags)
-__device__ __forceinline__ unsigned char lut_entry(unsigned c) {
-    return static_cast<unsigned char>(enc_read(c) | (c == ':' ? 0x18u : 0u) | (c == ' ' ? 0x08u : 0u));
+// shared-memory LUT entry of byte c for parse_header: bits 0-2 symbol code, bit 3 = c ends the key
+// when walking back from the end of the line (':' always, ' ' under the scan rule).  Nothing above bit 3.
+__device__ __forceinline__ unsigned char lut_entry(unsigned c, int rule) {
+    const bool delim = (c == ':') || (rule == FRB_RULE_SCAN && c == ' ');
+    return static_cast<unsigned char>(enc_read(c) | (delim ? 0x08u : 0u));
 }
 
 // Exact, byte-serial statement of both key rules over one header line (no trailing newline).
@@ -220,35 +222,35 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
         *key_out = 0;
         return 0;
     }
-    if (sb != kUnknown) {
-        *start_out = tile_off + sb - kHalo;
+    if (sb != kUnknown) *start_out = tile_off + sb - kHalo;
+    if (sb != kUnknown && eb - sb > static_cast<unsigned>(kMaxSyms)) {
         // Fast path, branch-free and latency-flat.  With exactly one ' ' in the line the key is the
-        // text after the last ':' or ' ' (the 2nd space token runs to the end of the line).
-        // lut[c]: bits 0-2 symbol code, bit 3 = delimiter under the scan rule, bit 4 = under the demux rule.
+        // text after the last ':' or ' ' (the 2nd space token runs to the end of the line).  The line
+        // has at least 22 bytes, so the 22 bytes before its end all belong to it.
         const int spaces = scan_rule ? count_spaces_fast(buf, sb, eb) : 1;
-        const unsigned dbit = scan_rule ? 3u : 4u;
-        unsigned delim = 0, zero = 0, lo = 0, hi = 0, top = 0;
+        const unsigned char* const e = buf + eb;
+        unsigned delim = 0, lo = 0, hi = 0, top = 0;
 #pragma unroll
-        for (int j = 0; j < kMaxSyms + 1; ++j) {  // last 22 bytes of the line, closest to EOL first
-            const int p = static_cast<int>(eb) - 1 - j;
-            const unsigned c = (p >= static_cast<int>(sb)) ? buf[p] : static_cast<unsigned>(':');
-            const unsigned v = lut[c];
+        for (int j = 0; j < kMaxSyms + 1; ++j) {  // closest to the end of the line first
+            const unsigned v = lut[e[-1 - j]];
             const unsigned code = v & 7u;
-            delim |= ((v >> dbit) & 1u) << j;
-            zero |= (code == 0 ? 1u : 0u) << j;
-            if (j < 10) lo |= code << (3 * j);
-            else if (j < 20) hi |= code << (3 * (j - 10));
+            delim += (v >> 3) << j;
+            if (j < 10) lo += code << (3 * j);
+            else if (j < 20) hi += code << (3 * (j - 10));
             else if (j == 20) top = code;
         }
         if (spaces == 0) return FRB_ERR_BAD_HEADER;
         if (spaces == 1 && delim != 0) {
             const int len = __ffs(delim) - 1;  // symbols in the key, <= 21
-            if (zero & ((1u << len) - 1u)) return FRB_ERR_BAD_ALPHABET;
-            // krev holds the key backwards (symbol j = j-th char from the end); reverse the order of the
-            // 3-bit groups: bit-reverse the word, then put the bits of every group back in order
+            // krev holds the key backwards (symbol j = j-th char from the end)
             const unsigned long long krev = static_cast<unsigned long long>(lo) |
                                             (static_cast<unsigned long long>(hi) << 30) |
                                             (static_cast<unsigned long long>(top) << 60);
+            // every one of the len symbols must have a non-zero code
+            const unsigned long long want = len ? (kFoldLsb3 & ((1ULL << (3 * len)) - 1ULL)) : 0ULL;
+            if (((krev | (krev >> 1) | (krev >> 2)) & want) != want) return FRB_ERR_BAD_ALPHABET;
+            // reverse the order of the 3-bit groups: bit-reverse the word, then put the bits of every
+            // group back in order
             const unsigned long long r = __brevll(krev) >> 1;  // group j now at group index 20 - j, bits mirrored
             const unsigned long long g = ((r & kFoldLsb3) << 2) | (r & (kFoldLsb3 << 1)) | ((r >> 2) & kFoldLsb3);
             *key_out = len ? (g >> (3 * (kMaxSyms - len))) : 0ULL;
@@ -462,8 +464,8 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
         tick(1);
     };
 
-    s_lut[tid & 255] = lut_entry(tid & 255);
-    if (kThreads < 256) s_lut[(tid + kThreads) & 255] = lut_entry((tid + kThreads) & 255);
+    s_lut[tid & 255] = lut_entry(tid & 255, a.rule);
+    if (kThreads < 256) s_lut[(tid + kThreads) & 255] = lut_entry((tid + kThreads) & 255, a.rule);
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);

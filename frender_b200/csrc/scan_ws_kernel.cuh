@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     volatile unsigned long long* status = a.status + 1;
 
-    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i);
+    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, a.rule);
     if (tid == 0) {
         s_have_prefix[0] = 0, s_have_prefix[1] = 0;
 #pragma unroll
