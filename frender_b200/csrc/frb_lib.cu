@@ -338,8 +338,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.dbg_flags = getenv("FRB_DBG_FLAGS") ? atoi(getenv("FRB_DBG_FLAGS")) : 0;
     static unsigned long long* timing = nullptr;
     if (getenv("FRB_SCAN_TIMING")) {
-        if (!timing) cudaMalloc(&timing, 80);
-        cudaMemsetAsync(timing, 0, 80, c->compute);
+        if (!timing) cudaMalloc(&timing, 128);
+        cudaMemsetAsync(timing, 0, 128, c->compute);
         a.timing = timing;
     }
     {
@@ -365,17 +365,18 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     }
     CU(c, cudaGetLastError());
     if (a.timing) {
-        unsigned long long h[10];
+        unsigned long long h[16];
         cudaStreamSynchronize(c->compute);
-        cudaMemcpy(h, a.timing, 80, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, a.timing, 128, cudaMemcpyDeviceToHost);
         const char* names_std[9] = {"wait", "count", "lookback", "positions", "parse", "insert", "tile-end", "claim-bar", "issue"};
-        const char* names_ws[9] = {"C:wait-bytes", "C:count", "P:wait-counted", "P:lookback", "P:endsync", "P:early-lb", "P:finish-pending", "P:parse_header", "P:match+issue"};
+        const char* names_ws[9] = {"C:wait-bytes", "C:count", "X:wait-ready", "H:halo+lookback", "H:wait-counted", "H:wait-extractors", "X:finish-pending", "X:parse_header", "X:match"};
         const char** names = ws ? names_ws : names_std;
         double sum = 0;
         for (int i = 0; i < 9; ++i) sum += static_cast<double>(h[i]);
         const double tiles = h[9] ? static_cast<double>(h[9]) : 1.0;
         fprintf(stderr, "SCAN TIMING tiles %llu cycles/tile %.0f:", h[9], sum / tiles);
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.0f", names[i], (double)h[i] / tiles);
+        if (ws) fprintf(stderr, " X:endsync %.0f X:issue %.0f", (double)h[10] / tiles, (double)h[11] / tiles);
         fprintf(stderr, "\n");
     }
     return FRB_OK;

@@ -1,18 +1,19 @@
 // Warp-specialised form of the scan kernel (hot path A).  Same arithmetic, same results and the
 // same helpers as scan_kernel.cuh; the difference is the schedule inside a CTA.
 //
-//   warps 0-3  COUNTERS  for tile i: wait for its bytes (TMA mbarrier), 256 bytes per thread ->
-//                        newline mask, group scan, ordered newline-position list in shared memory,
-//                        publish the tile's newline count, signal `counted[stage]`.
-//                        Thread 0 also draws tile tickets and starts the bulk copy of tile i+2 as
-//                        soon as the parsers have released that stage.
-//   warps 4-7  PARSERS   for tile i: wait `counted[stage]`, look-back over the published counts
-//                        (line number of the tile's first newline), one thread per header line:
-//                        key extraction, warp fold, deferred table update; signal `free[stage]`.
+//   warps 0-3  COUNTERS    for tile i: wait for its bytes (TMA mbarrier), 256 bytes per thread ->
+//                          newline mask, group scan, ordered newline-position list in shared memory,
+//                          publish the tile's newline count, signal `counted[stage]`.
+//   warps 4-6  EXTRACTORS  for tile i: one thread per header line: key extraction, warp fold, deferred
+//                          table update; thread 0 then refills the stage (bulk copy of tile i+3).
+//   warp  7    HELPER      runs one tile ahead of the extractors: start of the line that straddles the
+//                          tile start, look-back over the published counts (line number of the tile's
+//                          first newline -- the only wait on other CTAs), ticket for the next refill.
 //
-// The two groups only meet through shared-memory mbarriers (full -> counted -> free per stage) and
-// synchronise internally with named barriers, so counting tile i+1 overlaps parsing tile i and a
-// parser that waits on another CTA's count never stops its own CTA's counters.
+// Counters and the parser side only meet through shared-memory mbarriers (full -> counted per stage);
+// helper and extractors meet once per tile at a named barrier.  Counting tile i+1, preparing tile i+1
+// and extracting tile i overlap, and a helper that waits on another CTA's count never stops its own
+// CTA's counters or extractors.
 #pragma once
 #include "scan_kernel.cuh"
 
@@ -58,8 +59,8 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __shared__ unsigned s_tile[kStages], s_total[kStages], s_valid[kStages], s_vnl[kStages];
     __shared__ unsigned s_cwarp[kWsGroup / 32];
     __shared__ unsigned long long s_prefix[2];
-    __shared__ unsigned s_have_prefix[2];
-    __shared__ unsigned s_halo_start;
+    __shared__ volatile unsigned long long s_ticket[2];
+    __shared__ unsigned s_halo_start[2];
     __shared__ unsigned char s_lut[256];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 
     for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, a.rule);
     if (tid == 0) {
-        s_have_prefix[0] = 0, s_have_prefix[1] = 0;
+        s_ticket[0] = ~0ULL, s_ticket[1] = ~0ULL;
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], 1);
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
         // =============================== PARSERS =================================================
         const int pt = tid - kWsGroup;
         const int pwarp = warp - kWsGroup / 32;
-        constexpr int kLast = kPWarps - 1;  // helper warp: halo scan, early look-back
+        constexpr int kLast = kPWarps - 1;  // helper warp: halo scan, look-back, tickets
         // deferred table update, three steps (see scan_kernel.cuh)
         unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
         unsigned p_cnt = 0;
@@ -247,13 +248,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 if (a.rec_off_out) a.rec_off_out[slot] = start_g;
             }
         };
-        // Tickets and bulk copies are driven by parser thread 0: a stage is refilled the moment the
-        // parsers are done with it, and the ticket for it was drawn one tile earlier.  The counters never
-        // wait for anything but bytes.
-        unsigned claimed = 0;
-        auto claim_next = [&]() { claimed = static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL)); };
-        auto issue = [&](int s) {  // ticket -> stage s, start its bulk copy
-            const unsigned t = claimed < a.n_tiles ? claimed : kNoTile;
+        // A stage is refilled the moment the extractors are done with it; the ticket for it was drawn
+        // by the helper warp a tile earlier.  The counters never wait for anything but bytes.
+        auto issue = [&](int s, unsigned ticket) {  // ticket -> stage s, start its bulk copy
+            const unsigned t = ticket < a.n_tiles ? ticket : kNoTile;
             s_tile[s] = t;
             if (t == kNoTile) {
                 mbar_arrive(&s_full[s]);
@@ -271,153 +269,159 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 mbar_arrive(&s_full[s]);
             }
         };
-        if (pt == 0) {
-            for (int s = 0; s < kStages; ++s) {
-                claim_next();
-                issue(s);
-            }
-            claim_next();
-        }
         unsigned counted_parity = 0;
-        unsigned long long my_reads = 0;
-        long long tm = (a.timing && pt == 0) ? clock64() : 0;
-        unsigned long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        auto tick = [&](int k) {
-            if (a.timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
-        };
-        for (unsigned i = 0;; ++i) {
-            const int s = i % kStages;
-            mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
-            counted_parity ^= 1u << s;
-            tick(0);
-            const unsigned t = s_tile[s];
-            if (t == kNoTile) break;
-            unsigned char* const buf = smem + s * kWsBuf;
-            const unsigned total = s_total[s], valid = s_valid[s], vnl = s_vnl[s];
-            const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
-            const uint16_t* const nl = s_nl + s * kWsNlCap;
-
-            if (pwarp == 0) {
-                if (!s_have_prefix[i & 1]) {  // the early attempt of the previous tile did not complete
+        if (pwarp == kLast) {
+            // ------------------------- helper warp: runs one tile ahead of the extractors -------------
+            // For tile i: start of the line that straddles the tile start (halo scan), line number of the
+            // tile's first newline (look-back, the only place a CTA waits on other CTAs), then the ticket
+            // for the refill of this tile's stage.  All of it overlaps the key extraction of tile i-1.
+            if (lane == 0) {
+                for (int s = 0; s < kStages; ++s) issue(s, static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL)));
+            }
+            long long tm = (a.timing && lane == 0) ? clock64() : 0;
+            unsigned long long h_wait = 0, h_look = 0, h_bar = 0;
+            auto htick = [&](unsigned long long& acc) {
+                if (a.timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
+            };
+            for (unsigned i = 0;; ++i) {
+                const int s = i % kStages;
+                mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
+                counted_parity ^= 1u << s;
+                htick(h_wait);
+                const unsigned t = s_tile[s];
+                if (t != kNoTile) {
+                    if (t == 0) {
+                        if (lane == 0) s_halo_start[i & 1] = kHalo;
+                    } else {
+                        const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(smem + s * kWsBuf)[lane]);
+                        const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+                        if (any == 0) {
+                            if (lane == 0) s_halo_start[i & 1] = kUnknown;
+                        } else if (lane == 31 - __clz(any)) {
+                            s_halo_start[i & 1] = lane * 16 + (31 - __clz(m)) + 1;
+                        }
+                    }
                     unsigned long long excl;
-                    tile_prefix<true>(status, t, total, lane, &excl);
+                    tile_prefix<true>(status, t, s_total[s], lane, &excl);
                     if (lane == 0) s_prefix[i & 1] = excl;
                 }
-            } else if (pwarp == kLast) {
-                if (t == 0) {
-                    if (lane == 0) s_halo_start = kHalo;
-                } else {
-                    const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane]);
-                    const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
-                    if (any == 0) {
-                        if (lane == 0) s_halo_start = kUnknown;
-                    } else if (lane == 31 - __clz(any)) {
-                        s_halo_start = lane * 16 + (31 - __clz(m)) + 1;
-                    }
+                htick(h_look);
+                group_sync<kPGroup>(2);  // tile i is prepared AND the extractors have finished tile i-1
+                htick(h_bar);
+                if (t == kNoTile) break;
+                if (lane == 0) {  // ticket for the refill at the end of tile i, tagged with i
+                    const unsigned long long ticket = atomicAdd(&a.status[0], 1ULL) & 0xFFFFFFFFULL;
+                    s_ticket[i & 1] = (static_cast<unsigned long long>(i) << 32) | ticket;
                 }
             }
-            group_sync<kPGroup>(2);
-            tick(1);
-            const unsigned long long K0 = L0 + s_prefix[i & 1];
-            const unsigned halo_start = s_halo_start;
-            const unsigned long long o_first = (K0 + 3) >> 2;
-            const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
-            const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
-            const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
-            // Look-back of the NEXT tile in the shadow of this tile's key extraction: only if its count
-            // is already in (non-blocking probe) and without ever waiting on another CTA.
-            if (pwarp == kLast) {
-                // this warp has no header lines in ordinary tiles: it keeps probing (bounded, never
-                // blocking on another CTA) while the other parser warps extract keys
-                const int sn = (i + 1) % kStages;
-                unsigned long long excl = 0;
-                bool ok = false;
-                const bool idle = n_owned <= static_cast<unsigned>(kPGroup - 32);
-                for (int attempt = 0; attempt < 1 && !ok; ++attempt) {
-                    if (mbar_test(&s_counted[sn], (counted_parity >> sn) & 1u)) {
-                        const unsigned tn = s_tile[sn];
-                        if (tn == kNoTile) break;
-                        ok = tile_prefix<false>(status, tn, s_total[sn], lane, &excl);
-                    }
-                    if (!ok && idle) __nanosleep(100);
-                }
-                if (lane == 0) s_prefix[(i + 1) & 1] = excl, s_have_prefix[(i + 1) & 1] = ok ? 1u : 0u;
+            if (a.timing && lane == 0) {
+                atomicAdd(&a.timing[3], h_look), atomicAdd(&a.timing[4], h_wait), atomicAdd(&a.timing[5], h_bar);
             }
-            tick(4);
-            if (n_owned == 0) finish_pending();
-            tick(5);
-            if (total + vnl <= static_cast<unsigned>(kWsNlCap)) {
+        } else {
+            // ------------------------- extractor warps -------------------------------------------------
+            constexpr int kExt = kPGroup - 32;
+            unsigned long long my_reads = 0;
+            long long tm = (a.timing && pt == 0) ? clock64() : 0;
+            unsigned long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            auto tick = [&](int k) {
+                if (a.timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
+            };
+            for (unsigned i = 0;; ++i) {
+                const int s = i % kStages;
+                group_sync<kPGroup>(2);
+                mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);  // complete already: the helper saw it
+                counted_parity ^= 1u << s;
+                tick(0);
+                const unsigned t = s_tile[s];
+                if (t == kNoTile) break;
+                unsigned char* const buf = smem + s * kWsBuf;
+                const unsigned total = s_total[s], valid = s_valid[s], vnl = s_vnl[s];
+                const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
+                const uint16_t* const nl = s_nl + s * kWsNlCap;
+                const unsigned long long K0 = L0 + s_prefix[i & 1];
+                const unsigned halo_start = s_halo_start[i & 1];
+                const unsigned long long o_first = (K0 + 3) >> 2;
+                const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
+                const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
+                const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
+                if (n_owned == 0) finish_pending();
+                if (total + vnl <= static_cast<unsigned>(kWsNlCap)) {
 #pragma unroll 1
-                for (unsigned h0 = 0; h0 < n_owned; h0 += kPGroup) {
-                    // table updates of the previous tile (or pass): issued here, far from the next
-                    // barrier, so that their atomics never stall one
-                    finish_pending();
-                    const unsigned h = h0 + pt;
-                    const unsigned long long o = o_first + h;
-                    bool have = (h < n_owned) && (o < a.read_limit);
-                    unsigned long long key = 0, start_g = 0;
-                    if (have) {
-                        const unsigned j = j0 + 4 * h;
-                        const unsigned sb = j ? nl[j - 1] + 1u : halo_start;
-                        const int rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
-                        if (rc) {
-                            raise_error(a.st, rc, o);
-                            have = false;
-                        }
-                    }
-                    const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
-                    tick(6);
-                    if (have) {
-                        const unsigned same = __match_any_sync(grp, key);
-                        if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
-                            p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
-                            p_slot = hash64(key) & a.table_mask;
-                            p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
-                        }
-                        emit(o, key, start_g);
-                    }
-                }
-            } else if (pt == 0) {
-                // more newlines than the list holds (lines < 16 bytes on average): exact but serial
-                unsigned long long k = K0;
-                unsigned prev = halo_start;
-                for (unsigned p = 0; p <= valid; ++p) {
-                    const bool is_end = (p < valid) ? (buf[kHalo + p] == '\n') : (vnl != 0);
-                    if (!is_end) continue;
-                    if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
+                    for (unsigned h0 = 0; h0 < n_owned; h0 += kExt) {
+                        // table updates of the previous tile (or pass): issued here, far from the next
+                        // barrier, so that their atomics never stall one
+                        finish_pending();
+                        tick(1);
+                        const unsigned h = h0 + pt;
+                        const unsigned long long o = o_first + h;
+                        bool have = (h < n_owned) && (o < a.read_limit);
                         unsigned long long key = 0, start_g = 0;
-                        const int rc = parse_header(buf, s_lut, prev, kHalo + p, a, tile_off, &key, &start_g);
-                        if (rc) raise_error(a.st, rc, k >> 2);
-                        else {
-                            if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
-                            emit(k >> 2, key, start_g);
+                        if (have) {
+                            const unsigned j = j0 + 4 * h;
+                            const unsigned sb = j ? nl[j - 1] + 1u : halo_start;
+                            const int rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
+                            if (rc) {
+                                raise_error(a.st, rc, o);
+                                have = false;
+                            }
                         }
+                        const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
+                        tick(6);
+                        if (have) {
+                            const unsigned same = __match_any_sync(grp, key);
+                            if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
+                                p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
+                                p_slot = hash64(key) & a.table_mask;
+                                p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
+                            }
+                            emit(o, key, start_g);
+                        }
+                        tick(7);
                     }
-                    prev = kHalo + p + 1;
-                    ++k;
+                } else if (pt == 0) {
+                    // more newlines than the list holds (lines < 16 bytes on average): exact but serial
+                    unsigned long long k = K0;
+                    unsigned prev = halo_start;
+                    for (unsigned p = 0; p <= valid; ++p) {
+                        const bool is_end = (p < valid) ? (buf[kHalo + p] == '\n') : (vnl != 0);
+                        if (!is_end) continue;
+                        if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
+                            unsigned long long key = 0, start_g = 0;
+                            const int rc = parse_header(buf, s_lut, prev, kHalo + p, a, tile_off, &key, &start_g);
+                            if (rc) raise_error(a.st, rc, k >> 2);
+                            else {
+                                if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
+                                emit(k >> 2, key, start_g);
+                            }
+                        }
+                        prev = kHalo + p + 1;
+                        ++k;
+                    }
                 }
+                group_sync<kExt>(3);  // every extractor is done reading stage s
+                tick(2);
+                if (pt == 0) {
+                    unsigned long long tk;
+                    do {
+                        tk = s_ticket[i & 1];
+                    } while (static_cast<unsigned>(tk >> 32) != i);
+                    issue(s, static_cast<unsigned>(tk));
+                    const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
+                    if (c_hi > o_first) my_reads += c_hi - o_first;
+                    if (t == a.n_tiles - 1) a.st->line_carry = K0 + total + vnl;
+                    tp[3] += 1;
+                }
+                tick(4);
             }
-            tick(7);
-            group_sync<kPGroup>(2);  // everyone is done reading stage s
-            tick(2);
-            if (pt == 0) {
-                issue(s);      // the stage is free: refill it with the ticket drawn one tile ago
-                claim_next();  // consumed one tile from now; the next barrier is a whole tile away
-                const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
-                if (c_hi > o_first) my_reads += c_hi - o_first;
-                if (t == a.n_tiles - 1) a.st->line_carry = K0 + total + vnl;
-                tp[3] += 1;
+            if (a.timing && pt == 0) {
+                atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[6], tp[1]), atomicAdd(&a.timing[7], tp[6]);
+                atomicAdd(&a.timing[8], tp[7]), atomicAdd(&a.timing[10], tp[2]), atomicAdd(&a.timing[11], tp[4]);
+                atomicAdd(&a.timing[9], tp[3]);
             }
-        }
-        if (a.timing && pt == 0) {
-            atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[3], tp[1]), atomicAdd(&a.timing[4], tp[2]);
-            atomicAdd(&a.timing[5], tp[4]), atomicAdd(&a.timing[6], tp[5]), atomicAdd(&a.timing[7], tp[6]);
-            atomicAdd(&a.timing[8], tp[7]);
-            atomicAdd(&a.timing[9], tp[3]);
+            if (pt == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
         }
 #pragma unroll 1
         for (int k = 0; k < 2; ++k) finish_pending();  // the second call retires a CAS issued by the first
-        if (pt == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
     }
 }
 
