@@ -26,6 +26,8 @@ struct DevState {
     unsigned long long scratch;     // generic counter (compaction)
     int err_code;                   // first FRB_ERR_* raised on the device, 0 if none
     int pad;
+    unsigned long long chunk_l0;    // lines before the chunk the scan kernel last ran on
+    unsigned long long redo_n;      // tiles of that chunk left to scan_redo_kernel
 };
 
 constexpr unsigned long long kEmpty = FRB_EMPTY_KEY;

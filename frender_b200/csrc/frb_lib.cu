@@ -55,6 +55,7 @@ struct frb_ctx {
     DevState* st = nullptr;
     DevState* st_host = nullptr;  // pinned mirror
     unsigned long long* status = nullptr;
+    unsigned int* redo = nullptr;  // tiles left to scan_redo_kernel (same capacity as status)
     size_t status_cap = 0;
     // host-chunk staging
     unsigned char* stage[kHostStages] = {nullptr, nullptr, nullptr};
@@ -315,6 +316,9 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         c->status_cap = 0;
         const size_t want = std::max<size_t>(n_tiles + 1, 1 << 16);
         CU(c, cudaMalloc(&c->status, want * 8));
+        if (c->redo) CU(c, cudaFree(c->redo));
+        c->redo = nullptr;
+        CU(c, cudaMalloc(&c->redo, want * 4));
         c->status_cap = want;
     }
     CU(c, cudaMemsetAsync(c->status, 0, (n_tiles + 1) * 8, c->compute));
@@ -335,6 +339,11 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.n_tiles = static_cast<unsigned>(n_tiles);
     a.rule = rule;
     a.no_tma = getenv("FRB_SCAN_NO_TMA") != nullptr;
+    static const bool no_guess = getenv("FRB_SCAN_NO_GUESS") != nullptr;
+    a.no_guess = no_guess;
+    a.redo = ws ? c->redo : nullptr;
+    a.tile_bytes = static_cast<unsigned>(tile);
+    if (a.redo) CU(c, cudaMemsetAsync(&c->st->redo_n, 0, 8, c->compute));
     a.dbg_flags = getenv("FRB_DBG_FLAGS") ? atoi(getenv("FRB_DBG_FLAGS")) : 0;
     static unsigned long long* timing = nullptr;
     if (getenv("FRB_SCAN_TIMING")) {
@@ -352,6 +361,10 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
                 const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsWide::ctas));
                 scan_ws_kernel<WsWide><<<grid, WsWide::threads, WsWide::smem, c->compute>>>(a);
             }
+            // tiles the kernel left out (empty list unless the input is not well-formed FASTQ or has
+            // lines shorter than 16 bytes on average)
+            scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
+            c->launches++;
         } else if (nt == 128) {
             using Cfg = ScanCfg<128>;
             const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
@@ -369,14 +382,14 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         cudaStreamSynchronize(c->compute);
         cudaMemcpy(h, a.timing, 128, cudaMemcpyDeviceToHost);
         const char* names_std[9] = {"wait", "count", "lookback", "positions", "parse", "insert", "tile-end", "claim-bar", "issue"};
-        const char* names_ws[9] = {"C:wait-bytes", "C:count", "X:wait-ready", "H:halo+lookback", "H:wait-counted", "H:wait-extractors", "X:finish-pending", "X:parse_header", "X:match"};
+        const char* names_ws[9] = {"C:wait-bytes", "C:count", "X:wait-counted", "K:lookback", "K:wait-batch", "X:phase", "K:commit", "X:parse_header", "X:send"};
         const char** names = ws ? names_ws : names_std;
         double sum = 0;
         for (int i = 0; i < 9; ++i) sum += static_cast<double>(h[i]);
         const double tiles = h[9] ? static_cast<double>(h[9]) : 1.0;
         fprintf(stderr, "SCAN TIMING tiles %llu cycles/tile %.0f:", h[9], sum / tiles);
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.0f", names[i], (double)h[i] / tiles);
-        if (ws) fprintf(stderr, " X:endsync %.0f X:issue %.0f", (double)h[10] / tiles, (double)h[11] / tiles);
+        if (ws) fprintf(stderr, " X:endsync+issue %.0f", (double)h[10] / tiles);
         fprintf(stderr, "\n");
     }
     return FRB_OK;
@@ -462,7 +475,7 @@ void frb_destroy(frb_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& f : c->files) free_list(c, f);
     free_list(c, c->total);
-    cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status);
+    cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status), cudaFree(c->redo);
     for (int i = 0; i < kHostStages; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]), cudaEventDestroy(c->stage_copied[i]), cudaEventDestroy(c->stage_done[i]);
         if (c->ring[i]) cudaFreeHost(c->ring[i]);

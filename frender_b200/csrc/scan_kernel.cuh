@@ -60,6 +60,9 @@ struct ScanArgs {
     unsigned long long* timing;  // optional: per-stage clock64 sums of thread 0 of every CTA
     int dbg_flags;  // experiments: 1 = no table update, 2 = no atomicMin, 4 = no parse
     int no_tma;     // debug / A-B: stage tiles with plain 16-byte loads instead of the bulk copy
+    unsigned int* redo;       // warp-specialised kernel: tiles left to scan_redo_kernel, capacity n_tiles
+    unsigned int tile_bytes;  // tile size of the kernel that filled status[] (for scan_redo_kernel)
+    int no_guess;             // A-B: never guess the line phase from the text
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy ------------------------------------------------

@@ -31,15 +31,16 @@ struct WsGeom {
     static constexpr int tile = kWsGroup * per_thread;
     static constexpr int buf = tile + kHalo;
     static constexpr int nl_cap = NLCAP;
-    static constexpr int pwarps = PW;
-    static constexpr int pgroup = PW * 32;
-    static constexpr int threads = kWsGroup + pgroup;
+    static constexpr int xwarps = PW;                        // extractor warps
+    static constexpr int xgroup = PW * 32;
+    static constexpr int threads = kWsGroup + xgroup + 32;  // + the committer warp
     static constexpr int ctas = CTAS;
-    static constexpr int maxreg = (65536 / (CTAS * threads)) / 8 * 8;  // per-thread budget that keeps CTAS resident
+    // per-thread register budget that keeps CTAS resident (registers are allocated per 4 warps)
+    static constexpr int maxreg = (65536 / (CTAS * ((threads + 127) / 128 * 128))) / 8 * 8;
     static constexpr int smem = kStages * buf + kStages * nl_cap * (int)sizeof(uint16_t);
 };
-using WsWide = WsGeom<16, 4, 2, 2048>;   // 32 KiB tiles, 2 x 8 warps per SM
-using WsDense = WsGeom<10, 3, 3, 1024>;  // 20 KiB tiles, 3 x 7 warps per SM
+using WsWide = WsGeom<16, 3, 2, 2048>;   // 32 KiB tiles, 2 x 8 warps per SM
+using WsDense = WsGeom<10, 2, 3, 1024>;  // 20 KiB tiles, 3 x 7 warps per SM (A-B variant)
 constexpr int kWsTile = WsWide::tile;
 constexpr int kWsThreads = WsWide::threads;
 constexpr int kWsSmem = WsWide::smem;
@@ -52,15 +53,21 @@ __device__ __forceinline__ void group_sync(int id) {
 template <class G>
 __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
     constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
-    constexpr int kPGroup = G::pgroup, kPWarps = G::pwarps;
+    constexpr int kExt = G::xgroup, kXWarps = G::xwarps;
+    constexpr int kBatches = 3;  // key batches in flight between the extractors and the committer
     extern __shared__ __align__(128) unsigned char smem[];
     uint16_t* const s_nl = reinterpret_cast<uint16_t*>(smem + kStages * kWsBuf);
     __shared__ __align__(8) unsigned long long s_full[kStages], s_counted[kStages];
     __shared__ unsigned s_tile[kStages], s_total[kStages], s_valid[kStages], s_vnl[kStages];
     __shared__ unsigned s_cwarp[kWsGroup / 32];
-    __shared__ unsigned long long s_prefix[2];
-    __shared__ volatile unsigned long long s_ticket[2];
-    __shared__ unsigned s_halo_start[2];
+    __shared__ unsigned s_halo[kStages];
+    __shared__ unsigned long long s_prefix[4];
+    __shared__ volatile unsigned s_ready[4];  // i + 1 once s_prefix[i & 3] holds the prefix of local tile i
+    __shared__ __align__(8) unsigned long long s_bfull[kBatches], s_bfree[kBatches];
+    __shared__ unsigned long long s_keys[kBatches][kExt];  // kEmpty except on the first lane of every run of equal keys
+    __shared__ unsigned char s_kcnt[kBatches][kExt];      // reads folded into that entry
+    __shared__ unsigned s_bmeta[kBatches][8];  // see BM_* below
+    __shared__ unsigned s_berr[kBatches][kXWarps];
     __shared__ unsigned char s_lut[256];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -71,11 +78,17 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 
     for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, a.rule);
     if (tid == 0) {
-        s_ticket[0] = ~0ULL, s_ticket[1] = ~0ULL;
+        s_ready[0] = 0, s_ready[1] = 0, s_ready[2] = 0, s_ready[3] = 0;
+        if (blockIdx.x == 0) a.st->chunk_l0 = L0;
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_counted[i], 1);
+        }
+#pragma unroll
+        for (int i = 0; i < kBatches; ++i) {
+            mbar_init(&s_bfull[i], kXWarps);
+            mbar_init(&s_bfree[i], 1);
         }
         mbar_fence_init();
     }
@@ -194,6 +207,19 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 }
                 if (ct == 0 && vnl && total < static_cast<unsigned>(kWsNlCap)) nl[total] = static_cast<uint16_t>(kHalo + valid);
             }
+            if (warp == 0) {  // start of the line that straddles the tile start (last newline of the halo)
+                if (t == 0) {
+                    if (lane == 0) s_halo[s] = kHalo;
+                } else {
+                    const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane]);
+                    const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+                    if (any == 0) {
+                        if (lane == 0) s_halo[s] = kUnknown;
+                    } else if (lane == 31 - __clz(any)) {
+                        s_halo[s] = lane * 16 + (31 - __clz(m)) + 1;
+                    }
+                }
+            }
             if (ct == 0) {
                 s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
                 status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
@@ -204,123 +230,90 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
         }
         if (a.timing && ct == 0) atomicAdd(&a.timing[0], t_wait), atomicAdd(&a.timing[1], t_work);
     } else {
-        // =============================== PARSERS =================================================
+        // =============================== EXTRACTORS + COMMITTER ====================================
+        // Batch descriptor words (s_bmeta): local tile index, global tile, first header index of the
+        // batch, entries, newlines in the tile, lines (newlines + unterminated last line), guessed j0,
+        // flags.
+        enum { BM_I, BM_T, BM_H0, BM_N, BM_TOTAL, BM_LINES, BM_J0, BM_FLAGS };
+        enum { BF_FIRST = 1, BF_GUESSED = 2, BF_NEED_PREFIX = 4, BF_DENSE = 8, BF_END = 16 };
         const int pt = tid - kWsGroup;
         const int pwarp = warp - kWsGroup / 32;
-        constexpr int kLast = kPWarps - 1;  // helper warp: halo scan, look-back, tickets
-        // deferred table update, three steps (see scan_kernel.cuh)
-        unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
-        unsigned p_cnt = 0;
-        unsigned long long q_key = 0, q_pos = 0, q_slot = 0, q_old = 0;
-        unsigned q_cnt = 0;
-        auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
-            atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
-            atomicMin(&a.table[slot].first, pos);
-        };
-        auto finish_pending = [&]() {
-            if (q_cnt) {
-                if (q_old == kEmpty) {
-                    atomicAdd(&a.st->occupied, 1ULL);
-                    bump(q_slot, q_cnt, q_pos);
-                } else if (q_old == q_key) {
-                    bump(q_slot, q_cnt, q_pos);
-                } else {
-                    table_add(a.table, a.table_mask, q_key, q_cnt, q_pos, &a.st->occupied, a.st);
-                }
-                q_cnt = 0;
-            }
-            if (p_cnt) {
-                if (p_seen == p_key) {
-                    bump(p_slot, p_cnt, p_pos);
-                } else if (p_seen == kEmpty) {
-                    q_key = p_key, q_pos = p_pos, q_slot = p_slot, q_cnt = p_cnt;
-                    q_old = atomicCAS(&a.table[p_slot].key, kEmpty, p_key);
-                } else {
-                    table_add(a.table, a.table_mask, p_key, p_cnt, p_pos, &a.st->occupied, a.st);
-                }
-                p_cnt = 0;
-            }
-        };
-        auto emit = [&](unsigned long long o, unsigned long long key, unsigned long long start_g) {
-            const unsigned long long slot = o - chunk_first_read;
-            if (slot < a.out_cap) {
-                if (a.keys_out) a.keys_out[slot] = key;
-                if (a.rec_off_out) a.rec_off_out[slot] = start_g;
-            }
-        };
-        // A stage is refilled the moment the extractors are done with it; the ticket for it was drawn
-        // by the helper warp a tile earlier.  The counters never wait for anything but bytes.
-        auto issue = [&](int s, unsigned ticket) {  // ticket -> stage s, start its bulk copy
-            const unsigned t = ticket < a.n_tiles ? ticket : kNoTile;
-            s_tile[s] = t;
-            if (t == kNoTile) {
-                mbar_arrive(&s_full[s]);
-                return;
-            }
-            const unsigned long long off = static_cast<unsigned long long>(t) * kWsTile;
-            const unsigned halo = t ? kHalo : 0;
-            const unsigned long long left = a.nbytes - off;
-            const unsigned avail = static_cast<unsigned>(left < kWsTile ? left : kWsTile) + halo;
-            const unsigned bulk = avail & ~15u;
-            if (bulk) {
-                mbar_expect_tx(&s_full[s], bulk);
-                bulk_g2s(smem + s * kWsBuf + (kHalo - halo), a.data + off - halo, bulk, &s_full[s]);
-            } else {
-                mbar_arrive(&s_full[s]);
-            }
-        };
         unsigned counted_parity = 0;
-        if (pwarp == kLast) {
-            // ------------------------- helper warp: runs one tile ahead of the extractors -------------
-            // For tile i: start of the line that straddles the tile start (halo scan), line number of the
-            // tile's first newline (look-back, the only place a CTA waits on other CTAs), then the ticket
-            // for the refill of this tile's stage.  All of it overlaps the key extraction of tile i-1.
-            if (lane == 0) {
+        if (pwarp < kXWarps) {
+            // ------------------------- extractor warps -------------------------------------------------
+            // Key extraction needs to know WHICH lines of the tile are header lines (line number mod 4) and
+            // nothing else from the look-back.  In well-formed FASTQ that shows in the tile itself (a line
+            // that starts with '@' whose second successor starts with '+' and fourth with '@' is a header
+            // line), so the extractors guess the phase from the text, extract, and hand the keys to the
+            // committer, which checks the guess against the newline count before anything reaches the
+            // table.  A wrong guess (input that is not well-formed FASTQ) sends the tile to
+            // scan_redo_kernel; without a confident guess the extractors ask the committer for the count
+            // first.  Either way every tile is tallied by line COUNT, exactly as F:161-169 does.
+            // The extractors issue no global atomics, so none of their barrier arrivals waits for one.
+            auto emit = [&](unsigned long long o, unsigned long long key, unsigned long long start_g) {
+                const unsigned long long slot = o - chunk_first_read;
+                if (slot < a.out_cap) {
+                    if (a.keys_out) a.keys_out[slot] = key;
+                    if (a.rec_off_out) a.rec_off_out[slot] = start_g;
+                }
+            };
+            auto issue = [&](int s, unsigned ticket) {  // ticket -> stage s, start its bulk copy
+                const unsigned t = ticket < a.n_tiles ? ticket : kNoTile;
+                s_tile[s] = t;
+                if (t == kNoTile) {
+                    mbar_arrive(&s_full[s]);
+                    return;
+                }
+                const unsigned long long off = static_cast<unsigned long long>(t) * kWsTile;
+                const unsigned halo = t ? kHalo : 0;
+                const unsigned long long left = a.nbytes - off;
+                const unsigned avail = static_cast<unsigned>(left < kWsTile ? left : kWsTile) + halo;
+                const unsigned bulk = avail & ~15u;
+                if (bulk) {
+                    mbar_expect_tx(&s_full[s], bulk);
+                    bulk_g2s(smem + s * kWsBuf + (kHalo - halo), a.data + off - halo, bulk, &s_full[s]);
+                } else {
+                    mbar_arrive(&s_full[s]);
+                }
+            };
+            const bool may_guess = !a.no_guess && !a.keys_out && !a.rec_off_out && a.read_limit == ~0ULL;
+            unsigned nb = 0;  // batches sent
+            // hand one batch to the committer: keys (kEmpty = none), first parse error, descriptor
+            auto send = [&](unsigned long long key, int rc, unsigned i, unsigned t, unsigned h0, unsigned n,
+                            unsigned total, unsigned lines, unsigned j0, unsigned flags) {
+                const unsigned b = nb % kBatches;
+                // fold equal keys of the warp: the lowest lane (lowest read ordinal) carries the count
+                unsigned cnt = 0;
+                if (n) {
+                    const unsigned grp = __ballot_sync(0xFFFFFFFFu, key != kEmpty);
+                    if (key != kEmpty) {
+                        const unsigned same = __match_any_sync(grp, key);
+                        if (lane == __ffs(same) - 1) cnt = __popc(same);
+                        else key = kEmpty;
+                    }
+                }
+                mbar_wait(&s_bfree[b], ((nb / kBatches) & 1u) ^ 1u);
+                if (n) s_keys[b][pt] = key, s_kcnt[b][pt] = static_cast<unsigned char>(cnt);
+                const unsigned e = __reduce_min_sync(0xFFFFFFFFu, rc ? ((static_cast<unsigned>(pt) << 8) | static_cast<unsigned>(-rc)) : 0xFFFFFFFFu);
+                if (lane == 0) s_berr[b][pwarp] = e;
+                if (pt == 0) {
+                    unsigned* m = s_bmeta[b];
+                    m[BM_I] = i, m[BM_T] = t, m[BM_H0] = h0, m[BM_N] = n, m[BM_TOTAL] = total, m[BM_LINES] = lines;
+                    m[BM_J0] = j0, m[BM_FLAGS] = flags;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_bfull[b]);
+                ++nb;
+            };
+            auto wait_prefix = [&](unsigned i) -> unsigned long long {
+                while (s_ready[i & 3] != i + 1) {}
+                __threadfence_block();
+                return L0 + *reinterpret_cast<volatile unsigned long long*>(&s_prefix[i & 3]);
+            };
+            unsigned long long next_ticket = 0;
+            if (pt == 0) {
                 for (int s = 0; s < kStages; ++s) issue(s, static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL)));
             }
-            long long tm = (a.timing && lane == 0) ? clock64() : 0;
-            unsigned long long h_wait = 0, h_look = 0, h_bar = 0;
-            auto htick = [&](unsigned long long& acc) {
-                if (a.timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
-            };
-            for (unsigned i = 0;; ++i) {
-                const int s = i % kStages;
-                mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
-                counted_parity ^= 1u << s;
-                htick(h_wait);
-                const unsigned t = s_tile[s];
-                if (t != kNoTile) {
-                    if (t == 0) {
-                        if (lane == 0) s_halo_start[i & 1] = kHalo;
-                    } else {
-                        const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(smem + s * kWsBuf)[lane]);
-                        const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
-                        if (any == 0) {
-                            if (lane == 0) s_halo_start[i & 1] = kUnknown;
-                        } else if (lane == 31 - __clz(any)) {
-                            s_halo_start[i & 1] = lane * 16 + (31 - __clz(m)) + 1;
-                        }
-                    }
-                    unsigned long long excl;
-                    tile_prefix<true>(status, t, s_total[s], lane, &excl);
-                    if (lane == 0) s_prefix[i & 1] = excl;
-                }
-                htick(h_look);
-                group_sync<kPGroup>(2);  // tile i is prepared AND the extractors have finished tile i-1
-                htick(h_bar);
-                if (t == kNoTile) break;
-                if (lane == 0) {  // ticket for the refill at the end of tile i, tagged with i
-                    const unsigned long long ticket = atomicAdd(&a.status[0], 1ULL) & 0xFFFFFFFFULL;
-                    s_ticket[i & 1] = (static_cast<unsigned long long>(i) << 32) | ticket;
-                }
-            }
-            if (a.timing && lane == 0) {
-                atomicAdd(&a.timing[3], h_look), atomicAdd(&a.timing[4], h_wait), atomicAdd(&a.timing[5], h_bar);
-            }
-        } else {
-            // ------------------------- extractor warps -------------------------------------------------
-            constexpr int kExt = kPGroup - 32;
-            unsigned long long my_reads = 0;
             long long tm = (a.timing && pt == 0) ? clock64() : 0;
             unsigned long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             auto tick = [&](int k) {
@@ -328,100 +321,244 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             };
             for (unsigned i = 0;; ++i) {
                 const int s = i % kStages;
-                group_sync<kPGroup>(2);
-                mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);  // complete already: the helper saw it
+                mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
                 counted_parity ^= 1u << s;
                 tick(0);
                 const unsigned t = s_tile[s];
-                if (t == kNoTile) break;
+                if (t == kNoTile) {
+                    send(0, 0, i, t, 0, 0, 0, 0, 0, BF_END);
+                    break;
+                }
+                if (pt == 0) {  // ticket for the refill at the end of this tile; its round trip hides here
+                    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(next_ticket) : "l"(a.status) : "memory");
+                }
                 unsigned char* const buf = smem + s * kWsBuf;
-                const unsigned total = s_total[s], valid = s_valid[s], vnl = s_vnl[s];
+                const unsigned total = s_total[s], vnl = s_vnl[s];
+                const unsigned lines = total + vnl;
+                const unsigned halo_start = s_halo[s];
                 const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
                 const uint16_t* const nl = s_nl + s * kWsNlCap;
-                const unsigned long long K0 = L0 + s_prefix[i & 1];
-                const unsigned halo_start = s_halo_start[i & 1];
-                const unsigned long long o_first = (K0 + 3) >> 2;
-                const unsigned long long o_end = (K0 + total + vnl + 3) >> 2;
-                const unsigned n_owned = static_cast<unsigned>(o_end - o_first);
-                const unsigned j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
-                if (n_owned == 0) finish_pending();
-                if (total + vnl <= static_cast<unsigned>(kWsNlCap)) {
+                if (lines > static_cast<unsigned>(kWsNlCap)) {
+                    // more newlines than the list holds (lines < 16 bytes on average): scan_redo_kernel
+                    send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_DENSE);
+                } else {
+                    // ---- which list entries end header lines? ----
+                    bool guessed = false;
+                    unsigned j0 = 0;
+                    if (may_guess && total >= 9 && halo_start != kUnknown) {
+                        unsigned first[8];  // first byte of the tile's lines 0..7
+                        first[0] = buf[halo_start];
+#pragma unroll
+                        for (int c = 1; c < 8; ++c) first[c] = buf[nl[c - 1] + 1u];
+                        unsigned hits = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (first[c] == '@' && first[c + 2] == '+' && first[c + 4] == '@') hits |= 1u << c;
+                        }
+                        if (__popc(hits) == 1) guessed = true, j0 = __ffs(hits) - 1;
+                    }
+                    unsigned long long of = 0;  // first read ordinal owned by the tile (known if !guessed)
+                    unsigned flags = BF_FIRST | (guessed ? BF_GUESSED : 0u);
+                    if (!guessed) {
+                        send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_NEED_PREFIX);
+                        const unsigned long long K0 = wait_prefix(i);
+                        j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
+                        of = (K0 + 3) >> 2;
+                        flags = 0;
+                    }
+                    const unsigned n_owned = lines > j0 ? (lines - j0 + 3) / 4 : 0;
+                    tick(1);
 #pragma unroll 1
                     for (unsigned h0 = 0; h0 < n_owned; h0 += kExt) {
-                        // table updates of the previous tile (or pass): issued here, far from the next
-                        // barrier, so that their atomics never stall one
-                        finish_pending();
-                        tick(1);
                         const unsigned h = h0 + pt;
-                        const unsigned long long o = o_first + h;
-                        bool have = (h < n_owned) && (o < a.read_limit);
-                        unsigned long long key = 0, start_g = 0;
+                        bool have = h < n_owned && (guessed || of + h < a.read_limit);
+                        unsigned long long key = kEmpty, start_g = 0;
+                        int rc = 0;
                         if (have) {
                             const unsigned j = j0 + 4 * h;
                             const unsigned sb = j ? nl[j - 1] + 1u : halo_start;
-                            const int rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
-                            if (rc) {
-                                raise_error(a.st, rc, o);
-                                have = false;
-                            }
+                            rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
+                            if (rc) key = kEmpty;
+                            else if (!guessed) emit(of + h, key, start_g);
                         }
-                        const unsigned grp = __ballot_sync(0xFFFFFFFFu, have);
                         tick(6);
-                        if (have) {
-                            const unsigned same = __match_any_sync(grp, key);
-                            if (a.table && lane == __ffs(same) - 1) {  // lowest lane = lowest read ordinal
-                                p_key = key, p_pos = a.pos_base + o, p_cnt = __popc(same);
-                                p_slot = hash64(key) & a.table_mask;
-                                p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
-                            }
-                            emit(o, key, start_g);
-                        }
+                        const unsigned n = n_owned - h0 < static_cast<unsigned>(kExt) ? n_owned - h0 : kExt;
+                        send(key, rc, i, t, h0, n, total, lines, j0, flags);
+                        flags &= ~static_cast<unsigned>(BF_FIRST);
                         tick(7);
-                    }
-                } else if (pt == 0) {
-                    // more newlines than the list holds (lines < 16 bytes on average): exact but serial
-                    unsigned long long k = K0;
-                    unsigned prev = halo_start;
-                    for (unsigned p = 0; p <= valid; ++p) {
-                        const bool is_end = (p < valid) ? (buf[kHalo + p] == '\n') : (vnl != 0);
-                        if (!is_end) continue;
-                        if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
-                            unsigned long long key = 0, start_g = 0;
-                            const int rc = parse_header(buf, s_lut, prev, kHalo + p, a, tile_off, &key, &start_g);
-                            if (rc) raise_error(a.st, rc, k >> 2);
-                            else {
-                                if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
-                                emit(k >> 2, key, start_g);
-                            }
-                        }
-                        prev = kHalo + p + 1;
-                        ++k;
                     }
                 }
                 group_sync<kExt>(3);  // every extractor is done reading stage s
-                tick(2);
                 if (pt == 0) {
-                    unsigned long long tk;
-                    do {
-                        tk = s_ticket[i & 1];
-                    } while (static_cast<unsigned>(tk >> 32) != i);
-                    issue(s, static_cast<unsigned>(tk));
-                    const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
-                    if (c_hi > o_first) my_reads += c_hi - o_first;
-                    if (t == a.n_tiles - 1) a.st->line_carry = K0 + total + vnl;
+                    issue(s, static_cast<unsigned>(next_ticket));
                     tp[3] += 1;
                 }
-                tick(4);
+                tick(2);
             }
             if (a.timing && pt == 0) {
-                atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[6], tp[1]), atomicAdd(&a.timing[7], tp[6]);
-                atomicAdd(&a.timing[8], tp[7]), atomicAdd(&a.timing[10], tp[2]), atomicAdd(&a.timing[11], tp[4]);
+                atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[5], tp[1]), atomicAdd(&a.timing[7], tp[6]);
+                atomicAdd(&a.timing[8], tp[7]), atomicAdd(&a.timing[10], tp[2]);
                 atomicAdd(&a.timing[9], tp[3]);
             }
-            if (pt == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
-        }
+        } else {
+            // ------------------------- committer warp --------------------------------------------------
+            // Per tile: look-back over the published counts (the only place a CTA waits on other CTAs),
+            // check of the extractors' guess, bookkeeping; per batch: fold equal keys, update the table.
+            // Table updates are deferred in three steps -- slot load, then RED or CAS one batch later,
+            // then the RED after a CAS one batch after that -- so no L2 round trip is waited for in line.
+            constexpr int kRounds = kExt / 32;
+            unsigned long long p_key[kRounds], p_pos[kRounds], p_slot[kRounds], p_seen[kRounds];
+            unsigned long long q_key[kRounds], q_pos[kRounds], q_slot[kRounds], q_old[kRounds];
+            unsigned p_cnt[kRounds], q_cnt[kRounds];
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) p_cnt[r] = 0, q_cnt[r] = 0;
+            auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
+                atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
+                atomicMin(&a.table[slot].first, pos);
+            };
+            auto finish = [&](int r) {
+                if (q_cnt[r]) {
+                    if (q_old[r] == kEmpty) {
+                        atomicAdd(&a.st->occupied, 1ULL);
+                        bump(q_slot[r], q_cnt[r], q_pos[r]);
+                    } else if (q_old[r] == q_key[r]) {
+                        bump(q_slot[r], q_cnt[r], q_pos[r]);
+                    } else {
+                        table_add(a.table, a.table_mask, q_key[r], q_cnt[r], q_pos[r], &a.st->occupied, a.st);
+                    }
+                    q_cnt[r] = 0;
+                }
+                if (p_cnt[r]) {
+                    if (p_seen[r] == p_key[r]) {
+                        bump(p_slot[r], p_cnt[r], p_pos[r]);
+                    } else if (p_seen[r] == kEmpty) {
+                        q_key[r] = p_key[r], q_pos[r] = p_pos[r], q_slot[r] = p_slot[r], q_cnt[r] = p_cnt[r];
+                        q_old[r] = atomicCAS(&a.table[p_slot[r]].key, kEmpty, p_key[r]);
+                    } else {
+                        table_add(a.table, a.table_mask, p_key[r], p_cnt[r], p_pos[r], &a.st->occupied, a.st);
+                    }
+                    p_cnt[r] = 0;
+                }
+            };
+            unsigned long long my_reads = 0, of = 0;
+            bool tile_ok = false;
+            long long tm = (a.timing && lane == 0) ? clock64() : 0;
+            unsigned long long k_wait = 0, k_look = 0, k_commit = 0;
+            auto ktick = [&](unsigned long long& acc) {
+                if (a.timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
+            };
+            for (unsigned nb = 0;; ++nb) {
+                const unsigned b = nb % kBatches;
+                mbar_wait(&s_bfull[b], (nb / kBatches) & 1u);
+                ktick(k_wait);
+                const unsigned* m = s_bmeta[b];
+                const unsigned flags = m[BM_FLAGS];
+                if (flags & BF_END) break;
+                const unsigned i = m[BM_I], t = m[BM_T], h0 = m[BM_H0], n = m[BM_N];
+                if (flags & BF_FIRST) {
+                    unsigned long long excl;
+                    tile_prefix<true>(status, t, m[BM_TOTAL], lane, &excl);
+                    const unsigned long long K0 = L0 + excl;
+                    of = (K0 + 3) >> 2;
+                    tile_ok = !(flags & BF_DENSE) &&
+                              (!(flags & BF_GUESSED) || static_cast<unsigned>((4 - (K0 & 3)) & 3) == m[BM_J0]);
+                    if (lane == 0) {
+                        s_prefix[i & 3] = excl;
+                        __threadfence_block();
+                        s_ready[i & 3] = i + 1;
+                        if (tile_ok) {
+                            const unsigned long long o_end = (K0 + m[BM_LINES] + 3) >> 2;
+                            const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
+                            if (c_hi > of) my_reads += c_hi - of;
+                            if (t == a.n_tiles - 1) a.st->line_carry = K0 + m[BM_LINES];
+                        } else {
+                            a.redo[atomicAdd(&a.st->redo_n, 1ULL)] = t;
+                        }
+                    }
+                    ktick(k_look);
+                }
+                unsigned long long key[kRounds];
+                unsigned cnt[kRounds];
+#pragma unroll
+                for (int r = 0; r < kRounds; ++r) {
+                    const unsigned idx = r * 32 + lane;
+                    key[r] = (tile_ok && idx < n) ? s_keys[b][idx] : kEmpty;
+                    cnt[r] = s_kcnt[b][idx];
+                }
+                unsigned err = 0xFFFFFFFFu;
+#pragma unroll
+                for (int w = 0; w < kXWarps; ++w) err = min(err, s_berr[b][w]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_bfree[b]);  // the batch is in registers
+                if (tile_ok && n && err != 0xFFFFFFFFu && lane == 0)
+                    raise_error(a.st, -static_cast<int>(err & 0xFFu), of + h0 + (err >> 8));
+                if (a.table) {
+#pragma unroll
+                    for (int r = 0; r < kRounds; ++r) {
+                        finish(r);  // the sets of the previous batch (their slot loads are long back)
+                        if (key[r] != kEmpty) {
+                            p_key[r] = key[r], p_pos[r] = a.pos_base + of + h0 + r * 32 + lane, p_cnt[r] = cnt[r];
+                            p_slot[r] = hash64(key[r]) & a.table_mask;
+                            p_seen[r] = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot[r]].key);
+                        }
+                    }
+                }
+                ktick(k_commit);
+            }
 #pragma unroll 1
-        for (int k = 0; k < 2; ++k) finish_pending();  // the second call retires a CAS issued by the first
+            for (int k = 0; k < 2; ++k) {  // the second pass retires a CAS issued by the first
+#pragma unroll
+                for (int r = 0; r < kRounds; ++r) finish(r);
+            }
+            if (lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
+            if (a.timing && lane == 0) {
+                atomicAdd(&a.timing[3], k_look), atomicAdd(&a.timing[4], k_wait), atomicAdd(&a.timing[6], k_commit);
+            }
+        }
+    }
+}
+
+// Tiles the warp-specialised kernel left out -- a guessed line phase that turned out wrong (input that is
+// not well-formed FASTQ), or more newlines than a tile's position list holds -- tallied strictly by line
+// count, one thread per tile, from the bytes in global memory.  status[] holds every tile's inclusive
+// newline prefix by now.  Slow and exact; the list is empty for ordinary input.
+__global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
+    const unsigned long long n = a.st->redo_n;
+    const unsigned long long L0 = a.st->chunk_l0;
+    const unsigned long long chunk_first_read = (L0 + 3) >> 2;
+    for (unsigned long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const unsigned t = a.redo[idx];
+        const unsigned long long off = static_cast<unsigned long long>(t) * a.tile_bytes;
+        const unsigned long long end = off + a.tile_bytes < a.nbytes ? off + a.tile_bytes : a.nbytes;
+        unsigned long long k = L0 + (t ? (a.status[t] & kValMask) : 0ULL);  // a.status[1 + (t - 1)]
+        unsigned long long prev = off;
+        while (prev > 0 && a.data[prev - 1] != '\n') --prev;
+        const bool vnl = t == a.n_tiles - 1 && end > off && a.data[end - 1] != '\n';
+        unsigned long long reads = 0;
+        for (unsigned long long p = off; p <= end; ++p) {
+            const bool is_end = p < end ? a.data[p] == '\n' : vnl;
+            if (!is_end) continue;
+            if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
+                unsigned long long key = 0;
+                const int rc = a.rule == kRuleOffsetsOnly ? 0 : parse_serial(a.data + prev, p - prev, a.rule, &key);
+                ++reads;
+                if (rc) {
+                    raise_error(a.st, rc, k >> 2);
+                } else {
+                    if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
+                    const unsigned long long slot = (k >> 2) - chunk_first_read;
+                    if (slot < a.out_cap) {
+                        if (a.keys_out) a.keys_out[slot] = key;
+                        if (a.rec_off_out) a.rec_off_out[slot] = prev;
+                    }
+                }
+            }
+            prev = p + 1;
+            ++k;
+        }
+        if (reads) atomicAdd(&a.st->n_reads, reads);
+        if (t == a.n_tiles - 1) a.st->line_carry = k;
     }
 }
 

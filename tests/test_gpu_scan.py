@@ -170,6 +170,37 @@ def test_short_lines_serial_fallback(ctx):
         assert list(ctx.counter()["total"].items()) == list(want.items())
 
 
+def test_line_phase_is_by_count_not_by_content(ctx):
+    """The kernel guesses which lines are headers from the text ('@' ... '+' ... '@') and checks the guess
+    against the newline count before anything reaches the table.  Here the text says one thing and the
+    count another (F:161-169 takes every 4th line, whatever it looks like): the result must follow the
+    count."""
+    import random
+
+    import frender_oracle as O
+    rnd = random.Random(11)
+    keys = ["".join(rnd.choice("ACGT") for _ in range(8)) for _ in range(50)]
+    # by count the headers are the '@r' lines; by content ('@', then '+' two lines on) the '@q' lines
+    recs = "".join(f"@r{i} 1:N:0:{rnd.choice(keys)}\n@q{i} 1:N:0:{rnd.choice(keys)}\n{'ACGT' * 30}\n+{'F' * 100}\n"
+                   for i in range(30000))
+    want, visited = O.tally_text(recs.splitlines(keepends=True))
+    for chunk in (None, 1 << 20):
+        ctx.reset()
+        reads, uniq = ctx.scan_bytes(recs.encode(), chunk=chunk)
+        assert reads == visited == 30000 and uniq == len(want)
+        assert list(ctx.counter()["total"].items()) == list(want.items())
+    # and a file that only goes wrong half way: a stray line shifts the phase of everything after it
+    good = "".join(f"@r{i} 1:N:0:{rnd.choice(keys)}\n{'ACGT' * 30}\n+\n{'F' * 120}\n" for i in range(20000))
+    lines = good.splitlines(keepends=True)
+    shifted = "".join(lines[:40000]) + "@x 1:N:0:ACGTACGT\n" + "".join(
+        f"@s{i} 1:N:0:{rnd.choice(keys)}\n{'ACGT' * 30}\n+\n@t{i} 1:N:0:{rnd.choice(keys)}\n" for i in range(15000))
+    want, visited = O.tally_text(shifted.splitlines(keepends=True))
+    ctx.reset()
+    reads, uniq = ctx.scan_bytes(shifted.encode())
+    assert reads == visited and uniq == len(want)
+    assert list(ctx.counter()["total"].items()) == list(want.items())
+
+
 def test_single_index_c5(ctx, tmp_path):
     """Config 5 shape: 6 bp single index.  The tally is pinned by the oracle (the reference can run it,
     F:154-207); the matcher for single-index sheets is an extension (the reference cannot: F:104-107,
