@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * G::seg;
             if constexpr (G::seg == 16) {
                 unsigned long long m00 = 0, m01 = 0, m10 = 0, m11 = 0;
-#pragma unroll
+                // two iterations in flight: four 16-byte loads outstanding, a quarter of the code of the
+                // fully unrolled loop (the kernel's three roles share one instruction cache)
+#pragma unroll 2
                 for (int j = 0; j < 8; ++j) {
                     const int r = (j + ct) & 7;
                     const unsigned long long ma = newline_mask16(t4[r]);
@@ -411,34 +413,52 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             unsigned long long q_key[kRounds], q_pos[kRounds], q_slot[kRounds], q_old[kRounds];
             unsigned p_cnt[kRounds], q_cnt[kRounds];
 #pragma unroll
-            for (int r = 0; r < kRounds; ++r) p_cnt[r] = 0, q_cnt[r] = 0;
+            for (int r = 0; r < kRounds; ++r) p_cnt[r] = 0, q_cnt[r] = 0, q_slot[r] = 0, q_key[r] = 0, q_old[r] = 0;
             auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
                 atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
                 atomicMin(&a.table[slot].first, pos);
             };
+            // Step 2/3 of a set: q holds a key whose slot looked free (compare-and-swap issued, q_old = its
+            // result) or taken by another key (next slot's key requested, q_old = that key).  Only a second
+            // mismatch falls back to the in-line probe loop, whose loads are L2 round trips.
+            bool q_cas[kRounds];
+            unsigned long long my_occ = 0;
             auto finish = [&](int r) {
                 if (q_cnt[r]) {
-                    if (q_old[r] == kEmpty) {
-                        atomicAdd(&a.st->occupied, 1ULL);
-                        bump(q_slot[r], q_cnt[r], q_pos[r]);
-                    } else if (q_old[r] == q_key[r]) {
+                    if (q_old[r] == q_key[r] || (q_cas[r] && q_old[r] == kEmpty)) {
+                        if (q_old[r] == kEmpty) ++my_occ;
                         bump(q_slot[r], q_cnt[r], q_pos[r]);
                     } else {
                         table_add(a.table, a.table_mask, q_key[r], q_cnt[r], q_pos[r], &a.st->occupied, a.st);
                     }
                     q_cnt[r] = 0;
                 }
+                const bool claim = p_cnt[r] && p_seen[r] == kEmpty;                           // free slot: take it
+                const bool reprobe = p_cnt[r] && p_seen[r] != kEmpty && p_seen[r] != p_key[r];  // other key: next slot
                 if (p_cnt[r]) {
                     if (p_seen[r] == p_key[r]) {
                         bump(p_slot[r], p_cnt[r], p_pos[r]);
-                    } else if (p_seen[r] == kEmpty) {
-                        q_key[r] = p_key[r], q_pos[r] = p_pos[r], q_slot[r] = p_slot[r], q_cnt[r] = p_cnt[r];
-                        q_old[r] = atomicCAS(&a.table[p_slot[r]].key, kEmpty, p_key[r]);
                     } else {
-                        table_add(a.table, a.table_mask, p_key[r], p_cnt[r], p_pos[r], &a.st->occupied, a.st);
+                        q_key[r] = p_key[r], q_pos[r] = p_pos[r], q_cnt[r] = p_cnt[r], q_cas[r] = claim;
+                        q_slot[r] = claim ? p_slot[r] : ((p_slot[r] + 1) & a.table_mask);
                     }
                     p_cnt[r] = 0;
                 }
+                // Both requests are predicated INSIDE the asm statement with q_old as in/out operand (for
+                // the compare-and-swap also as the compare value, preset to kEmpty: the SASS instruction
+                // returns the old value in the compare register).  Written as `if (..) q_old = atomicCAS(..)`
+                // the compiler lands the result in a scratch register and copies it at the join, which
+                // waits out the L2 round trip on the spot.
+                if (claim) q_old[r] = kEmpty;
+                asm volatile(
+                    "{\n\t.reg .pred p, q;\n\t"
+                    "setp.ne.u32 p, %3, 0;\n\t"
+                    "setp.ne.u32 q, %4, 0;\n\t"
+                    "@p atom.global.cas.b64 %0, [%1], %0, %2;\n\t"
+                    "@q ld.volatile.global.u64 %0, [%1];\n\t}"
+                    : "+l"(q_old[r])
+                    : "l"(&a.table[q_slot[r] & a.table_mask].key), "l"(q_key[r]), "r"(claim ? 1u : 0u), "r"(reprobe ? 1u : 0u)
+                    : "memory");
             };
             unsigned long long my_reads = 0, of = 0;
             bool tile_ok = false;
@@ -511,6 +531,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 for (int r = 0; r < kRounds; ++r) finish(r);
             }
             if (lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
+            if (my_occ) atomicAdd(&a.st->occupied, my_occ);
             if (a.timing && lane == 0) {
                 atomicAdd(&a.timing[3], k_look), atomicAdd(&a.timing[4], k_wait), atomicAdd(&a.timing[6], k_commit);
             }
