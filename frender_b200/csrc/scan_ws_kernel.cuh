@@ -197,15 +197,30 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 uint16_t* const nl = s_nl + s * kWsNlCap;
                 unsigned idx = wbase + incl - cnt;
                 unsigned pos0 = kHalo + ct * kWsPerThread;
+                // A list that does not fit is never read (the tile goes to scan_redo_kernel), so one range
+                // check per thread is enough.  Straight-line code for the first two newlines of a 32-byte
+                // word -- a third one means lines shorter than 16 bytes -- keeps the warp out of a
+                // data-dependent loop.
+                if (wbase + incl <= static_cast<unsigned>(kWsNlCap)) {
 #pragma unroll
-                for (int q = 0; q < kWords; ++q) {
-                    unsigned m = w[q];
-                    while (m) {
-                        if (idx < static_cast<unsigned>(kWsNlCap)) nl[idx] = static_cast<uint16_t>(pos0 + (__ffs(m) - 1));
-                        m &= m - 1;
-                        ++idx;
+                    for (int q = 0; q < kWords; ++q) {
+                        const unsigned m = w[q];
+                        if (m) {
+                            nl[idx] = static_cast<uint16_t>(pos0 + (__ffs(m) - 1));
+                            unsigned m2 = m & (m - 1);
+                            if (m2) {
+                                nl[idx + 1] = static_cast<uint16_t>(pos0 + (__ffs(m2) - 1));
+                                m2 &= m2 - 1;
+                                unsigned k = idx + 2;
+                                while (m2) {
+                                    nl[k++] = static_cast<uint16_t>(pos0 + (__ffs(m2) - 1));
+                                    m2 &= m2 - 1;
+                                }
+                            }
+                            idx += __popc(m);
+                        }
+                        pos0 += 32;
                     }
-                    pos0 += 32;
                 }
                 if (ct == 0 && vnl && total < static_cast<unsigned>(kWsNlCap)) nl[total] = static_cast<uint16_t>(kHalo + valid);
             }
