@@ -306,7 +306,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     // default: warp-specialised kernel; FRB_SCAN_KERNEL=std selects the barrier-synchronous pipeline
     static const bool ws = getenv("FRB_SCAN_KERNEL") ? strcmp(getenv("FRB_SCAN_KERNEL"), "std") != 0 : true;
     static const bool dense = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "dense") == 0 : false;
-    const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : WsWide::tile)
+    static const bool tall = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "tall") == 0 : false;
+    const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : tall ? WsTall::tile : WsWide::tile)
                                                    : (nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile));
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
@@ -354,7 +355,10 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     {
         ProfScope ps(c, FRB_K_SCAN);
         if (ws) {
-            if (dense) {
+            if (tall) {
+                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTall::ctas));
+                scan_ws_kernel<WsTall><<<grid, WsTall::threads, WsTall::smem, c->compute>>>(a);
+            } else if (dense) {
                 const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsDense::ctas));
                 scan_ws_kernel<WsDense><<<grid, WsDense::threads, WsDense::smem, c->compute>>>(a);
             } else {
@@ -462,6 +466,7 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaFuncSetAttribute(scan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<128>::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsWide::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsDense::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTall>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTall::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TRY(clear_table(c, c->total_tab));
     CU(c, cudaStreamSynchronize(c->compute));

@@ -24,8 +24,9 @@ constexpr unsigned kNoTile = 0xFFFFFFFFu;
 
 // Tile geometry.  SEG = 16-byte segments per counter thread, PW = parser warps, CTAS = resident CTAs
 // per SM the shared memory and registers are budgeted for.
-template <int SEG, int PW, int CTAS, int NLCAP>
+template <int SEG, int PW, int CTAS, int NLCAP, int STAGES = kStages>
 struct WsGeom {
+    static constexpr int stages = STAGES;
     static constexpr int seg = SEG;
     static constexpr int per_thread = SEG * 16;
     static constexpr int tile = kWsGroup * per_thread;
@@ -37,10 +38,11 @@ struct WsGeom {
     static constexpr int ctas = CTAS;
     // per-thread register budget that keeps CTAS resident (registers are allocated per 4 warps)
     static constexpr int maxreg = (65536 / (CTAS * ((threads + 127) / 128 * 128))) / 8 * 8;
-    static constexpr int smem = kStages * buf + kStages * nl_cap * (int)sizeof(uint16_t);
+    static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
 using WsWide = WsGeom<16, 3, 2, 2048>;   // 32 KiB tiles, 2 x 8 warps per SM
 using WsDense = WsGeom<10, 2, 3, 1024>;  // 20 KiB tiles, 3 x 7 warps per SM (A-B variant)
+using WsTall = WsGeom<24, 3, 2, 3072, 2>;  // 48 KiB tiles, two stages (A-B variant)
 constexpr int kWsTile = WsWide::tile;
 constexpr int kWsThreads = WsWide::threads;
 constexpr int kWsSmem = WsWide::smem;
@@ -52,6 +54,7 @@ __device__ __forceinline__ void group_sync(int id) {
 
 template <class G>
 __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
+    constexpr int kStages = G::stages;
     constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
     constexpr int kExt = G::xgroup, kXWarps = G::xwarps;
     constexpr int kBatches = 3;  // key batches in flight between the extractors and the committer
@@ -129,23 +132,31 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             constexpr int kWords = kWsPerThread / 32;
             unsigned w[kWords];
             const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * G::seg;
-            if constexpr (G::seg == 16) {
-                unsigned long long m00 = 0, m01 = 0, m10 = 0, m11 = 0;
-                // two iterations in flight: four 16-byte loads outstanding, a quarter of the code of the
-                // fully unrolled loop (the kernel's three roles share one instruction cache)
+            if constexpr (G::seg % 8 == 0) {
+                // thread stride is a multiple of 128 bytes: within every group of 8 segments lane l starts at
+                // segment l & 7, so the eight lanes of a load phase hit eight different bank groups
+                constexpr int kGroups = G::seg / 8;
+                unsigned long long mlo[kGroups], mhi[kGroups];
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) mlo[g] = 0, mhi[g] = 0;
+                // two iterations in flight; a fraction of the code of the fully unrolled loop (the kernel's
+                // three roles share one instruction cache)
 #pragma unroll 2
                 for (int j = 0; j < 8; ++j) {
                     const int r = (j + ct) & 7;
-                    const unsigned long long ma = newline_mask16(t4[r]);
-                    const unsigned long long mb = newline_mask16(t4[8 + r]);
                     const int sh = (r & 3) * 16;
-                    if (r < 4) m00 |= ma << sh, m10 |= mb << sh;
-                    else m01 |= ma << sh, m11 |= mb << sh;
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        const unsigned long long mg = newline_mask16(t4[8 * g + r]);
+                        if (r < 4) mlo[g] |= mg << sh;
+                        else mhi[g] |= mg << sh;
+                    }
                 }
-                w[0] = static_cast<unsigned>(m00), w[1] = static_cast<unsigned>(m00 >> 32);
-                w[2] = static_cast<unsigned>(m01), w[3] = static_cast<unsigned>(m01 >> 32);
-                w[4] = static_cast<unsigned>(m10), w[5] = static_cast<unsigned>(m10 >> 32);
-                w[6] = static_cast<unsigned>(m11), w[7] = static_cast<unsigned>(m11 >> 32);
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    w[4 * g + 0] = static_cast<unsigned>(mlo[g]), w[4 * g + 1] = static_cast<unsigned>(mlo[g] >> 32);
+                    w[4 * g + 2] = static_cast<unsigned>(mhi[g]), w[4 * g + 3] = static_cast<unsigned>(mhi[g] >> 32);
+                }
             } else {
                 // thread stride 160 bytes = 10 bank groups: lanes 4-7 of a phase start one segment later
                 static_assert(G::seg == 10, "rotation below is written for 10 segments per thread");
