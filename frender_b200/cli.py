@@ -215,11 +215,18 @@ def scan_files_concurrent(files, sample, streams, device, table_log2, main_ctx):
         except BaseException as exc:
             errors.append(exc)
 
+    # each stream is bound by its zlib thread (≈ 0.5 GB/s), so small staging buffers are enough and make the
+    # per-context set-up (pinned ring, device stages) cheap
+    had = os.environ.get("FRB_STAGE_MB")
+    if had is None:
+        os.environ["FRB_STAGE_MB"] = "16"
     threads = [threading.Thread(target=worker) for _ in range(streams)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
+    if had is None:
+        del os.environ["FRB_STAGE_MB"]
     if errors:
         raise errors[0]
     main_ctx.reset()
