@@ -563,23 +563,41 @@ def frender_demux(args, ctx=None):
     own_ctx = ctx is None
     ctx = ctx or Context(int(os.environ.get("FRENDER_DEVICE", "0")), table_log2=12)
     chunk = max(int(os.environ.get("FRENDER_DEMUX_CHUNK_MB", "64")) << 20, MIN_CHUNK)
+    # Host side of the router: inflate of the two mates and deflate of the sinks run on a thread pool (zlib
+    # releases the GIL).  Every sink sees the same sequence of compress() calls as a serial loop would make,
+    # so the output files are byte-identical to it; the writes of chunk k overlap the inflate of chunk k+1.
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(2, int(os.environ.get("FRENDER_DEMUX_THREADS", str(len(os.sched_getaffinity(0))))))
+    pool = ThreadPoolExecutor(max_workers=workers)
+    writes = []
+
+    def drain():
+        for f in writes:
+            f.result()
+        writes.clear()
+
     try:
         ctx.route_load(keys, routes, n_sinks + 1)
         for r1_path, r2_path in pairs:
             print(f"Demultiplexing {r1_path.name}...")
             a, b = TextChunks(r1_path, chunk), TextChunks(r2_path, chunk)
             while True:
-                a.fill()
-                b.fill()
+                fills = [pool.submit(a.fill), pool.submit(b.fill)]
+                for f in fills:
+                    f.result()
                 fa, fb = a.eof, b.eof                       # eof: the buffer holds all that is left
                 na, nb = a.take(), b.take()
                 o1, o2, off1, off2, done, used1, used2 = ctx.route_pair(
                     a.buf[:na], b.buf[:nb], (1 if fa else 0) | (2 if fb else 0))
                 if off1[reject + 1] > off1[reject]:
                     raise SystemExit("Unrecognized read type found in supplied frender result file!")
+                drain()                                     # a sink's compress() calls stay in order
+                v1, v2 = memoryview(o1), memoryview(o2)
                 for s in range(n_sinks):
-                    sinks[s]["R1"].write(o1[off1[s]:off1[s + 1]])
-                    sinks[s]["R2"].write(o2[off2[s]:off2[s + 1]])
+                    if off1[s + 1] > off1[s]:
+                        writes.append(pool.submit(sinks[s]["R1"].write, v1[off1[s]:off1[s + 1]]))
+                    if off2[s + 1] > off2[s]:
+                        writes.append(pool.submit(sinks[s]["R2"].write, v2[off2[s]:off2[s + 1]]))
                 a.buf, b.buf = a.buf[used1:], b.buf[used2:]
                 if (fa and not a.buf) or (fb and not b.buf) or (fa and fb):
                     break                                   # zip() ends with the shorter mate (F:777)
@@ -591,9 +609,11 @@ def frender_demux(args, ctx=None):
             raise SystemExit(exc.message)
         raise
     finally:
-        for s in sinks:
-            s["R1"].close()
-            s["R2"].close()
+        try:
+            drain()
+        finally:
+            list(pool.map(lambda s: (s["R1"].close(), s["R2"].close()), sinks))
+            pool.shutdown()
         if own_ctx:
             ctx.close()
 
