@@ -9,7 +9,9 @@ sorted unique list -> matcher pass 1 (forward + reverse-complement) -> per-sampl
 call -> matcher pass 2.  `value` is kernel-only (input resident in HBM, results left on the
 device); `e2e` feeds HOST buffers through the C-ABI (H2D of every input byte and D2H of the
 per-key results inside the timed region).  N > 1: one process per GPU (torchrun), each rank owns
-one lane (weak scaling), the per-rank unique tables are merged over NCCL inside the step.
+one lane (weak scaling); inside the step the per-rank unique tables are merged over NCCL so that every
+key ends on one rank (frb_shardmerge), each rank matches its share, and the per-sample orientation sums
+are all-reduced (the call of F:354-388 is over all reads of the job).
 `--impl reference` times the CPU oracle port of the reference (the reference is a Python script
 that cannot travel to the GPU box) on a bounded sample with all host cores.
 """
@@ -209,6 +211,7 @@ def run_b200(args):
 
     sheet = ctx.load_sheet(PackedSheet(spec.indexes()))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         ident = (C.c_char * 128)()
         if rank == 0:
             ck(lib.frb_nccl_unique_id(ident))
@@ -223,7 +226,10 @@ def run_b200(args):
     def analyze(want_outputs):
         """matcher pass 1 (rc) -> orientation call -> pass 2; returns unique count"""
         r = ctx.match(N_SUBS, True, None, want_outputs=False)
-        use = np.array([r["f_sum"][g] < r["rc_sum"][g] for g in sheet.group], np.uint8)     # F:376
+        f_sum, rc_sum = r["f_sum"], r["rc_sum"]
+        if world > 1:   # every rank matched its share of the merged keys: the call is over the whole job
+            f_sum, rc_sum = ctx.allreduce(f_sum), ctx.allreduce(rc_sum)
+        use = np.array([f_sum[g] < rc_sum[g] for g in sheet.group], np.uint8)               # F:376
         out = ctx.match(N_SUBS, False, use, want_outputs=want_outputs)
         return out
 
@@ -234,7 +240,7 @@ def run_b200(args):
         n_reads, n_uniq = C.c_uint64(), C.c_uint64()
         ck(lib.frb_scan_end(h, C.byref(n_reads), C.byref(n_uniq)))
         if world > 1:
-            ck(lib.frb_allmerge(h, C.byref(n_uniq)))
+            ck(lib.frb_shardmerge(h, C.byref(n_uniq)))
         analyze(False)
         return n_reads.value
 
@@ -268,6 +274,10 @@ def run_b200(args):
     prof = {k: ctx.prof_read(k, reset=True) for k in range(L.K_OTHER + 1)}
     n_uniq = C.c_uint64()
     ck(lib.frb_total_finish(h, C.byref(n_uniq)))
+    if dist:    # the shares are disjoint: the job's unique keys are their sum
+        box = [None] * world
+        dist.all_gather_object(box, n_uniq.value)
+        n_uniq = C.c_uint64(sum(box))
 
     # device time of the step, max over ranks
     ms_step = ms_total / args.steps
@@ -319,7 +329,7 @@ def run_b200(args):
             n_reads, n_uniq = C.c_uint64(), C.c_uint64()
             ck(lib.frb_scan_end(h, C.byref(n_reads), C.byref(n_uniq)))
             if world > 1:
-                ck(lib.frb_allmerge(h, C.byref(n_uniq)))
+                ck(lib.frb_shardmerge(h, C.byref(n_uniq)))
             keys, counts, _ = ctx.total_arrays()
             out = analyze(True)
             d2h[0] = keys.nbytes + counts.nbytes + sum(v.nbytes for v in out.values())

@@ -59,6 +59,8 @@ SIGNATURES = {
     "frb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "frb_nccl_init": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int]),
     "frb_allmerge": (C.c_int, [vp, P(u64)]),
+    "frb_shardmerge": (C.c_int, [vp, P(u64)]),
+    "frb_allreduce_u64": (C.c_int, [vp, vp, u64]),
     "frb_synth_load": (C.c_int, [vp, u64, u32, u32, u32, vp, vp, vp, u32, u32, u32, u32, u64, u64]),
     "frb_synth_generate": (C.c_int, [vp, u64, u64, C.c_int, vp, u64, P(u64)]),
     "frb_timer_start": (C.c_int, [vp]),

@@ -10,6 +10,11 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -32,7 +37,14 @@ NcclApi* nccl_api(std::string* why) {
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
         api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
-        if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.GetErrorString) err = "NCCL symbols missing";
+        api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(api.lib, "ncclSend"));
+        api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(api.lib, "ncclRecv"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.lib, "ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.lib, "ncclGroupEnd"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.GetErrorString || !api.Send || !api.Recv ||
+            !api.GroupStart || !api.GroupEnd || !api.AllReduce)
+            err = "NCCL symbols missing";
     });
     if (!err.empty()) {
         *why = err;
@@ -135,6 +147,141 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
     c->total_ready = true;
     c->total_gen++;
     if (n_unique) *n_unique = c->total.n;
+    return FRB_OK;
+}
+
+// Sharded merge: key k belongs to rank key_owner(k).  Every rank partitions its total list by owner and
+// sends each part to its owner (one grouped ncclSend/ncclRecv exchange over NVLink); the owner folds what
+// it receives into its cleared total table.  Afterwards the ranks hold disjoint shares whose union is what
+// frb_allmerge would leave on every rank, each share in first-appearance order; matcher work and table
+// size per rank stay constant as ranks are added.
+int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
+    CU(c, cudaSetDevice(c->device));
+    static const bool timing = getenv("FRB_MERGE_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(c->compute);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[shardmerge rank %d] %-22s %.3f ms\n", c->rank, what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
+    TRY(frb_total_finish(c, nullptr));
+    lap("local total");
+    if (c->n_ranks <= 1 || !c->nccl_comm) {
+        if (n_unique) *n_unique = c->total.n;
+        return FRB_OK;
+    }
+    std::string why;
+    NcclApi* api = nccl_api(&why);
+    ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
+    const int R = c->n_ranks;
+    if (R > 256) return fail(c, FRB_ERR_ARG, "frb_shardmerge: at most 256 ranks");
+    const unsigned long long n = c->total.n;
+    // 1. owner of every entry, histogram, entries grouped by owner
+    unsigned long long *d_hist = nullptr, *d_all = nullptr;
+    TRY(dmalloc(c, &d_hist, R * 8));
+    TRY(dmalloc(c, &d_all, static_cast<size_t>(R) * R * 8));
+    CU(c, cudaMemsetAsync(d_hist, 0, R * 8, c->compute));
+    unsigned *own = nullptr, *own_sorted = nullptr, *idx = nullptr, *idx_sorted = nullptr;
+    unsigned long long* part = nullptr;  // [3][n]: keys, counts, first grouped by owner
+    const unsigned long long n1 = std::max<unsigned long long>(n, 1);
+    TRY(dmalloc(c, &own, n1 * 4));
+    TRY(dmalloc(c, &own_sorted, n1 * 4));
+    TRY(dmalloc(c, &idx, n1 * 4));
+    TRY(dmalloc(c, &idx_sorted, n1 * 4));
+    TRY(dmalloc(c, &part, 3 * n1 * 8));
+    if (n) {
+        ProfScope ps(c, FRB_K_EXPORT);
+        const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+        owner_kernel<<<grid, 256, 0, c->compute>>>(c->total.keys, n, static_cast<unsigned>(R), own, d_hist);
+        iota_kernel<<<grid, 256, 0, c->compute>>>(idx, n);
+        size_t tmp = 0;
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, own, own_sorted, idx, idx_sorted, static_cast<int>(n), 0, 8,
+                                              c->compute));
+        TRY(ensure_cub_tmp(c, tmp));
+        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, own, own_sorted, idx, idx_sorted, static_cast<int>(n), 0, 8,
+                                              c->compute));
+        gather3_kernel<<<grid, 256, 0, c->compute>>>(idx_sorted, c->total.keys, c->total.counts, c->total.first, part,
+                                                     part + n, part + 2 * n, n);
+        c->launches += 5;
+        CU(c, cudaGetLastError());
+    }
+    lap("partition by owner");
+    // 2. everybody learns everybody's histogram
+    NC(c, api, api->AllGather(d_hist, d_all, R, ncclUint64, comm, c->compute));
+    std::vector<unsigned long long> all(static_cast<size_t>(R) * R);
+    CU(c, cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    std::vector<unsigned long long> send_off(R + 1, 0), recv_off(R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+        send_off[r + 1] = send_off[r] + all[static_cast<size_t>(c->rank) * R + r];  // my entries owned by r
+        recv_off[r + 1] = recv_off[r] + all[static_cast<size_t>(r) * R + c->rank];  // r's entries owned by me
+    }
+    if (send_off[R] != n) return fail(c, FRB_ERR_STATE, "frb_shardmerge: owner histogram does not add up");
+    const unsigned long long m = recv_off[R];
+    const unsigned long long m1 = std::max<unsigned long long>(m, 1);
+    unsigned long long* got = nullptr;  // [3][m]
+    TRY(dmalloc(c, &got, 3 * m1 * 8));
+    lap("histogram exchange");
+    // 3. the exchange
+    NC(c, api, api->GroupStart());
+    for (int r = 0; r < R; ++r) {
+        const unsigned long long ns = send_off[r + 1] - send_off[r], nr = recv_off[r + 1] - recv_off[r];
+        for (int f = 0; f < 3; ++f) {
+            if (ns) NC(c, api, api->Send(part + f * n + send_off[r], ns, ncclUint64, r, comm, c->compute));
+            if (nr) NC(c, api, api->Recv(got + f * m + recv_off[r], nr, ncclUint64, r, comm, c->compute));
+        }
+    }
+    NC(c, api, api->GroupEnd());
+    lap("send/recv");
+    // 4. fold my share into the cleared total table, rebuild the sorted list
+    CU(c, cudaMemsetAsync(&c->st->occupied_total, 0, 8, c->compute));
+    TRY(clear_table(c, c->total_tab));
+    c->total_tab_clean = false;
+    c->merged_upto = c->files.size();
+    if (m) {
+        ProfScope ps(c, FRB_K_EXPORT);
+        merge_list_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, c->compute>>>(
+            c->total_tab, c->cap - 1, got, got + m, got + 2 * m, m, 0ULL, &c->st->occupied_total, c->st);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    lap("clear + merge");
+    TRY(dfree(c, d_hist));
+    TRY(dfree(c, d_all));
+    TRY(dfree(c, own));
+    TRY(dfree(c, own_sorted));
+    TRY(dfree(c, idx));
+    TRY(dfree(c, idx_sorted));
+    TRY(dfree(c, part));
+    TRY(dfree(c, got));
+    CU(c, cudaStreamSynchronize(c->compute));
+    TRY(device_error_check(c));
+    TRY(free_list(c, c->total));
+    TRY(table_to_sorted_list(c, c->total_tab, c->st_host->occupied_total, &c->total));
+    lap("sorted share");
+    c->total_ready = true;
+    c->total_gen++;
+    if (n_unique) *n_unique = c->total.n;
+    return FRB_OK;
+}
+
+// Element-wise sum of a small u64 host array over all ranks (the per-sample orientation sums of the first
+// matcher pass when the total is sharded: the f < rc call of F:354-388 is over ALL reads of the job).
+int frb_allreduce_u64(frb_ctx* c, uint64_t* host_inout, uint64_t n) {
+    CU(c, cudaSetDevice(c->device));
+    if (c->n_ranks <= 1 || !c->nccl_comm || n == 0) return FRB_OK;
+    std::string why;
+    NcclApi* api = nccl_api(&why);
+    ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
+    unsigned long long* d = nullptr;
+    TRY(dmalloc(c, &d, n * 8));
+    CU(c, cudaMemcpyAsync(d, host_inout, n * 8, cudaMemcpyHostToDevice, c->compute));
+    NC(c, api, api->AllReduce(d, d, n, ncclUint64, ncclSum, comm, c->compute));
+    CU(c, cudaMemcpyAsync(host_inout, d, n * 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    TRY(dfree(c, d));
     return FRB_OK;
 }
 

@@ -82,4 +82,42 @@ __global__ void __launch_bounds__(256) merge_list_kernel(Slot* dst, unsigned lon
     if (i < n) table_add(dst, mask, keys[i], counts[i], first ? pos_base + first[i] : pos_base + i, occupied, st);
 }
 
+// Owner rank of a key in the sharded merge: hash bits the table index does not use.
+__host__ __device__ __forceinline__ unsigned key_owner(unsigned long long key, unsigned n_ranks) {
+    return static_cast<unsigned>((hash64(key) >> 40) % n_ranks);
+}
+
+// owner[i] of every list entry + per-owner histogram (shared-memory partial counts, one atomic per block and owner)
+__global__ void __launch_bounds__(256) owner_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                    unsigned n_ranks, unsigned* __restrict__ owner,
+                                                    unsigned long long* __restrict__ hist) {
+    __shared__ unsigned s_hist[256];
+    if (threadIdx.x < n_ranks) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const unsigned o = key_owner(keys[i], n_ranks);
+        owner[i] = o;
+        atomicAdd(&s_hist[o], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_ranks && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(s_hist[threadIdx.x]));
+}
+
+__global__ void __launch_bounds__(256) gather3_kernel(const unsigned* __restrict__ perm,
+                                                      const unsigned long long* __restrict__ a_in,
+                                                      const unsigned long long* __restrict__ b_in,
+                                                      const unsigned long long* __restrict__ c_in,
+                                                      unsigned long long* __restrict__ a_out,
+                                                      unsigned long long* __restrict__ b_out,
+                                                      unsigned long long* __restrict__ c_out, unsigned long long n) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n) {
+        const unsigned p = perm[i];
+        a_out[i] = a_in[p];
+        b_out[i] = b_in[p];
+        c_out[i] = c_in[p];
+    }
+}
+
 }  // namespace frb

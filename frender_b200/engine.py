@@ -119,6 +119,7 @@ class Context:
     def reset(self):
         self._ck(lib.frb_reset(self._h))
         self.file_names = []
+        self._sharded = False
 
     def scan_gz(self, path, ordinal, sample=None):
         """One fastq.gz through the inflate -> H2D -> kernel pipeline (scan_file, F:154-181).
@@ -226,7 +227,22 @@ class Context:
         """Merge the per-rank totals over NCCL; every rank ends with the same total list."""
         n = C.c_uint64()
         self._ck(lib.frb_allmerge(self._h, C.byref(n)))
+        self._sharded = False
         return n.value
+
+    def shardmerge(self):
+        """Merge the per-rank totals over NCCL so that every key ends on one rank (its owner by hash):
+        this rank's total becomes its share of the job-wide total.  Returns the size of the share."""
+        n = C.c_uint64()
+        self._ck(lib.frb_shardmerge(self._h, C.byref(n)))
+        self._sharded = True
+        return n.value
+
+    def allreduce(self, arr):
+        """Element-wise sum of a small uint64 array over all ranks."""
+        arr = np.ascontiguousarray(arr, np.uint64).copy()
+        self._ck(lib.frb_allreduce_u64(self._h, _ptr(arr), arr.size))
+        return arr
 
     def match(self, n_subs, rc_mode, use_rc_rows=None, want_outputs=True):
         """Raw matcher call over the context's total list.  Returns a dict of numpy arrays."""
@@ -290,6 +306,8 @@ class Context:
         results, raw = self.process(counter, indexes, num_subs, rc_mode)
         if not rc_mode:
             return results, None, list(self.sheet.idx2)
+        if getattr(self, "_sharded", False):   # the orientation call is over all reads of the job (F:354-388)
+            raw = dict(raw, f_sum=self.allreduce(raw["f_sum"]), rc_sum=self.allreduce(raw["rc_sum"]))
         calls = self.rc_calls(raw)
         use = np.array([calls[name]["call"] for name in self.sheet.ids], np.uint8)      # F:618-623
         oriented = [b if u else a for a, b, u in zip(self.sheet.idx2, self.sheet.rc_idx2, use)]

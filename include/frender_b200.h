@@ -165,6 +165,11 @@ int frb_route_pair(frb_ctx* ctx, const void* r1, uint64_t r1_bytes, const void* 
 int frb_nccl_unique_id(char id128[128]);
 int frb_nccl_init(frb_ctx* ctx, const char id128[128], int rank, int n_ranks);
 int frb_allmerge(frb_ctx* ctx, uint64_t* n_unique);
+/* frb_shardmerge: the same merge, but every key ends on ONE rank (its owner by hash): the ranks hold disjoint
+ * shares of the merged total, each in first-appearance order; the matcher then runs on the share.           */
+int frb_shardmerge(frb_ctx* ctx, uint64_t* n_unique);
+/* element-wise sum of a small host array over all ranks (orientation sums of a sharded total, F:354-388) */
+int frb_allreduce_u64(frb_ctx* ctx, uint64_t* host_inout, uint64_t n);
 
 /* ---- synthetic input (bench / tests): device twin of frender_b200/synth.py ----------------- */
 int frb_synth_load(frb_ctx* ctx, uint64_t seed, uint32_t l1, uint32_t l2, uint32_t n_samples,

@@ -43,9 +43,29 @@ def main():
     res, calls, _ = ctx.analyze(spec.indexes(), 1, True)
     want_res, want_calls, _ = O.scan_analysis(1, {"total": want}, spec.indexes(), 1, True)
     assert res == want_res and calls == want_calls, f"rank {rank}: matcher differs from the oracle"
+    # sharded merge of the same per-rank tallies: disjoint shares, union == the oracle's tally (counts and
+    # first-appearance order), every share classified like the oracle classifies those keys
+    ctx.reset()
+    ctx.scan_bytes(shard, ordinal=rank)
+    ctx.shardmerge()
+    skeys, scounts, sfirst = ctx.total_arrays()
+    sres, _, _ = ctx.analyze(spec.indexes(), 1, True)
+    shares = [None] * world
+    dist.all_gather_object(shares, (unpack_keys(skeys), scounts.tolist(), sfirst.tolist(), sres))
+    union = [(f, k, n) for ks, ns, fs, _ in shares for k, n, f in zip(ks, ns, fs)]
+    assert len({k for _, k, _ in union}) == len(union), "shares overlap"
+    assert sorted(fs for fs in shares[rank][2]) == shares[rank][2], "share not in first-appearance order"
+    union.sort()
+    assert [(k, n) for _, k, n in union] == list(want.items()), "union of the shares differs from the oracle"
+    merged_res = {}
+    for _, _, _, part in shares:
+        merged_res.update(part["total"] if "total" in part else part)
+    ref = want_res["total"] if "total" in want_res else want_res
+    assert merged_res == ref or {k: merged_res[k] for k in ref} == ref, "sharded matcher differs from the oracle"
     dist.barrier()
     if rank == 0:
-        print(f"mgpu ok: {world} ranks, {len(got)} unique keys, merged == oracle on every rank")
+        print(f"mgpu ok: {world} ranks, {len(got)} unique keys, merged == oracle on every rank, "
+              f"shares {[len(s[0]) for s in shares]}")
     ctx.close()
     dist.destroy_process_group()
 
