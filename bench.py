@@ -117,44 +117,87 @@ def workload_config(reads_per_gpu, n_gpus):
 
 # ------------------------------------------------------------------------------------------------
 class Clocks:
-    """nvidia-smi sampler for the timed region (recipe of B200_PROFILING.md)."""
+    """SM clock and throttle-reason sampler for the timed region (the counters of B200_PROFILING.md's
+    nvidia-smi line, every 200 ms).  Read through NVML in-process when pynvml is importable: an
+    `nvidia-smi -lms` child re-queries the whole device each period and was seen to hold up the sampled
+    rank's CUDA calls for 10-600 ms at a time; falls back to that child otherwise."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device):
+        self.proc = self.thread = None
+        self.sm, self.mx, self.reasons = [], 0, set()
+        try:
+            if os.environ.get("FRB_BENCH_NO_CLOCKS"):
+                raise RuntimeError("clock sampling disabled")
+            import threading
+
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip()]
+            index = int(ids[device]) if ids and all(v.strip().isdigit() for v in ids) else device
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                        self.reasons.update(name for name, bit in self.BITS.items() if mask & bit)
+                    except pynvml.NVMLError:
+                        pass
+                    self.stop_flag.wait(0.2)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        self.source = "nvidia-smi"
         self.path = tempfile.mktemp(suffix=".csv")
         self.fh = open(self.path, "w")
         try:
+            if os.environ.get("FRB_BENCH_NO_CLOCKS"):
+                raise OSError("clock sampling disabled")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            self.proc.wait()
-        self.fh.close()
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in open(self.path):
-            f = [x.strip() for x in row.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = max(mx, float(f[2]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, f[5:9]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
+        if self.thread:
+            self.stop_flag.set()
+            self.thread.join()
+        else:
+            if self.proc:
+                self.proc.terminate()
+                self.proc.wait()
+            self.fh.close()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for row in open(self.path):
+                f = [x.strip() for x in row.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    self.sm.append(float(f[1]))
+                    self.mx = max(self.mx, float(f[2]))
+                except ValueError:
+                    continue
+                for name, flag in zip(names, f[5:9]):
+                    if flag.lower().startswith("active"):
+                        self.reasons.add(name)
+            os.unlink(self.path)
+        sm = self.sm
         busy = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 def run_b200(args):
@@ -257,6 +300,8 @@ def run_b200(args):
             ms = C.c_float()
             ck(lib.frb_timer_stop(h, C.byref(ms)))
             ms_all.append(ms.value)
+            if os.environ.get("FRB_BENCH_VERBOSE"):
+                print(f"[rank {rank}] step {len(ms_all)}: {ms.value:.2f} ms", file=sys.stderr)
         ck(lib.frb_sync(h))
         t_wall = time.perf_counter() - t_wall
         barrier()

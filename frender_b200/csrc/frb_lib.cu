@@ -71,6 +71,10 @@ struct frb_ctx {
     bool total_ready = false, in_file = false;
     size_t merged_upto = 0;        // file lists already folded into total_tab
     bool ext_merged = false;       // lists from other contexts were folded in (frb_total_merge)
+    bool sharded = false;          // total holds this rank's share of a sharded merge (no table behind it)
+    // exchange buffers of the sharded merge: kept (grow-only) so that NCCL sees the same addresses every step
+    unsigned long long* xchg[3] = {nullptr, nullptr, nullptr};  // send parts, received parts, histograms
+    size_t xchg_cap[3] = {0, 0, 0};
     bool total_tab_clean = true;   // total_tab holds no keys
     uint32_t cur_ordinal = 0;
     uint64_t cur_limit = ~0ULL;
@@ -257,28 +261,20 @@ int ensure_cub_tmp(frb_ctx* c, size_t bytes) {
     return FRB_OK;
 }
 
-// Table -> list sorted by `first` (first-appearance order, F:172-177 / F:199-205).
-int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
+// Dense (key,count,first) arrays in arbitrary order -> list sorted by `first` (first-appearance order,
+// F:172-177 / F:199-205).  Takes over k0/c0/f0 (pool allocations) and frees them.
+int unsorted_to_sorted_list(frb_ctx* c, unsigned long long* k0, unsigned long long* c0, unsigned long long* f0,
+                            uint64_t n, KeyList* out) {
     out->n = n;
-    if (n == 0) return FRB_OK;
-    if (n >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
-    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr;
     unsigned *i0 = nullptr, *i1 = nullptr;
-    TRY(dmalloc(c, &k0, n * 8));
-    TRY(dmalloc(c, &c0, n * 8));
-    TRY(dmalloc(c, &f0, n * 8));
-    TRY(dmalloc(c, &i0, n * 4));
-    TRY(dmalloc(c, &i1, n * 4));
-    TRY(dmalloc(c, &out->keys, n * 8));
-    TRY(dmalloc(c, &out->counts, n * 8));
-    TRY(dmalloc(c, &out->first, n * 8));
-    {
+    if (n) {
+        TRY(dmalloc(c, &i0, n * 4));
+        TRY(dmalloc(c, &i1, n * 4));
+        TRY(dmalloc(c, &out->keys, n * 8));
+        TRY(dmalloc(c, &out->counts, n * 8));
+        TRY(dmalloc(c, &out->first, n * 8));
         ProfScope ps(c, FRB_K_EXPORT);
-        CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
-        compact_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
-            tab, c->cap, k0, c0, f0, &c->st->scratch, n);
         iota_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i0, n);
-        c->launches += 2;
         size_t tmp = 0;
         CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0, 64,
                                               c->compute));
@@ -287,15 +283,35 @@ int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
                                               c->compute));
         gather2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i1, k0, c0, out->keys,
                                                                                        out->counts, n);
-        c->launches += 8;  // cub radix sort passes (approximate) + gather
+        c->launches += 9;  // iota, cub radix sort passes (approximate), gather
         CU(c, cudaGetLastError());
     }
     TRY(dfree(c, k0));
     TRY(dfree(c, c0));
     TRY(dfree(c, f0));
-    TRY(dfree(c, i0));
-    TRY(dfree(c, i1));
+    if (i0) TRY(dfree(c, i0));
+    if (i1) TRY(dfree(c, i1));
     return FRB_OK;
+}
+
+// Table -> list sorted by `first`.
+int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
+    out->n = n;
+    if (n == 0) return FRB_OK;
+    if (n >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
+    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr;
+    TRY(dmalloc(c, &k0, n * 8));
+    TRY(dmalloc(c, &c0, n * 8));
+    TRY(dmalloc(c, &f0, n * 8));
+    {
+        ProfScope ps(c, FRB_K_EXPORT);
+        CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
+        compact_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
+            tab, c->cap, k0, c0, f0, &c->st->scratch, n);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    return unsorted_to_sorted_list(c, k0, c0, f0, n, out);
 }
 
 int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t line_base, int rule,
@@ -482,6 +498,7 @@ void frb_destroy(frb_ctx* c) {
     for (auto& f : c->files) free_list(c, f);
     free_list(c, c->total);
     cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status), cudaFree(c->redo);
+    for (auto* p : c->xchg) cudaFree(p);
     for (int i = 0; i < kHostStages; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]), cudaEventDestroy(c->stage_copied[i]), cudaEventDestroy(c->stage_done[i]);
         if (c->ring[i]) cudaFreeHost(c->ring[i]);
@@ -577,6 +594,7 @@ int frb_unpack_key(uint64_t key, char* out) {
 int frb_scan_begin(frb_ctx* c, uint32_t file_ordinal, uint64_t read_limit) {
     CU(c, cudaSetDevice(c->device));
     if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_begin: previous file not ended");
+    if (c->sharded) return fail(c, FRB_ERR_STATE, "frb_scan_begin: the total is a share of a sharded merge; frb_reset first");
     if (file_ordinal >= (1u << 23)) return fail(c, FRB_ERR_ARG, "file ordinal too large");
     c->cur_ordinal = file_ordinal;
     c->cur_limit = read_limit ? read_limit : ~0ULL;
@@ -778,6 +796,7 @@ int frb_reset(frb_ctx* c) {
     CU(c, cudaMemsetAsync(c->st, 0, sizeof(DevState), c->compute));
     c->merged_upto = 0;
     c->ext_merged = false;
+    c->sharded = false;
     if (!c->total_tab_clean) {
         TRY(clear_table(c, c->total_tab));
         c->total_tab_clean = true;

@@ -59,6 +59,18 @@ NcclApi* nccl_api(std::string* why) {
         if (r_ != ncclSuccess) return fail(c, FRB_ERR_NCCL, "%s failed: %s", #call, (api)->GetErrorString(r_)); \
     } while (0)
 
+// grow-only device buffer with a stable address between calls (NCCL caches per-address state for send/recv)
+int xchg_reserve(frb_ctx* c, int which, size_t bytes) {
+    if (bytes <= c->xchg_cap[which]) return FRB_OK;
+    if (c->xchg[which]) CU(c, cudaFree(c->xchg[which]));
+    c->xchg[which] = nullptr;
+    c->xchg_cap[which] = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    CU(c, cudaMalloc(&c->xchg[which], want));
+    c->xchg_cap[which] = want;
+    return FRB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -155,6 +167,7 @@ int frb_allmerge(frb_ctx* c, uint64_t* n_unique) {
 // it receives into its cleared total table.  Afterwards the ranks hold disjoint shares whose union is what
 // frb_allmerge would leave on every rank, each share in first-appearance order; matcher work and table
 // size per rank stay constant as ranks are added.
+
 int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
     CU(c, cudaSetDevice(c->device));
     static const bool timing = getenv("FRB_MERGE_TIMING") != nullptr;
@@ -179,18 +192,18 @@ int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
     if (R > 256) return fail(c, FRB_ERR_ARG, "frb_shardmerge: at most 256 ranks");
     const unsigned long long n = c->total.n;
     // 1. owner of every entry, histogram, entries grouped by owner
-    unsigned long long *d_hist = nullptr, *d_all = nullptr;
-    TRY(dmalloc(c, &d_hist, R * 8));
-    TRY(dmalloc(c, &d_all, static_cast<size_t>(R) * R * 8));
+    TRY(xchg_reserve(c, 2, (static_cast<size_t>(R) + static_cast<size_t>(R) * R) * 8));
+    unsigned long long* d_hist = c->xchg[2];
+    unsigned long long* d_all = d_hist + R;
     CU(c, cudaMemsetAsync(d_hist, 0, R * 8, c->compute));
     unsigned *own = nullptr, *own_sorted = nullptr, *idx = nullptr, *idx_sorted = nullptr;
-    unsigned long long* part = nullptr;  // [3][n]: keys, counts, first grouped by owner
+    TRY(xchg_reserve(c, 0, 3 * std::max<unsigned long long>(n, 1) * 8));
+    unsigned long long* part = c->xchg[0];  // [3][n]: keys, counts, first grouped by owner
     const unsigned long long n1 = std::max<unsigned long long>(n, 1);
     TRY(dmalloc(c, &own, n1 * 4));
     TRY(dmalloc(c, &own_sorted, n1 * 4));
     TRY(dmalloc(c, &idx, n1 * 4));
     TRY(dmalloc(c, &idx_sorted, n1 * 4));
-    TRY(dmalloc(c, &part, 3 * n1 * 8));
     if (n) {
         ProfScope ps(c, FRB_K_EXPORT);
         const unsigned grid = static_cast<unsigned>((n + 255) / 256);
@@ -221,8 +234,8 @@ int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
     if (send_off[R] != n) return fail(c, FRB_ERR_STATE, "frb_shardmerge: owner histogram does not add up");
     const unsigned long long m = recv_off[R];
     const unsigned long long m1 = std::max<unsigned long long>(m, 1);
-    unsigned long long* got = nullptr;  // [3][m]
-    TRY(dmalloc(c, &got, 3 * m1 * 8));
+    TRY(xchg_reserve(c, 1, 3 * m1 * 8));
+    unsigned long long* got = c->xchg[1];  // [3][m]
     lap("histogram exchange");
     // 3. the exchange
     NC(c, api, api->GroupStart());
@@ -235,31 +248,46 @@ int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
     }
     NC(c, api, api->GroupEnd());
     lap("send/recv");
-    // 4. fold my share into the cleared total table, rebuild the sorted list
-    CU(c, cudaMemsetAsync(&c->st->occupied_total, 0, 8, c->compute));
-    TRY(clear_table(c, c->total_tab));
-    c->total_tab_clean = false;
-    c->merged_upto = c->files.size();
+    // 4. fold my share: sort what arrived by key, one entry per run of equal keys (count: +, first: min),
+    //    then the usual sort by first appearance.  No table involved: sequential traffic only.
+    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr, *ks = nullptr;
+    unsigned *pi = nullptr, *po = nullptr;
+    TRY(dmalloc(c, &k0, m1 * 8));
+    TRY(dmalloc(c, &c0, m1 * 8));
+    TRY(dmalloc(c, &f0, m1 * 8));
+    TRY(dmalloc(c, &ks, m1 * 8));
+    TRY(dmalloc(c, &pi, m1 * 4));
+    TRY(dmalloc(c, &po, m1 * 4));
+    CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
     if (m) {
+        if (m >= (1ULL << 31)) return fail(c, FRB_ERR_ARG, "frb_shardmerge: share too large");
         ProfScope ps(c, FRB_K_EXPORT);
-        merge_list_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, c->compute>>>(
-            c->total_tab, c->cap - 1, got, got + m, got + 2 * m, m, 0ULL, &c->st->occupied_total, c->st);
-        c->launches++;
+        const unsigned grid = static_cast<unsigned>((m + 255) / 256);
+        iota_kernel<<<grid, 256, 0, c->compute>>>(pi, m);
+        size_t tmp = 0;
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, got, ks, pi, po, static_cast<int>(m), 0, 64, c->compute));
+        TRY(ensure_cub_tmp(c, tmp));
+        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, got, ks, pi, po, static_cast<int>(m), 0, 64, c->compute));
+        fold_runs_kernel<<<grid, 256, 0, c->compute>>>(ks, po, got + m, got + 2 * m, m, k0, c0, f0, &c->st->scratch);
+        c->launches += 10;
         CU(c, cudaGetLastError());
     }
-    lap("clear + merge");
-    TRY(dfree(c, d_hist));
-    TRY(dfree(c, d_all));
+    unsigned long long u = 0;
+    CU(c, cudaMemcpyAsync(&u, &c->st->scratch, 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    lap("sort by key + fold");
     TRY(dfree(c, own));
     TRY(dfree(c, own_sorted));
     TRY(dfree(c, idx));
     TRY(dfree(c, idx_sorted));
-    TRY(dfree(c, part));
-    TRY(dfree(c, got));
-    CU(c, cudaStreamSynchronize(c->compute));
+    TRY(dfree(c, ks));
+    TRY(dfree(c, pi));
+    TRY(dfree(c, po));
     TRY(device_error_check(c));
     TRY(free_list(c, c->total));
-    TRY(table_to_sorted_list(c, c->total_tab, c->st_host->occupied_total, &c->total));
+    TRY(unsorted_to_sorted_list(c, k0, c0, f0, u, &c->total));
+    c->merged_upto = c->files.size();
+    c->sharded = true;
     lap("sorted share");
     c->total_ready = true;
     c->total_gen++;

@@ -82,6 +82,44 @@ __global__ void __launch_bounds__(256) merge_list_kernel(Slot* dst, unsigned lon
     if (i < n) table_add(dst, mask, keys[i], counts[i], first ? pos_base + first[i] : pos_base + i, occupied, st);
 }
 
+// Entries sorted by key (ks) with their original positions (perm): every run of equal keys becomes one entry
+// (count: +, first: min), appended in arbitrary order.  Runs are at most n_ranks long.
+__global__ void __launch_bounds__(256) fold_runs_kernel(const unsigned long long* __restrict__ ks,
+                                                        const unsigned* __restrict__ perm,
+                                                        const unsigned long long* __restrict__ counts,
+                                                        const unsigned long long* __restrict__ first,
+                                                        unsigned long long n, unsigned long long* __restrict__ k_out,
+                                                        unsigned long long* __restrict__ c_out,
+                                                        unsigned long long* __restrict__ f_out,
+                                                        unsigned long long* counter) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    const unsigned long long key = i < n ? ks[i] : 0ULL;
+    const bool head = i < n && (i == 0 || ks[i - 1] != key);
+    unsigned long long sum = 0, mn = ~0ULL;
+    if (head) {
+        for (unsigned long long j = i; j < n && ks[j] == key; ++j) {
+            const unsigned p = perm[j];
+            sum += counts[p];
+            const unsigned long long f = first[p];
+            mn = f < mn ? f : mn;
+        }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+    if (m) {
+        unsigned long long base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(counter, static_cast<unsigned long long>(__popc(m)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (head) {
+            const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+            k_out[idx] = key;
+            c_out[idx] = sum;
+            f_out[idx] = mn;
+        }
+    }
+}
+
 // Owner rank of a key in the sharded merge: hash bits the table index does not use.
 __host__ __device__ __forceinline__ unsigned key_owner(unsigned long long key, unsigned n_ranks) {
     return static_cast<unsigned>((hash64(key) >> 40) % n_ranks);
