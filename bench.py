@@ -254,7 +254,6 @@ def run_b200(args):
 
     sheet = ctx.load_sheet(PackedSheet(spec.indexes()))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         ident = (C.c_char * 128)()
         if rank == 0:
             ck(lib.frb_nccl_unique_id(ident))
@@ -482,6 +481,11 @@ def run_b200(args):
 
 
 def main():
+    # stdout carries the one JSON line: NCCL's version/warning banner (NCCL_DEBUG=VERSION|WARN in some
+    # environments) goes to stderr, or away
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
