@@ -13,34 +13,42 @@ __global__ void __launch_bounds__(256) clear_table_kernel(Slot* tab, unsigned lo
         t4[i] = make_ulonglong4(kEmpty, 0ULL, ~0ULL, 0ULL);
 }
 
-// Occupied slots -> dense arrays (arbitrary order); *counter receives the number written.
+// Occupied slots -> dense arrays (arbitrary order); *counter receives the number written.  One atomic per
+// block and pass (a per-warp atomic on the one counter was the kernel's bound: 2 M atomics for 2^26 slots).
 __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restrict__ tab, unsigned long long cap,
                                                             unsigned long long* __restrict__ keys,
                                                             unsigned long long* __restrict__ counts,
                                                             unsigned long long* __restrict__ first,
                                                             unsigned long long* counter,
                                                             unsigned long long out_cap) {
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned long long cap_up = (cap + 31) & ~31ULL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long cap_up = (cap + 255) & ~255ULL;
     for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
          i < cap_up; i += stride) {
         ulonglong4 s = make_ulonglong4(kEmpty, 0, 0, 0);
         if (i < cap) s = reinterpret_cast<const ulonglong4*>(tab)[i];
         const bool occ = s.x != kEmpty;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, occ);
-        if (m) {
-            unsigned long long base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(counter, static_cast<unsigned long long>(__popc(m)));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (occ) {
-                const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
-                if (idx < out_cap) {
-                    keys[idx] = s.x;
-                    counts[idx] = s.y;
-                    first[idx] = s.z;
-                }
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned v = s_warp[w];
+            if (w < warp) before += v;
+            total += v;
+        }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(counter, static_cast<unsigned long long>(total));
+        __syncthreads();
+        if (occ) {
+            const unsigned long long idx = s_base + before + __popc(m & ((1u << lane) - 1u));
+            if (idx < out_cap) {
+                keys[idx] = s.x;
+                counts[idx] = s.y;
+                first[idx] = s.z;
             }
         }
     }
