@@ -324,7 +324,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     static const bool ws = getenv("FRB_SCAN_KERNEL") ? strcmp(getenv("FRB_SCAN_KERNEL"), "std") != 0 : true;
     static const bool dense = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "dense") == 0 : false;
     static const bool tall = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "tall") == 0 : false;
-    const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : tall ? WsTall::tile : WsWide::tile)
+    static const bool trio = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "trio") == 0 : false;
+    const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : tall ? WsTall::tile : trio ? WsTrio::tile : WsWide::tile)
                                                    : (nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile));
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
@@ -372,7 +373,10 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     {
         ProfScope ps(c, FRB_K_SCAN);
         if (ws) {
-            if (tall) {
+            if (trio) {
+                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTrio::ctas));
+                scan_ws_kernel<WsTrio><<<grid, WsTrio::threads, WsTrio::smem, c->compute>>>(a);
+            } else if (tall) {
                 const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTall::ctas));
                 scan_ws_kernel<WsTall><<<grid, WsTall::threads, WsTall::smem, c->compute>>>(a);
             } else if (dense) {
@@ -484,6 +488,7 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsWide::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsDense::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTall>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTall::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTrio>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTrio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TRY(clear_table(c, c->total_tab));
     CU(c, cudaStreamSynchronize(c->compute));

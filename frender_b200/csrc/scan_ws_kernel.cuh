@@ -38,11 +38,15 @@ struct WsGeom {
     static constexpr int ctas = CTAS;
     // per-thread register budget that keeps CTAS resident (registers are allocated per 4 warps)
     static constexpr int maxreg = (65536 / (CTAS * ((threads + 127) / 128 * 128))) / 8 * 8;
+    // With 3 CTAs per SM the launch budget (80) is re-split inside the CTA: the counter warpgroup gives
+    // registers back (setmaxnreg.dec) and the extractor/committer warpgroup takes them (setmaxnreg.inc).
+    static constexpr bool split_regs = CTAS == 3 && threads == 256;
     static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
 using WsWide = WsGeom<16, 3, 2, 2048>;   // 32 KiB tiles, 2 x 8 warps per SM
 using WsDense = WsGeom<10, 2, 3, 1024>;  // 20 KiB tiles, 3 x 7 warps per SM (A-B variant)
 using WsTall = WsGeom<24, 3, 2, 3072, 2>;  // 48 KiB tiles, two stages (A-B variant)
+using WsTrio = WsGeom<16, 3, 3, 1536, 2>;  // 32 KiB tiles, two stages, 3 CTAs per SM (A-B variant)
 constexpr int kWsTile = WsWide::tile;
 constexpr int kWsThreads = WsWide::threads;
 constexpr int kWsSmem = WsWide::smem;
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __syncthreads();
 
     if (warp < kWsGroup / 32) {
+        if constexpr (G::split_regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         // =============================== COUNTERS ================================================
         const int ct = tid;
         unsigned full_parity = 0;  // bit s
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
         }
         if (a.timing && ct == 0) atomicAdd(&a.timing[0], t_wait), atomicAdd(&a.timing[1], t_work);
     } else {
+        if constexpr (G::split_regs) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // =============================== EXTRACTORS + COMMITTER ====================================
         // Batch descriptor words (s_bmeta): local tile index, global tile, first header index of the
         // batch, entries, newlines in the tile, lines (newlines + unterminated last line), guessed j0,
