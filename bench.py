@@ -118,7 +118,7 @@ def workload_config(reads_per_gpu, n_gpus):
 # ------------------------------------------------------------------------------------------------
 class Clocks:
     """SM clock and throttle-reason sampler for the timed region (the counters of B200_PROFILING.md's
-    nvidia-smi line, every 200 ms).  Read through NVML in-process when pynvml is importable: an
+    nvidia-smi line; every 50 ms through NVML, every 200 ms through the nvidia-smi child).  Read through NVML in-process when pynvml is importable: an
     `nvidia-smi -lms` child re-queries the whole device each period and was seen to hold up the sampled
     rank's CUDA calls for 10-600 ms at a time; falls back to that child otherwise."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -151,7 +151,7 @@ class Clocks:
                         self.reasons.update(name for name, bit in self.BITS.items() if mask & bit)
                     except pynvml.NVMLError:
                         pass
-                    self.stop_flag.wait(0.2)
+                    self.stop_flag.wait(0.05)
 
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
@@ -286,10 +286,12 @@ def run_b200(args):
         analyze(False)
         return n_reads.value
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, after_warmup=None):
         for _ in range(warmup):
             fn()
         ck(lib.frb_sync(h))
+        if after_warmup:
+            after_warmup()
         barrier()
         ms_all = []
         t_wall = time.perf_counter()
@@ -307,13 +309,17 @@ def run_b200(args):
         return sum(ms_all), t_wall, got
 
     ctx.prof(True)
-    for k in range(L.K_OTHER + 1):
-        ctx.prof_read(k, reset=True)
-    launches0 = ctx.launches()
+    mark = {}
+
+    def start_counting():      # the timed steps only: per-class device time and launch count start after warm-up
+        for k in range(L.K_OTHER + 1):
+            ctx.prof_read(k, reset=True)
+        mark["launches"] = ctx.launches()
+
     clocks = Clocks(local)
-    ms_total, wall_s, got_reads = timed(step_resident, args.steps, args.warmup)
+    ms_total, wall_s, got_reads = timed(step_resident, args.steps, args.warmup, start_counting)
     clk = clocks.stop()
-    launches = ctx.launches() - launches0
+    launches = ctx.launches() - mark["launches"]
     assert got_reads == reads, (got_reads, reads)
     prof = {k: ctx.prof_read(k, reset=True) for k in range(L.K_OTHER + 1)}
     n_uniq = C.c_uint64()
@@ -351,7 +357,7 @@ def run_b200(args):
                 "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "scan_ws_kernel (parse+pack+count, warp-specialised)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": scan_ms_per,
-                "step_share": {name: prof[k][0] / (args.steps + args.warmup) for name, k in
+                "step_share": {name: prof[k][0] / args.steps for name, k in
                                (("scan_ms", L.K_SCAN), ("export_sort_merge_ms", L.K_EXPORT),
                                 ("match_ms", L.K_MATCH), ("clear_ms", L.K_OTHER))}}
 

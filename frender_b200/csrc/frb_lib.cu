@@ -324,7 +324,7 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     static const bool ws = getenv("FRB_SCAN_KERNEL") ? strcmp(getenv("FRB_SCAN_KERNEL"), "std") != 0 : true;
     static const bool dense = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "dense") == 0 : false;
     static const bool tall = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "tall") == 0 : false;
-    static const bool trio = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "trio") == 0 : false;
+    static const bool trio = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "trio") == 0 : true;  // default
     const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : tall ? WsTall::tile : trio ? WsTrio::tile : WsWide::tile)
                                                    : (nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile));
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;

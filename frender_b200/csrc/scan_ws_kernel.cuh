@@ -44,7 +44,7 @@ struct WsGeom {
     static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
 using WsWide = WsGeom<16, 3, 2, 2048>;   // 32 KiB tiles, 2 x 8 warps per SM
-using WsDense = WsGeom<10, 2, 3, 1024>;  // 20 KiB tiles, 3 x 7 warps per SM (A-B variant)
+using WsDense = WsGeom<10, 3, 3, 1024>;  // 20 KiB tiles, three stages, 3 CTAs per SM (A-B variant)
 using WsTall = WsGeom<24, 3, 2, 3072, 2>;  // 48 KiB tiles, two stages (A-B variant)
 using WsTrio = WsGeom<16, 3, 3, 1536, 2>;  // 32 KiB tiles, two stages, 3 CTAs per SM (A-B variant)
 constexpr int kWsTile = WsWide::tile;
