@@ -653,6 +653,13 @@ int frb_scan_end(frb_ctx* c, uint64_t* n_reads, uint64_t* n_unique) {
     if (!c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_end: no file begun");
     c->in_file = false;
     CU(c, cudaStreamSynchronize(c->copy));
+    {   // unique keys of the file = occupied slots of its table
+        ProfScope ps(c, FRB_K_EXPORT);
+        CU(c, cudaMemsetAsync(&c->st->occupied, 0, 8, c->compute));
+        count_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(c->file_tab, c->cap,
+                                                                                          &c->st->occupied);
+        c->launches++;
+    }
     CU(c, cudaStreamSynchronize(c->compute));
     TRY(device_error_check(c));
     KeyList fl;

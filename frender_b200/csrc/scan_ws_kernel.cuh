@@ -450,46 +450,42 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
                 atomicMin(&a.table[slot].first, pos);
             };
-            // Step 2/3 of a set: q holds a key whose slot looked free (compare-and-swap issued, q_old = its
-            // result) or taken by another key (next slot's key requested, q_old = that key).  Only a second
-            // mismatch falls back to the in-line probe loop, whose loads are L2 round trips.
-            bool q_cas[kRounds];
-            unsigned long long my_occ = 0;
+            // Step 2/3 of a set: its home slot did not hold the key.  Slot free: compare-and-swap, result
+            // dropped (the instruction returns it in its compare register, the copy out of there would wait
+            // for the L2 round trip on the spot), then a load of the same slot -- same thread, same address,
+            // so it sees the slot after the swap.  Slot taken by another key: load of the next slot.  One
+            // batch later the loaded key decides: ours -> count/first update; anything else (lost race, two
+            // other keys in a row) -> the in-line probe loop, whose loads are L2 round trips.  Nobody knows
+            // who won a slot, so the number of occupied slots is counted when the file ends.
             auto finish = [&](int r) {
                 if (q_cnt[r]) {
-                    if (q_old[r] == q_key[r] || (q_cas[r] && q_old[r] == kEmpty)) {
-                        if (q_old[r] == kEmpty) ++my_occ;
+                    if (q_old[r] == q_key[r]) {
                         bump(q_slot[r], q_cnt[r], q_pos[r]);
                     } else {
                         table_add(a.table, a.table_mask, q_key[r], q_cnt[r], q_pos[r], &a.st->occupied, a.st);
                     }
                     q_cnt[r] = 0;
                 }
-                const bool claim = p_cnt[r] && p_seen[r] == kEmpty;                           // free slot: take it
-                const bool reprobe = p_cnt[r] && p_seen[r] != kEmpty && p_seen[r] != p_key[r];  // other key: next slot
+                const bool claim = p_cnt[r] && p_seen[r] == kEmpty;
+                const bool look = p_cnt[r] && p_seen[r] != p_key[r];  // claim or re-probe: a q set is born
                 if (p_cnt[r]) {
                     if (p_seen[r] == p_key[r]) {
                         bump(p_slot[r], p_cnt[r], p_pos[r]);
                     } else {
-                        q_key[r] = p_key[r], q_pos[r] = p_pos[r], q_cnt[r] = p_cnt[r], q_cas[r] = claim;
+                        q_key[r] = p_key[r], q_pos[r] = p_pos[r], q_cnt[r] = p_cnt[r];
                         q_slot[r] = claim ? p_slot[r] : ((p_slot[r] + 1) & a.table_mask);
                     }
                     p_cnt[r] = 0;
                 }
-                // Both requests are predicated INSIDE the asm statement with q_old as in/out operand (for
-                // the compare-and-swap also as the compare value, preset to kEmpty: the SASS instruction
-                // returns the old value in the compare register).  Written as `if (..) q_old = atomicCAS(..)`
-                // the compiler lands the result in a scratch register and copies it at the join, which
-                // waits out the L2 round trip on the spot.
-                if (claim) q_old[r] = kEmpty;
                 asm volatile(
-                    "{\n\t.reg .pred p, q;\n\t"
-                    "setp.ne.u32 p, %3, 0;\n\t"
-                    "setp.ne.u32 q, %4, 0;\n\t"
-                    "@p atom.global.cas.b64 %0, [%1], %0, %2;\n\t"
+                    "{\n\t.reg .pred p, q;\n\t.reg .b64 t;\n\t"
+                    "setp.ne.u32 p, %4, 0;\n\t"
+                    "setp.ne.u32 q, %5, 0;\n\t"
+                    "@p atom.global.cas.b64 t, [%1], %2, %3;\n\t"
                     "@q ld.volatile.global.u64 %0, [%1];\n\t}"
-                    : "+l"(q_old[r])
-                    : "l"(&a.table[q_slot[r] & a.table_mask].key), "l"(q_key[r]), "r"(claim ? 1u : 0u), "r"(reprobe ? 1u : 0u)
+                    : "=l"(q_old[r])
+                    : "l"(&a.table[q_slot[r] & a.table_mask].key), "l"(kEmpty), "l"(q_key[r]), "r"(claim ? 1u : 0u),
+                      "r"(look ? 1u : 0u)
                     : "memory");
             };
             unsigned long long my_reads = 0, of = 0;
@@ -563,7 +559,6 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 for (int r = 0; r < kRounds; ++r) finish(r);
             }
             if (lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
-            if (my_occ) atomicAdd(&a.st->occupied, my_occ);
             if (a.timing && lane == 0) {
                 atomicAdd(&a.timing[3], k_look), atomicAdd(&a.timing[4], k_wait), atomicAdd(&a.timing[6], k_commit);
             }

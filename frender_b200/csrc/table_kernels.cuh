@@ -13,6 +13,20 @@ __global__ void __launch_bounds__(256) clear_table_kernel(Slot* tab, unsigned lo
         t4[i] = make_ulonglong4(kEmpty, 0ULL, ~0ULL, 0ULL);
 }
 
+// Number of occupied slots (the unique keys of a file).  The scan kernel does not keep this count: knowing who
+// won a slot would mean waiting for every compare-and-swap's result.
+__global__ void __launch_bounds__(256) count_table_kernel(const Slot* __restrict__ tab, unsigned long long cap,
+                                                          unsigned long long* counter) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    unsigned n = 0;
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < cap;
+         i += stride)
+        n += tab[i].key != kEmpty ? 1u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, static_cast<unsigned long long>(n));
+}
+
 // Occupied slots -> dense arrays (arbitrary order); *counter receives the number written.  One atomic per
 // block and pass (a per-warp atomic on the one counter was the kernel's bound: 2 M atomics for 2^26 slots).
 __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restrict__ tab, unsigned long long cap,
