@@ -201,6 +201,25 @@ def test_line_phase_is_by_count_not_by_content(ctx):
     assert list(ctx.counter()["total"].items()) == list(want.items())
 
 
+def test_long_lines(ctx):
+    """Header lines longer than the 512-byte halo (their start is outside the staged bytes) and reads of
+    several kilobytes (a tile holds too few lines for a phase guess): both take the exact slow paths."""
+    import random
+
+    import frender_oracle as O
+    rnd = random.Random(5)
+    keys = ["".join(rnd.choice("ACGTN") for _ in range(10)) + "+" + "".join(rnd.choice("ACGT") for _ in range(10))
+            for _ in range(30)]
+    recs = "".join(f"@{'x' * rnd.choice((30, 700, 1500))}:{i} 1:N:0:{rnd.choice(keys)}\n{'ACGT' * rnd.choice((40, 1500))}\n+\n"
+                   f"{'F' * 100}\n" for i in range(4000))
+    want, visited = O.tally_text(recs.splitlines(keepends=True))
+    for chunk in (None, 1 << 20):
+        ctx.reset()
+        reads, uniq = ctx.scan_bytes(recs.encode(), chunk=chunk)
+        assert reads == visited == 4000 and uniq == len(want)
+        assert list(ctx.counter()["total"].items()) == list(want.items())
+
+
 def test_single_index_c5(ctx, tmp_path):
     """Config 5 shape: 6 bp single index.  The tally is pinned by the oracle (the reference can run it,
     F:154-207); the matcher for single-index sheets is an extension (the reference cannot: F:104-107,
