@@ -37,6 +37,7 @@ SIGNATURES = {
     "frb_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "frb_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "frb_mem_info": (C.c_int, [vp, P(u64), P(u64)]),
+    "frb_write_scan_csv": (C.c_int, [C.c_char_p, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, u32, C.c_int]),
     "frb_pack_key": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, P(u64)]),
     "frb_unpack_key": (C.c_int, [u64, C.c_char_p]),
     "frb_scan_begin": (C.c_int, [vp, u32, u64]),

@@ -424,21 +424,25 @@ def frender_scan(args, ctx=None):
 
 def write_scan_csv(path, tables, res, sheet, idx2_used, ok):
     """idx1,idx2,matched_idx1,matched_idx2,read_type,sample_name,reads,demux_ok -- the layout the
-    reference actually writes (dict insertion order, F:286-291, F:311, F:556; csv.DictWriter F:499)."""
-    keys = unpack_keys(tables.keys)
-    pick = lambda table, rows: [table[i] if i >= 0 else "" for i in rows.tolist()]
-    m1, m2 = pick(sheet.idx1, res["m1"]), pick(idx2_used, res["m2"])
-    if sheet.single:
-        m2 = [""] * len(keys)
-    kinds = [READ_TYPES[t] for t in res["type"].tolist()]
-    names = pick(sheet.ids, res["srow"])
-    with open(path, "w", newline="") as fh:
-        w = csv.writer(fh)
-        w.writerow(["idx1", "idx2", "matched_idx1", "matched_idx2", "read_type", "sample_name", "reads", "demux_ok"])
-        for key, a, b, kind, name, reads, good in zip(keys, m1, m2, kinds, names, tables.counts.tolist(),
-                                                      ok.tolist()):
-            parts = key.split("+")
-            w.writerow([parts[0], parts[1] if len(parts) > 1 else "", a, b, kind, name, reads, good])
+    reference actually writes (dict insertion order, F:286-291, F:311, F:556; csv.DictWriter F:499).
+    Formatted by the library (frb_write_scan_csv): a lane has ~10^7 unique keys."""
+    import ctypes as C
+    n = len(tables.keys)
+
+    def strings(items):
+        arr = (C.c_char_p * max(len(items), 1))()
+        for i, item in enumerate(items):
+            arr[i] = item.encode()
+        return arr
+
+    arrays = [np.ascontiguousarray(tables.keys, np.uint64), np.ascontiguousarray(tables.counts, np.uint64),
+              np.ascontiguousarray(res["m1"], np.int32), np.ascontiguousarray(res["m2"], np.int32),
+              np.ascontiguousarray(res["type"], np.uint8), np.ascontiguousarray(res["srow"], np.int32),
+              np.ascontiguousarray(ok, np.uint8)]
+    rc = _lib.lib.frb_write_scan_csv(os.fsencode(str(path)), *[a.ctypes.data_as(C.c_void_p) for a in arrays], n,
+                                     strings(sheet.idx1), strings(idx2_used), strings(sheet.ids), len(sheet.ids),
+                                     1 if sheet.single else 0)
+    _lib.check(None, rc)
 
 
 # ---------------------------------------------------------------------------------------------

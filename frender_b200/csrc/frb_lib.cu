@@ -1169,3 +1169,4 @@ uint64_t frb_launch_count(frb_ctx* c) { return c->launches; }
 
 #include "frb_route.inl"
 #include "frb_nccl.inl"
+#include "frb_csv.inl"

@@ -75,6 +75,14 @@ int frb_d2h(frb_ctx* ctx, void* host, const void* dptr, size_t nbytes); /* synch
 int frb_mem_info(frb_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes);
 
 /* ---- key packing (host side, exact inverse pair) ------------------------------------------- */
+/* Scan-results CSV, one row per unique key in the order given (F:499-501: csv.DictWriter, default dialect;
+ * idx1,idx2,matched_idx1,matched_idx2,read_type,sample_name,reads,demux_ok).  m1/m2/sample_row index the
+ * string tables of the sheet (-1 = empty field).  Host-only: no context, no device work.                 */
+int frb_write_scan_csv(const char* path, const uint64_t* keys, const uint64_t* counts, const int32_t* m1,
+                       const int32_t* m2, const uint8_t* read_type, const int32_t* sample_row,
+                       const uint8_t* demux_ok, uint64_t n, const char* const* idx1_strings,
+                       const char* const* idx2_strings, const char* const* id_strings, uint32_t rows,
+                       int single_index);
 int frb_pack_key(const char* s, size_t len, int sheet_mode, uint64_t* out);
 int frb_unpack_key(uint64_t key, char* out23); /* writes <= 21 chars + NUL, returns length       */
 

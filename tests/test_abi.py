@@ -74,3 +74,45 @@ def test_product_never_imports_the_oracle():
     if "oracle" in text:
         offenders.append("frender.py")
     assert not offenders, offenders
+
+
+def test_native_scan_csv_writer_matches_csv_module(tmp_path):
+    """frb_write_scan_csv is host-only: its bytes must equal csv.writer's (default dialect, F:499) for keys
+    with zero, one and two '+' parts, empty matches, 2^40 counts and sheet strings that need quoting."""
+    import csv
+    import ctypes as C
+    import io
+
+    import numpy as np
+    from frender_b200 import _lib
+    from frender_b200.engine import pack_keys, unpack_keys
+    keys = np.array(pack_keys(["ACGT+TTTT", "AAAA+CCCC+GG", "NNNN", "", "ACGTACGTAC+ACGTACGTAC"]), np.uint64)
+    counts = np.array([1, 22, 333, 4444, 2 ** 40], np.uint64)
+    m1, m2 = np.array([0, -1, 2, 1, 0], np.int32), np.array([1, -1, 0, 2, 0], np.int32)
+    kind, srow = np.array([2, 0, 3, 1, 2], np.uint8), np.array([0, -1, -1, -1, 2], np.int32)
+    ok = np.array([1, 0, 1, 1, 0], np.uint8)
+    idx1, idx2, ids = ["ACGT", "GG,TT", 'A"B'], ["TTTT", "CCCC", "x\ny"], ["S 1", 'we"ird,name', "plain"]
+
+    def strings(items):
+        arr = (C.c_char_p * len(items))()
+        for i, item in enumerate(items):
+            arr[i] = item.encode()
+        return arr
+
+    path = tmp_path / "out.csv"
+    rc = _lib.lib.frb_write_scan_csv(str(path).encode(),
+                                     *[a.ctypes.data_as(C.c_void_p) for a in (keys, counts, m1, m2, kind, srow, ok)],
+                                     len(keys), strings(idx1), strings(idx2), strings(ids), 3, 0)
+    assert rc == 0
+    buf = io.StringIO(newline="")
+    w = csv.writer(buf)
+    w.writerow(["idx1", "idx2", "matched_idx1", "matched_idx2", "read_type", "sample_name", "reads", "demux_ok"])
+    kinds = ("undetermined", "index_hop", "demuxable", "ambiguous")
+    for k, c, a, b, t, s, o in zip(unpack_keys(keys), counts.tolist(), m1.tolist(), m2.tolist(), kind.tolist(),
+                                   srow.tolist(), ok.tolist()):
+        parts = k.split("+")
+        w.writerow([parts[0], parts[1] if len(parts) > 1 else "", idx1[a] if a >= 0 else "",
+                    idx2[b] if b >= 0 else "", kinds[t], ids[s] if s >= 0 else "", c, bool(o)])
+    assert path.read_bytes() == buf.getvalue().encode()
+    assert _lib.lib.frb_write_scan_csv(b"/nonexistent-dir/x.csv", None, None, None, None, None, None, None, 0,
+                                       strings(idx1), strings(idx2), strings(ids), 3, 0) == _lib.ERR_IO
