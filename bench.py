@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: 400M or what HBM holds)")
+    ap.add_argument("--table-log2", type=int, default=0, help="slots of the unique-key tables (default: by input size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -221,7 +222,7 @@ def run_b200(args):
     probe.close()
     reads = args.reads or 400_000_000
     bytes_per_read = 375.0
-    table_log2 = 26 if reads > 100_000_000 else (24 if reads > 8_000_000 else 21)
+    table_log2 = args.table_log2 or (26 if reads > 100_000_000 else (24 if reads > 8_000_000 else 21))
     overhead = 2 * (32 << table_log2) + (8 << 30)
     fit = int((free_b.value - overhead) / bytes_per_read)
     if reads > fit:
