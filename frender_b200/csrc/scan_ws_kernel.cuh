@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 if (k < warp) wbase += v;
                 total += v;
             }
+            // the tile's newline count goes out the moment it is known (before the list is built): every later
+            // tile's look-back waits for it.  Thread 32: not the thread that arrives on the mbarrier below
+            if (ct == 32) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
             // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
             const unsigned vnl = (t == a.n_tiles - 1 && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
             {   // ordered list of newline positions; line numbers come later, from the look-back
@@ -255,7 +258,6 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             }
             if (ct == 0) {
                 s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
-                status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
             }
             group_sync<kWsGroup>(1);  // list + meta complete (also protects s_cwarp)
             if (ct == 0) mbar_arrive(&s_counted[s]);
