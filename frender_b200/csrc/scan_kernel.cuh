@@ -139,13 +139,14 @@ __device__ __forceinline__ unsigned eq_flags(unsigned w, unsigned pat) {
     return ~(t | x) & 0x80808080u;
 }
 // 16-bit mask (bit i = byte i) of the bytes of v equal to the byte replicated in `pat`.
-// One multiply moves a word's four flags (bits 7/15/23/31) into the top nibble of the product in
-// byte order: y * 0x204081 has flag b at bit 28 + b and nothing else up there (all partial
-// products land on distinct bits, so no carries).
+// The flags (0x80 per equal byte) are gathered with byte dot products: weights 1,2,4,8 for the first word
+// of a pair and 16,32,64,128 for the second give mask8 * 128, on the multiply pipe instead of the ALU.
 __device__ __forceinline__ unsigned eq_mask16(const uint4 v, unsigned pat) {
-    const unsigned p0 = eq_flags(v.x, pat) * 0x00204081u, p1 = eq_flags(v.y, pat) * 0x00204081u;
-    const unsigned p2 = eq_flags(v.z, pat) * 0x00204081u, p3 = eq_flags(v.w, pat) * 0x00204081u;
-    return (p0 >> 28) | ((p1 >> 24) & 0xF0u) | ((p2 >> 20) & 0xF00u) | ((p3 >> 16) & 0xF000u);
+    unsigned lo = __dp4a(eq_flags(v.x, pat), 0x08040201u, 0u);
+    lo = __dp4a(eq_flags(v.y, pat), 0x80402010u, lo);
+    unsigned hi = __dp4a(eq_flags(v.z, pat), 0x08040201u, 0u);
+    hi = __dp4a(eq_flags(v.w, pat), 0x80402010u, hi);
+    return (lo >> 7) | (hi << 1);
 }
 __device__ __forceinline__ unsigned newline_mask16(const uint4 v) { return eq_mask16(v, 0x0A0A0A0Au); }
 
