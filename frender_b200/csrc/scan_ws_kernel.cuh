@@ -149,12 +149,15 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 #pragma unroll 2
                 for (int j = 0; j < 8; ++j) {
                     const int r = (j + ct) & 7;
-                    const int sh = (r & 3) * 16;
+                    // the 16-bit mask lands at bit 16 * (r & 3) of the low or the high 64-bit word: as a
+                    // 32 x 64 -> 64-bit multiply-add (fields never overlap, so + is |), on the multiply pipe
+                    const unsigned long long place = 1ULL << ((r & 3) * 16);
+                    const unsigned long long to_lo = r < 4 ? place : 0ULL, to_hi = r < 4 ? 0ULL : place;
 #pragma unroll
                     for (int g = 0; g < kGroups; ++g) {
-                        const unsigned long long mg = newline_mask16(t4[8 * g + r]);
-                        if (r < 4) mlo[g] |= mg << sh;
-                        else mhi[g] |= mg << sh;
+                        const unsigned mg = newline_mask16(t4[8 * g + r]);
+                        mlo[g] += mg * to_lo;
+                        mhi[g] += mg * to_hi;
                     }
                 }
 #pragma unroll
