@@ -362,6 +362,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.no_guess = no_guess;
     a.redo = ws ? c->redo : nullptr;
     a.tile_bytes = static_cast<unsigned>(tile);
+    a.pat_nl = 0x0A0A0A0Au;
+    a.pat_sp = 0x20202020u;
     if (a.redo) CU(c, cudaMemsetAsync(&c->st->redo_n, 0, 8, c->compute));
     a.dbg_flags = getenv("FRB_DBG_FLAGS") ? atoi(getenv("FRB_DBG_FLAGS")) : 0;
     static unsigned long long* timing = nullptr;

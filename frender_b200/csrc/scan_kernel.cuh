@@ -63,6 +63,10 @@ struct ScanArgs {
     unsigned int* redo;       // warp-specialised kernel: tiles left to scan_redo_kernel, capacity n_tiles
     unsigned int tile_bytes;  // tile size of the kernel that filled status[] (for scan_redo_kernel)
     int no_guess;             // A-B: never guess the line phase from the text
+    // '\n' and ' ' replicated over a word.  Kernel parameters, not literals: with the pattern in a register the
+    // byte compare is three instructions per word (LOP3 takes one immediate; as a literal next to the 0x7f..
+    // mask the pattern costs a fourth).
+    unsigned int pat_nl, pat_sp;
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy ------------------------------------------------
@@ -132,11 +136,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 #define kFoldLsb3 0x1249249249249249ULL  // bit 0 of every 3-bit group
 
 // ---- byte-compare primitives ---------------------------------------------------------------
-// bit 7 of every byte of w that equals the byte replicated in `pat`; exact (no borrow leaks).
+// bit 7 of every byte of w that equals the byte replicated in `pat` (pattern bytes < 0x80); exact (no borrow
+// leaks).  (w & 0x7f..) ^ pat is the low seven bits of w ^ pat, and bit 7 of w ^ pat is bit 7 of w.
 __device__ __forceinline__ unsigned eq_flags(unsigned w, unsigned pat) {
-    unsigned x = w ^ pat;
-    unsigned t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    return ~(t | x) & 0x80808080u;
+    const unsigned t = ((w & 0x7F7F7F7Fu) ^ pat) + 0x7F7F7F7Fu;
+    return ~(t | w) & 0x80808080u;
 }
 // 16-bit mask (bit i = byte i) of the bytes of v equal to the byte replicated in `pat`.
 // The flags (0x80 per equal byte) are gathered with byte dot products: weights 1,2,4,8 for the first word
@@ -148,11 +152,11 @@ __device__ __forceinline__ unsigned eq_mask16(const uint4 v, unsigned pat) {
     hi = __dp4a(eq_flags(v.w, pat), 0x80402010u, hi);
     return (lo >> 7) | (hi << 1);
 }
-__device__ __forceinline__ unsigned newline_mask16(const uint4 v) { return eq_mask16(v, 0x0A0A0A0Au); }
+__device__ __forceinline__ unsigned newline_mask16(const uint4 v, unsigned pat_nl) { return eq_mask16(v, pat_nl); }
 
 // Number of ' ' in buf[sb, eb) for lines that end within 112 bytes of their 16-byte-aligned start,
 // else -1.  Fully unrolled and branch-free: seven independent 16-byte shared loads in flight.
-__device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsigned sb, unsigned eb) {
+__device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsigned sb, unsigned eb, unsigned pat_sp) {
     const unsigned a0 = sb & ~15u;
     if (eb - a0 > 112u) return -1;
     unsigned cnt = 0;
@@ -161,7 +165,7 @@ __device__ __forceinline__ int count_spaces_fast(const unsigned char* buf, unsig
         const unsigned p = a0 + 16u * i;
         if (i >= 4 && p >= eb) break;  // ordinary header lines span 5 segments; the loads stay batched
         const uint4 v = *reinterpret_cast<const uint4*>(buf + (p < eb ? p : a0));
-        unsigned m = eq_mask16(v, 0x20202020u);
+        unsigned m = eq_mask16(v, pat_sp);
         const unsigned lo_cut = sb > p ? sb - p : 0u;                  // bytes of this segment before the line
         const unsigned hi_cut = eb > p ? (eb - p < 16u ? eb - p : 16u) : 0u;  // bytes of it inside [.., eb)
         m &= (0xFFFFu << lo_cut) & ((1u << hi_cut) - 1u);
@@ -231,7 +235,7 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
         // Fast path, branch-free and latency-flat.  With exactly one ' ' in the line the key is the
         // text after the last ':' or ' ' (the 2nd space token runs to the end of the line).  The line
         // has at least 22 bytes, so the 22 bytes before its end all belong to it.
-        const int spaces = scan_rule ? count_spaces_fast(buf, sb, eb) : 1;
+        const int spaces = scan_rule ? count_spaces_fast(buf, sb, eb, a.pat_sp) : 1;
         const unsigned char* const e = buf + eb;
         unsigned delim = 0, lo = 0, hi = 0, top = 0;
 #pragma unroll
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
 #pragma unroll
         for (int j = 0; j < kPerThread / 16; ++j) {
             const int seg = (j + tid) & 7;  // rotate so a quarter-warp hits 8 distinct bank groups
-            const unsigned long long m = newline_mask16(t4[seg]);
+            const unsigned long long m = newline_mask16(t4[seg], a.pat_nl);
             const int sh = (seg & 3) * 16;
             if (seg < 4) lo |= m << sh;
             else hi |= m << sh;
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(NT, ScanCfg<NT>::ctas_per_sm) scan_kernel(cons
             if (t == 0) {
                 if (lane == 0) s_halo_start = kHalo;
             } else {
-                const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane]);
+                const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane], a.pat_nl);
                 const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
                 if (any == 0) {
                     if (lane == 0) s_halo_start = kUnknown;

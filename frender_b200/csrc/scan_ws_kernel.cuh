@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     const unsigned long long to_lo = r < 4 ? place : 0ULL, to_hi = r < 4 ? 0ULL : place;
 #pragma unroll
                     for (int g = 0; g < kGroups; ++g) {
-                        const unsigned mg = newline_mask16(t4[8 * g + r]);
+                        const unsigned mg = newline_mask16(t4[8 * g + r], a.pat_nl);
                         mlo[g] += mg * to_lo;
                         mhi[g] += mg * to_hi;
                     }
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 #pragma unroll
                 for (int j = 0; j < G::seg; ++j) {
                     const int r = (j == G::seg - 1) ? (rot ? 0 : j) : j + (rot ? 1 : 0);
-                    m[j] = newline_mask16(t4[r]);
+                    m[j] = newline_mask16(t4[r], a.pat_nl);
                 }
 #pragma unroll
                 for (int q = 0; q < kWords; ++q) {
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 if (t == 0) {
                     if (lane == 0) s_halo[s] = kHalo;
                 } else {
-                    const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane]);
+                    const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane], a.pat_nl);
                     const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
                     if (any == 0) {
                         if (lane == 0) s_halo[s] = kUnknown;
