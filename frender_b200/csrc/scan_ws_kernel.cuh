@@ -224,23 +224,28 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 // word -- a third one means lines shorter than 16 bytes -- keeps the warp out of a
                 // data-dependent loop.
                 if (wbase + incl <= static_cast<unsigned>(kWsNlCap)) {
+                    // predicated stores (no branch) for the first two newlines of a word; a third is rare
+                    auto store_if = [](uint16_t* p, unsigned value, unsigned cond) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}"
+                            ::"r"(smem_addr(p)), "h"(static_cast<unsigned short>(value)), "r"(cond)
+                            : "memory");
+                    };
 #pragma unroll
                     for (int q = 0; q < kWords; ++q) {
                         const unsigned m = w[q];
-                        if (m) {
-                            nl[idx] = static_cast<uint16_t>(pos0 + (__ffs(m) - 1));
-                            unsigned m2 = m & (m - 1);
-                            if (m2) {
-                                nl[idx + 1] = static_cast<uint16_t>(pos0 + (__ffs(m2) - 1));
+                        store_if(nl + idx, pos0 + (__ffs(m) - 1), m);
+                        unsigned m2 = m & (m - 1);
+                        store_if(nl + idx + 1, pos0 + (__ffs(m2) - 1), m2);
+                        m2 &= m2 - 1;
+                        if (m2) {
+                            unsigned k = idx + 2;
+                            do {
+                                nl[k++] = static_cast<uint16_t>(pos0 + (__ffs(m2) - 1));
                                 m2 &= m2 - 1;
-                                unsigned k = idx + 2;
-                                while (m2) {
-                                    nl[k++] = static_cast<uint16_t>(pos0 + (__ffs(m2) - 1));
-                                    m2 &= m2 - 1;
-                                }
-                            }
-                            idx += __popc(m);
+                            } while (m2);
                         }
+                        idx += __popc(m);
                         pos0 += 32;
                     }
                 }
