@@ -286,34 +286,55 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
 template <bool kBlocking>
 __device__ __forceinline__ bool tile_prefix(volatile unsigned long long* status, unsigned t, unsigned total,
                                             int lane, unsigned long long* out) {
+    // Windows of 128 predecessors per step (four independent loads per lane, one L2 round trip).  The distance
+    // to the nearest inclusive word is (look-back latency) x (tiles finished per cycle), and the latency is
+    // (distance / window) round trips: with 32-wide windows that loop gain was about 1 at this kernel's tile
+    // rate (a look-back took 4-5 round trips); at 128 it is a quarter of that.
+    constexpr int kSub = 4;
     *out = 0;
     if (t == 0) return true;  // published as inclusive by the count stage
-    unsigned long long excl = 0;
+    unsigned long long acc = 0;  // lane-local partial sum, reduced once at the end
     long long idx = static_cast<long long>(t) - 1;
     for (;;) {
-        const long long j = idx - lane;
-        bool done;
-        for (;;) {
-            const unsigned long long s = (j >= 0) ? status[j] : kFlagInc;
-            const unsigned none = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 0);
-            const unsigned inc = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
-            const int first_inc = inc ? (__ffs(inc) - 1) : 32;
-            const unsigned relevant = (first_inc >= 31) ? 0xFFFFFFFFu : ((2u << first_inc) - 1u);
-            if ((none & relevant) == 0) {
-                unsigned long long v = (lane <= first_inc) ? (s & kValMask) : 0ULL;
+        bool done = false;
+        for (;;) {  // until every word this step needs has been published
+            unsigned long long s[kSub];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                excl += v;
-                done = first_inc < 32;
+            for (int m = 0; m < kSub; ++m) {
+                const long long j = idx - 32 * m - lane;
+                s[m] = (j >= 0) ? status[j] : kFlagInc;
+            }
+            unsigned long long part = 0;
+            bool ready = true;
+#pragma unroll
+            for (int m = 0; m < kSub; ++m) {
+                if (ready && !done) {
+                    const unsigned none = __ballot_sync(0xFFFFFFFFu, (s[m] >> 62) == 0);
+                    const unsigned inc = __ballot_sync(0xFFFFFFFFu, (s[m] >> 62) == 2);
+                    const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+                    const unsigned relevant = (first_inc >= 31) ? 0xFFFFFFFFu : ((2u << first_inc) - 1u);
+                    if (none & relevant) {
+                        ready = false;
+                    } else {
+                        part += (lane <= first_inc) ? (s[m] & kValMask) : 0ULL;
+                        done = first_inc < 32;
+                    }
+                }
+            }
+            if (ready) {
+                acc += part;
                 break;
             }
+            done = false;
             if (!kBlocking) return false;
         }
         if (done) break;
-        idx -= 32;
+        idx -= 32 * kSub;
     }
-    if (lane == 0) status[t] = kFlagInc | (excl + total);
-    *out = excl;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if (lane == 0) status[t] = kFlagInc | (acc + total);
+    *out = acc;
     return true;
 }
 
