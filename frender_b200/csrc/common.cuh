@@ -50,14 +50,13 @@ __host__ __device__ __forceinline__ char dec_sym(uint32_t code) {
     return t[code & 7];
 }
 
-// Table hash: fold the high symbols down, one 64-bit multiply, keep the well-mixed upper half.  (Keys are
-// packed 3-bit symbols; sheets of a few hundred samples plus their one-mismatch neighbourhoods differ in
-// one or two symbols anywhere in the word, so both halves have to reach the slot index.)  Measured on the
-// unique keys of a C2-shaped lane: same share of keys with a shared home slot as the murmur3 finaliser.
 __host__ __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
-    k ^= k >> 31;
-    k *= 0x9E3779B97F4A7C15ULL;
-    return (k >> 29) ^ (k >> 47);
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
 }
 
 #ifdef __CUDACC__
