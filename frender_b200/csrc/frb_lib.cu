@@ -328,7 +328,7 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : tall ? WsTall::tile : trio ? WsTrio::tile : WsWide::tile)
                                                    : (nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile));
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
-    if (n_tiles >= 0xFFFFFFFFULL) return fail(c, FRB_ERR_ARG, "chunk too large");
+    if (n_tiles >= 0xFFFFFFFFULL || nbytes >= (1ULL << 40)) return fail(c, FRB_ERR_ARG, "chunk too large");
     if (n_tiles + 1 > c->status_cap) {
         if (c->status) CU(c, cudaFree(c->status));
         c->status = nullptr;

@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __shared__ unsigned s_tile[kStages], s_total[kStages], s_valid[kStages], s_vnl[kStages];
     __shared__ unsigned s_cwarp[kWsGroup / 32];
     __shared__ unsigned s_halo[kStages];
-    __shared__ unsigned long long s_prefix[4];
-    __shared__ volatile unsigned s_ready[4];  // i + 1 once s_prefix[i & 3] holds the prefix of local tile i
+    // prefix of local tile i for the extractors that asked for it: ((i + 1) & 0xFFFFFF) << 40 | newlines before
+    // the tile (< 2^40), one word so that no fence is needed between value and flag (a fence in the committer
+    // waits for its outstanding table atomics)
+    __shared__ volatile unsigned long long s_prefix[4];
     __shared__ __align__(8) unsigned long long s_bfull[kBatches], s_bfree[kBatches];
     __shared__ unsigned long long s_keys[kBatches][kExt];  // kEmpty except on the first lane of every run of equal keys
     __shared__ unsigned char s_kcnt[kBatches][kExt];      // reads folded into that entry
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 
     for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, a.rule);
     if (tid == 0) {
-        s_ready[0] = 0, s_ready[1] = 0, s_ready[2] = 0, s_ready[3] = 0;
+        s_prefix[0] = 0, s_prefix[1] = 0, s_prefix[2] = 0, s_prefix[3] = 0;
         if (blockIdx.x == 0) a.st->chunk_l0 = L0;
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
@@ -350,9 +352,11 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 ++nb;
             };
             auto wait_prefix = [&](unsigned i) -> unsigned long long {
-                while (s_ready[i & 3] != i + 1) {}
-                __threadfence_block();
-                return L0 + *reinterpret_cast<volatile unsigned long long*>(&s_prefix[i & 3]);
+                unsigned long long word;
+                do {
+                    word = s_prefix[i & 3];
+                } while ((word >> 40) != ((i + 1) & 0xFFFFFFu));
+                return L0 + (word & ((1ULL << 40) - 1));
             };
             unsigned long long next_ticket = 0;
             if (pt == 0) {
@@ -521,9 +525,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     tile_ok = !(flags & BF_DENSE) &&
                               (!(flags & BF_GUESSED) || static_cast<unsigned>((4 - (K0 & 3)) & 3) == m[BM_J0]);
                     if (lane == 0) {
-                        s_prefix[i & 3] = excl;
-                        __threadfence_block();
-                        s_ready[i & 3] = i + 1;
+                        s_prefix[i & 3] = (static_cast<unsigned long long>((i + 1) & 0xFFFFFFu) << 40) | excl;
                         if (tile_ok) {
                             const unsigned long long o_end = (K0 + m[BM_LINES] + 3) >> 2;
                             const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
