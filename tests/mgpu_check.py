@@ -54,6 +54,8 @@ def main():
     dist.all_gather_object(shares, (unpack_keys(skeys), scounts.tolist(), sfirst.tolist(), sres))
     union = [(f, k, n) for ks, ns, fs, _ in shares for k, n, f in zip(ks, ns, fs)]
     assert len({k for _, k, _ in union}) == len(union), "shares overlap"
+    from frender_b200.shard import key_owner           # host twin of the device's owner function
+    assert all(key_owner(int(pk), world) == rank for pk in skeys.tolist()), "a key sits on the wrong rank"
     assert sorted(fs for fs in shares[rank][2]) == shares[rank][2], "share not in first-appearance order"
     union.sort()
     assert [(k, n) for _, k, n in union] == list(want.items()), "union of the shares differs from the oracle"

@@ -48,6 +48,57 @@ def test_merge_is_rank_count_invariant_gloo(tmp_path):
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+SHARD_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+import numpy as np
+import torch.distributed as dist
+import frender_oracle as O
+from frender_b200 import synth
+from frender_b200.engine import pack_keys
+from frender_b200.shard import assign, fold_share, key_owner, merge_lists, shard_lists
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+spec = synth.make_spec("C1", n_samples=12)
+chunks = [(i, i * 500, (i + 1) * 500) for i in range(7)]
+local = []
+for ordinal, g0, g1 in assign(chunks, rank, world):
+    counter, _ = O.tally_text(synth.generate(spec, g0, g1).decode().splitlines(keepends=True))
+    firsts = {{}}
+    for pos, key in enumerate(synth.keys_of(spec, g0, g1)):
+        firsts.setdefault(key, (ordinal << 40) | pos)
+    local += [(k, n, firsts[k]) for k, n in counter.items()]
+mine = merge_lists([local])                                   # the rank's own total, as before the exchange
+entries = [(k, n, min(p for kk, _, p in local if kk == k)) for k, n in mine.items()]
+pack = lambda key: int(pack_keys([key])[0])
+parts = shard_lists(entries, world, pack)                     # what this rank sends to every peer
+everything = [None] * world
+dist.all_gather_object(everything, parts)                     # stands in for the grouped send/recv
+share = fold_share([everything[src][rank] for src in range(world)])
+assert all(key_owner(pack(k), world) == rank for k, _, _ in share)
+shares = [None] * world
+dist.all_gather_object(shares, share)
+union = sorted((pos, k, n) for sh in shares for k, n, pos in sh)
+assert len({{k for _, k, _ in union}}) == len(union), "shares overlap"
+want, _ = O.tally_text(synth.generate(spec, 0, 3500).decode().splitlines(keepends=True))
+assert [(k, n) for _, k, n in union] == list(want.items()), "union of the shares differs from the oracle"
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_merge_gloo(tmp_path):
+    """Host twin of frb_shardmerge on two gloo ranks: owner partition, exchange, fold; the shares are
+    disjoint, every key sits on its owner, and their union is the single-process oracle's tally in order."""
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29536", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_assign_covers_everything_once():
     from frender_b200.shard import assign
     items = list(range(23))
