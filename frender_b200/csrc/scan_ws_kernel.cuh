@@ -3,17 +3,19 @@
 //
 //   warps 0-3  COUNTERS    for tile i: wait for its bytes (TMA mbarrier), 256 bytes per thread ->
 //                          newline mask, group scan, ordered newline-position list in shared memory,
-//                          publish the tile's newline count, signal `counted[stage]`.
-//   warps 4-6  EXTRACTORS  for tile i: one thread per header line: key extraction, warp fold, deferred
-//                          table update; thread 0 then refills the stage (bulk copy of tile i+3).
-//   warp  7    HELPER      runs one tile ahead of the extractors: start of the line that straddles the
-//                          tile start, look-back over the published counts (line number of the tile's
-//                          first newline -- the only wait on other CTAs), ticket for the next refill.
+//                          start of the line that straddles the tile start, publish the tile's newline
+//                          count, signal `counted[stage]`.
+//   warps 4-6  EXTRACTORS  for tile i: guess which lines are header lines from the text, one thread per
+//                          header line: key extraction, fold inside the warp, key batch into a shared-
+//                          memory ring for the committer; thread 0 then refills the stage (ticket +
+//                          bulk copy).  No global atomics besides the ticket.
+//   warp  7    COMMITTER   per tile: look-back over the published counts (the only wait on other CTAs),
+//                          check of the extractors' guess against it, bookkeeping; per batch: deferred
+//                          table updates.  Tiles whose guess was wrong go to scan_redo_kernel.
 //
-// Counters and the parser side only meet through shared-memory mbarriers (full -> counted per stage);
-// helper and extractors meet once per tile at a named barrier.  Counting tile i+1, preparing tile i+1
-// and extracting tile i overlap, and a helper that waits on another CTA's count never stops its own
-// CTA's counters or extractors.
+// The roles only meet through shared-memory mbarriers (full -> counted per stage, full/free per key
+// batch).  With 3 CTAs per SM the launch register budget is re-split between the two warpgroups
+// (setmaxnreg): counters 48, extractors + committer 112.
 #pragma once
 #include "scan_kernel.cuh"
 
