@@ -492,6 +492,8 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTall>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTall::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTrio>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTrio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(match_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(c, cudaFuncSetAttribute(match_idx1_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TRY(clear_table(c, c->total_tab));
     CU(c, cudaStreamSynchronize(c->compute));
     *out = c;
@@ -1047,10 +1049,20 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
         c->m1_total_gen = c->total_gen, c->m1_sheet_gen = c->sheet_gen, c->m1_n_subs = n_subs;
         c->m1_from_rc = rc_mode != 0;
         ProfScope ps(c, FRB_K_MATCH);
+        // candidate rows from per-part tables instead of a sweep over the sheet, whenever the shape allows
+        static const bool sweep_only = getenv("FRB_MATCH") && strcmp(getenv("FRB_MATCH"), "sweep") == 0;
+        const unsigned parts = n_subs + 1;
+        const unsigned slots = static_cast<unsigned long long>(c->rows) * parts * 2 <= 2048 ? 2048u : 4096u;
+        const bool cand = !sweep_only && c->l2 > 0 && parts_usable(c->l1, n_subs, c->rows, slots) &&
+                          parts_usable(c->l2, n_subs, c->rows, slots);
         if (!reuse) {
             CU(c, cudaMemsetAsync(c->work_n, 0, 8, c->compute));
-            match_idx1_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads,
-                                static_cast<size_t>(c->rows) * 8 + 16, c->compute>>>(a);
+            if (cand)
+                match_idx1_cand_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 4), kMatchThreads,
+                                         cand_bytes(c->rows, parts, slots) + 16, c->compute>>>(a, slots);
+            else
+                match_idx1_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads,
+                                    static_cast<size_t>(c->rows) * 8 + 16, c->compute>>>(a);
             c->launches++;
         } else {
             // keys off the work list stay undetermined; m1 is already -1 for them
@@ -1058,8 +1070,13 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
             CU(c, cudaMemsetAsync(c->srow, 0xFF, n * 4, c->compute));
             CU(c, cudaMemsetAsync(c->type, 0, n, c->compute));
         }
-        const size_t smem = static_cast<size_t>(c->rows) * (4 * 8 + 4) + 16;
-        match_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads, smem, c->compute>>>(a);
+        if (cand) {
+            const size_t smem = static_cast<size_t>(c->rows) * 24 + 32 + (rc_mode ? 2 : 1) * cand_bytes(c->rows, parts, slots);
+            match_cand_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 4), kMatchThreads, smem, c->compute>>>(a, slots);
+        } else {
+            const size_t smem = static_cast<size_t>(c->rows) * (4 * 8 + 4) + 16;
+            match_kernel<<<grid_for(n, kMatchThreads, c->sm_count, 8), kMatchThreads, smem, c->compute>>>(a);
+        }
         c->launches++;
         CU(c, cudaGetLastError());
     }
