@@ -96,6 +96,42 @@ def test_matcher_kats(ctx, golden):
         assert got == {c["key"]: c["want"]} and list(got[c["key"]]) == list(c["want"]), c
 
 
+def test_matcher_random_sheets_vs_oracle(ctx):
+    """Random sheets (duplicated index values as in combinatorial designs, 6/8/10 bp, n = 0..4) and keys a few
+    substitutions away from sheet rows, N included: the device matcher (candidate tables for n <= 3, sweep
+    beyond) must give the oracle's classification, matched strings, sample names and orientation calls."""
+    import random
+
+    import frender_oracle as O
+    from frender_b200.engine import process
+    rnd = random.Random(23)
+    for trial in range(24):
+        l = rnd.choice([6, 8, 10])
+        n = rnd.choice([0, 1, 1, 2, 3, 4])
+        rows = rnd.choice([3, 17, 96])
+        pool1 = ["".join(rnd.choice("ACGT") for _ in range(l)) for _ in range(max(2, rows // rnd.choice([1, 1, 4])))]
+        pool2 = ["".join(rnd.choice("ACGT") for _ in range(l)) for _ in range(max(2, rows // rnd.choice([1, 1, 4])))]
+        idx = {"id": [f"s{r % max(1, rows - 2)}" for r in range(rows)],          # a few repeated sample names
+               "idx1": [rnd.choice(pool1) for _ in range(rows)], "idx2": [rnd.choice(pool2) for _ in range(rows)]}
+        counter = {}
+        for _ in range(400):
+            r = rnd.randrange(rows)
+            a = list(idx["idx1"][r])
+            b = list(rnd.choice([idx["idx2"][rnd.randrange(rows)], O.reverse_complement(idx["idx2"][r])]))
+            for word in (a, b):
+                for _ in range(rnd.choice([0, 0, 1, 2, 3])):
+                    word[rnd.randrange(l)] = rnd.choice("ACGTN")
+            counter.setdefault("".join(a) + "+" + "".join(b), rnd.randrange(1, 50))
+        rc_mode = trial % 2 == 0
+        got = process(1, counter, idx, n, rc_mode, ctx=ctx)
+        want = O.process(1, counter, idx, n, rc_mode)
+        assert got == want, (trial, l, n, rows, rc_mode)
+        if rc_mode:
+            res, calls, _ = ctx.analyze(idx, n, True, counter=counter)
+            want_res, want_calls, _ = O.scan_analysis(1, {"total": counter}, idx, n, True)
+            assert res == want_res and calls == want_calls, (trial, "second pass")
+
+
 def test_length_mismatch_raises(ctx):
     from frender_b200.engine import process
     idx = {"id": ["a"], "idx1": ["AAAAAAAA"], "idx2": ["CCCCCCCC"]}
