@@ -264,7 +264,7 @@ int ensure_cub_tmp(frb_ctx* c, size_t bytes) {
 // Dense (key,count,first) arrays in arbitrary order -> list sorted by `first` (first-appearance order,
 // F:172-177 / F:199-205).  Takes over k0/c0/f0 (pool allocations) and frees them.
 int unsorted_to_sorted_list(frb_ctx* c, unsigned long long* k0, unsigned long long* c0, unsigned long long* f0,
-                            uint64_t n, KeyList* out) {
+                            uint64_t n, KeyList* out, int first_bits = 64) {
     out->n = n;
     unsigned *i0 = nullptr, *i1 = nullptr;
     if (n) {
@@ -276,11 +276,13 @@ int unsorted_to_sorted_list(frb_ctx* c, unsigned long long* k0, unsigned long lo
         ProfScope ps(c, FRB_K_EXPORT);
         iota_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i0, n);
         size_t tmp = 0;
-        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0, 64,
-                                              c->compute));
+        // first_bits: significant bits of `first` (a file's read ordinals stay below 2^40: five radix passes
+        // instead of eight)
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0,
+                                              first_bits, c->compute));
         TRY(ensure_cub_tmp(c, tmp));
-        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0, 64,
-                                              c->compute));
+        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, f0, out->first, i0, i1, static_cast<int>(n), 0,
+                                              first_bits, c->compute));
         gather2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i1, k0, c0, out->keys,
                                                                                        out->counts, n);
         c->launches += 9;  // iota, cub radix sort passes (approximate), gather
@@ -295,7 +297,7 @@ int unsorted_to_sorted_list(frb_ctx* c, unsigned long long* k0, unsigned long lo
 }
 
 // Table -> list sorted by `first`.
-int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
+int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out, int first_bits = 64) {
     out->n = n;
     if (n == 0) return FRB_OK;
     if (n >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
@@ -311,7 +313,7 @@ int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out) {
         c->launches++;
         CU(c, cudaGetLastError());
     }
-    return unsorted_to_sorted_list(c, k0, c0, f0, n, out);
+    return unsorted_to_sorted_list(c, k0, c0, f0, n, out, first_bits);
 }
 
 int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t line_base, int rule,
@@ -669,7 +671,7 @@ int frb_scan_end(frb_ctx* c, uint64_t* n_reads, uint64_t* n_unique) {
     KeyList fl;
     fl.reads = c->st_host->n_reads;
     fl.ordinal = c->cur_ordinal;
-    TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl));
+    TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl, 40));  // read ordinals of one file
     c->files.push_back(fl);
     c->total_ready = false;
     if (n_reads) *n_reads = fl.reads;
