@@ -396,15 +396,12 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     bool guessed = false;
                     unsigned j0 = 0;
                     if (may_guess && total >= 9 && halo_start != kUnknown) {
-                        unsigned first[8];  // first byte of the tile's lines 0..7
-                        first[0] = buf[halo_start];
-#pragma unroll
-                        for (int c = 1; c < 8; ++c) first[c] = buf[nl[c - 1] + 1u];
-                        unsigned hits = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (first[c] == '@' && first[c + 2] == '+' && first[c + 4] == '@') hits |= 1u << c;
-                        }
+                        // lane c < 8 looks at the first byte of the tile's line c
+                        const unsigned c = lane & 7;
+                        const unsigned first = buf[c ? nl[c - 1] + 1u : halo_start];
+                        const unsigned at = __ballot_sync(0xFFFFFFFFu, first == '@') & 0xFFu;
+                        const unsigned plus = __ballot_sync(0xFFFFFFFFu, first == '+') & 0xFFu;
+                        const unsigned hits = at & (plus >> 2) & (at >> 4) & 0xFu;
                         if (__popc(hits) == 1) guessed = true, j0 = __ffs(hits) - 1;
                     }
                     unsigned long long of = 0;  // first read ordinal owned by the tile (known if !guessed)
