@@ -22,8 +22,9 @@
 #include "common.cuh"
 #include "match_kernel.cuh"
 #include "route_kernel.cuh"
-#include "scan_kernel.cuh"
+#include "scan_common.cuh"
 #include "scan_ws_kernel.cuh"
+#include "scan_ws_r1_kernel.cuh"
 #include "synth_kernel.cuh"
 #include "table_kernels.cuh"
 
@@ -321,14 +322,10 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
                 uint64_t out_cap = ~0ULL) {
     if (nbytes == 0) return FRB_OK;
     if (reinterpret_cast<uintptr_t>(dev) & 15) return fail(c, FRB_ERR_ARG, "chunk pointer must be 16-byte aligned");
-    static const int nt = getenv("FRB_SCAN_THREADS") ? atoi(getenv("FRB_SCAN_THREADS")) : 256;
-    // default: warp-specialised kernel; FRB_SCAN_KERNEL=std selects the barrier-synchronous pipeline
-    static const bool ws = getenv("FRB_SCAN_KERNEL") ? strcmp(getenv("FRB_SCAN_KERNEL"), "std") != 0 : true;
-    static const bool dense = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "dense") == 0 : false;
-    static const bool tall = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "tall") == 0 : false;
-    static const bool trio = getenv("FRB_WS_GEOM") ? strcmp(getenv("FRB_WS_GEOM"), "trio") == 0 : true;  // default
-    const uint64_t tile = static_cast<uint64_t>(ws ? (dense ? WsDense::tile : tall ? WsTall::tile : trio ? WsTrio::tile : WsWide::tile)
-                                                   : (nt == 128 ? ScanCfg<128>::tile : ScanCfg<256>::tile));
+    // FRB_SCAN_KERNEL=r1: the round-1 kernel (same-box A/B); FRB_SCAN_LEAN=0: general instantiation everywhere
+    static const bool r1 = getenv("FRB_SCAN_KERNEL") && strcmp(getenv("FRB_SCAN_KERNEL"), "r1") == 0;
+    static const bool lean_ok = !(getenv("FRB_SCAN_LEAN") && atoi(getenv("FRB_SCAN_LEAN")) == 0);
+    const uint64_t tile = static_cast<uint64_t>(r1 ? R1Trio::tile : WsTile::tile);
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL || nbytes >= (1ULL << 40)) return fail(c, FRB_ERR_ARG, "chunk too large");
     if (n_tiles + 1 > c->status_cap) {
@@ -359,66 +356,49 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.out_cap = out_cap;
     a.n_tiles = static_cast<unsigned>(n_tiles);
     a.rule = rule;
-    a.no_tma = getenv("FRB_SCAN_NO_TMA") != nullptr;
     static const bool no_guess = getenv("FRB_SCAN_NO_GUESS") != nullptr;
     a.no_guess = no_guess;
-    a.redo = ws ? c->redo : nullptr;
+    a.redo = c->redo;
     a.tile_bytes = static_cast<unsigned>(tile);
     a.pat_nl = 0x0A0A0A0Au;
     a.pat_sp = 0x20202020u;
-    if (a.redo) CU(c, cudaMemsetAsync(&c->st->redo_n, 0, 8, c->compute));
-    a.dbg_flags = getenv("FRB_DBG_FLAGS") ? atoi(getenv("FRB_DBG_FLAGS")) : 0;
+    CU(c, cudaMemsetAsync(&c->st->redo_n, 0, 8, c->compute));
     static unsigned long long* timing = nullptr;
     if (getenv("FRB_SCAN_TIMING")) {
         if (!timing) cudaMalloc(&timing, 128);
         cudaMemsetAsync(timing, 0, 128, c->compute);
         a.timing = timing;
     }
+    // the lean instantiation serves the tally of whole files: scan rule, no per-read outputs, no -s limit
+    const bool lean = lean_ok && !r1 && !a.timing && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
+                      c->cur_limit == ~0ULL && table != nullptr;
     {
         ProfScope ps(c, FRB_K_SCAN);
-        if (ws) {
-            if (trio) {
-                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTrio::ctas));
-                scan_ws_kernel<WsTrio><<<grid, WsTrio::threads, WsTrio::smem, c->compute>>>(a);
-            } else if (tall) {
-                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTall::ctas));
-                scan_ws_kernel<WsTall><<<grid, WsTall::threads, WsTall::smem, c->compute>>>(a);
-            } else if (dense) {
-                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsDense::ctas));
-                scan_ws_kernel<WsDense><<<grid, WsDense::threads, WsDense::smem, c->compute>>>(a);
-            } else {
-                const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsWide::ctas));
-                scan_ws_kernel<WsWide><<<grid, WsWide::threads, WsWide::smem, c->compute>>>(a);
-            }
-            // tiles the kernel left out (empty list unless the input is not well-formed FASTQ or has
-            // lines shorter than 16 bytes on average)
-            scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
-            c->launches++;
-        } else if (nt == 128) {
-            using Cfg = ScanCfg<128>;
-            const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
-            scan_kernel<128><<<grid, Cfg::threads, Cfg::smem, c->compute>>>(a);
+        const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTile::ctas));
+        if (r1) {
+            scan_ws_r1_kernel<R1Trio><<<grid, R1Trio::threads, R1Trio::smem, c->compute>>>(a);
+            scan_redo_r1_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
         } else {
-            using Cfg = ScanCfg<256>;
-            const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * Cfg::ctas_per_sm));
-            scan_kernel<256><<<grid, Cfg::threads, Cfg::smem, c->compute>>>(a);
+            if (lean) scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            else scan_ws_kernel<WsTile, 0><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            // tiles the kernel left out (empty list unless the input is not well-formed FASTQ or has
+            // lines shorter than 20 bytes on average)
+            scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
         }
-        c->launches++;
+        c->launches += 2;
     }
     CU(c, cudaGetLastError());
     if (a.timing) {
         unsigned long long h[16];
         cudaStreamSynchronize(c->compute);
         cudaMemcpy(h, a.timing, 128, cudaMemcpyDeviceToHost);
-        const char* names_std[9] = {"wait", "count", "lookback", "positions", "parse", "insert", "tile-end", "claim-bar", "issue"};
-        const char* names_ws[9] = {"C:wait-bytes", "C:count", "X:wait-counted", "K:lookback", "K:wait-batch", "X:phase", "K:commit", "X:parse_header", "X:send"};
-        const char** names = ws ? names_ws : names_std;
+        const char* names[9] = {"C:wait-bytes", "C:count", "X:wait+refill", "K:lookback", "K:wait-batch", "-", "K:commit",
+                                "X:parse_header", "X:send"};
         double sum = 0;
         for (int i = 0; i < 9; ++i) sum += static_cast<double>(h[i]);
         const double tiles = h[9] ? static_cast<double>(h[9]) : 1.0;
         fprintf(stderr, "SCAN TIMING tiles %llu cycles/tile %.0f:", h[9], sum / tiles);
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.0f", names[i], (double)h[i] / tiles);
-        if (ws) fprintf(stderr, " X:endsync+issue %.0f", (double)h[10] / tiles);
         fprintf(stderr, "\n");
     }
     return FRB_OK;
@@ -487,12 +467,9 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaMallocHost(&c->st_host, sizeof(DevState)));
     CU(c, cudaEventCreate(&c->t0));
     CU(c, cudaEventCreate(&c->t1));
-    CU(c, cudaFuncSetAttribute(scan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<256>::smem));
-    CU(c, cudaFuncSetAttribute(scan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanCfg<128>::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsWide::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsDense::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTall>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTall::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTrio>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTrio::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_r1_kernel<R1Trio>, cudaFuncAttributeMaxDynamicSharedMemorySize, R1Trio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(match_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(match_idx1_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -1,48 +1,36 @@
-// Hot path A: fused read-name parse + 3-bit key packing + unique-combination count, warp-specialised.
-// Replaces scan_file's loop (reference frender.py:161-177): "every 4th line from the start of the file",
-// key = 2nd space token's last ':' field (F:169) or, for demux, the last ':' field of the whole line (F:778).
+// Warp-specialised form of the scan kernel (hot path A).  Same arithmetic, same results and the
+// same helpers as scan_kernel.cuh; the difference is the schedule inside a CTA.
 //
-// Persistent CTAs (three per SM) claim tiles from a global ticket counter; a tile and the 512 bytes in front
-// of it arrive in shared memory by one bulk copy (cp.async.bulk + mbarrier), two stages deep, so every input
-// byte crosses HBM once.  Inside a CTA three roles meet only through shared-memory mbarriers:
-//
-//   warps 0-3  COUNTERS    for tile i: wait for its bytes (TMA mbarrier), 15 x 16 bytes per thread ->
+//   warps 0-3  COUNTERS    for tile i: wait for its bytes (TMA mbarrier), 256 bytes per thread ->
 //                          newline mask, group scan, ordered newline-position list in shared memory,
 //                          start of the line that straddles the tile start, publish the tile's newline
-//                          count, guess of the line phase from the text, signal `counted[stage]`.
-//   warps 4-6  EXTRACTORS  for tile i: one thread per (guessed) header line: key extraction, fold inside
-//                          the warp, key batch into a shared-memory ring for the committer; thread 0 then
-//                          refills the stage (ticket + bulk copy).  No global atomics besides the ticket.
+//                          count, signal `counted[stage]`.
+//   warps 4-6  EXTRACTORS  for tile i: guess which lines are header lines from the text, one thread per
+//                          header line: key extraction, fold inside the warp, key batch into a shared-
+//                          memory ring for the committer; thread 0 then refills the stage (ticket +
+//                          bulk copy).  No global atomics besides the ticket.
 //   warp  7    COMMITTER   per tile: look-back over the published counts (the only wait on other CTAs),
-//                          check of the guess against it, bookkeeping; per batch: deferred table updates.
-//                          Tiles whose guess was wrong go to scan_redo_kernel.
+//                          check of the extractors' guess against it, bookkeeping; per batch: deferred
+//                          table updates.  Tiles whose guess was wrong go to scan_redo_r1_kernel.
 //
-// With 3 CTAs per SM the launch register budget is re-split between the two warpgroups (setmaxnreg):
-// counters 48, extractors + committer 112.
-//
-// A counter thread owns 15 segments of 16 bytes (240 contiguous bytes).  The odd segment count is what
-// makes the shared-memory loads conflict-free with compile-time register indices: lane l reads segment j at
-// bank group (15 l + j) mod 8 = (j - l) mod 8, so the eight lanes of a 128-bit load phase hit eight different
-// bank groups.  (Round 1 used 16 segments and rotated the segment order per lane at run time, which cost
-// 36 instructions per segment for the dynamic placement of each 16-bit mask against 19 here.)
+// The roles only meet through shared-memory mbarriers (full -> counted per stage, full/free per key
+// batch).  With 3 CTAs per SM the launch register budget is re-split between the two warpgroups
+// (setmaxnreg): counters 48, extractors + committer 112.
 #pragma once
-#include "scan_common.cuh"
+#include "scan_ws_kernel.cuh"  // TEMPORARY: round-1 kernel kept for a same-box A/B, removed after the measurement
 
 namespace frb {
 
-constexpr int kWsGroup = 128;                 // counter threads
-constexpr unsigned kNoTile = 0xFFFFFFFFu;
-constexpr unsigned kNoGuess = 0xFFu;
 
-// Tile geometry.  SEG = 16-byte segments per counter thread (odd: see above), PW = extractor warps,
-// CTAS = resident CTAs per SM the shared memory and registers are budgeted for.
-template <int SEG, int PW, int CTAS, int NLCAP, int STAGES>
-struct WsGeom {
-    static_assert(SEG % 2 == 1, "an odd segment count keeps the 128-bit shared loads conflict-free");
+
+
+// Tile geometry.  SEG = 16-byte segments per counter thread, PW = parser warps, CTAS = resident CTAs
+// per SM the shared memory and registers are budgeted for.
+template <int SEG, int PW, int CTAS, int NLCAP, int STAGES = 3>
+struct WsGeomR1 {
     static constexpr int stages = STAGES;
     static constexpr int seg = SEG;
     static constexpr int per_thread = SEG * 16;
-    static constexpr int words = (per_thread + 31) / 32;     // 32-byte mask words per thread
     static constexpr int tile = kWsGroup * per_thread;
     static constexpr int buf = tile + kHalo;
     static constexpr int nl_cap = NLCAP;
@@ -55,33 +43,16 @@ struct WsGeom {
     // With 3 CTAs per SM the launch budget (80) is re-split inside the CTA: the counter warpgroup gives
     // registers back (setmaxnreg.dec) and the extractor/committer warpgroup takes them (setmaxnreg.inc).
     static constexpr bool split_regs = CTAS == 3 && threads == 256;
-    static constexpr int regs_count = 56, regs_work = 104;  // their mean is the launch budget (80)
     static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
-using WsTile = WsGeom<15, 3, 3, 1536, 2>;  // 30 KiB tiles, two stages, 3 CTAs per SM
+   // 32 KiB tiles, 2 x 8 warps per SM
+  // 20 KiB tiles, three stages, 3 CTAs per SM (A-B variant)
+  // 48 KiB tiles, two stages (A-B variant)
+using R1Trio = WsGeomR1<16, 3, 3, 1536, 2>;  // 32 KiB tiles, two stages, 3 CTAs per SM (A-B variant)
 
-// Instantiation flags.
-//   WS_LEAN   the tally of a whole file under the scan rule: no per-read outputs, no -s limit, no clock
-//             instrumentation -- none of those branches exist in the code.  Everything else (demux parse,
-//             -s, timing) runs the general instantiation.
-enum : int { WS_LEAN = 1 };
 
-// (1 << (f & 31)) - 1 in one instruction (BMSK)
-__device__ __forceinline__ unsigned bits_below(unsigned f) {
-    unsigned m;
-    asm("bmsk.wrap.b32 %0, 0, %1;" : "=r"(m) : "r"(f));
-    return m;
-}
-
-template <int N>
-__device__ __forceinline__ void group_sync(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
-}
-
-template <class G, int OPT>
-__global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
-    constexpr bool kLean = (OPT & WS_LEAN) != 0;
-    constexpr int kRule = kLean ? FRB_RULE_SCAN : kRuleRuntime;
+template <class G>
+__global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_r1_kernel(const ScanArgs a) {
     constexpr int kStages = G::stages;
     constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
     constexpr int kExt = G::xgroup, kXWarps = G::xwarps;
@@ -89,7 +60,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     extern __shared__ __align__(128) unsigned char smem[];
     uint16_t* const s_nl = reinterpret_cast<uint16_t*>(smem + kStages * kWsBuf);
     __shared__ __align__(8) unsigned long long s_full[kStages], s_counted[kStages];
-    __shared__ unsigned s_tile[kStages], s_total[kStages], s_valid[kStages], s_vnl[kStages], s_guess[kStages];
+    __shared__ unsigned s_tile[kStages], s_total[kStages], s_valid[kStages], s_vnl[kStages];
     __shared__ unsigned s_cwarp[kWsGroup / 32];
     __shared__ unsigned s_halo[kStages];
     // prefix of local tile i for the extractors that asked for it: ((i + 1) & 0xFFFFFF) << 40 | newlines before
@@ -108,9 +79,8 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
         a.use_carry ? *reinterpret_cast<volatile unsigned long long*>(&a.st->line_carry) : a.line_base;
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     volatile unsigned long long* status = a.status + 1;
-    const bool timing = !kLean && a.timing != nullptr;
 
-    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, kLean ? FRB_RULE_SCAN : a.rule);
+    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, a.rule);
     if (tid == 0) {
         s_prefix[0] = 0, s_prefix[1] = 0, s_prefix[2] = 0, s_prefix[3] = 0;
         if (blockIdx.x == 0) a.st->chunk_l0 = L0;
@@ -129,20 +99,17 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __syncthreads();
 
     if (warp < kWsGroup / 32) {
-        if constexpr (G::split_regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kLean ? G::regs_count : 48));
+        if constexpr (G::split_regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         // =============================== COUNTERS ================================================
         const int ct = tid;
         unsigned full_parity = 0;  // bit s
-        long long tm = (timing && ct == 0) ? clock64() : 0;
+        long long tm = (a.timing && ct == 0) ? clock64() : 0;
         unsigned long long t_wait = 0, t_work = 0;
-        // may the line phase be guessed from the text at all?  (per-read outputs and -s need the exact
-        // read ordinal before extraction)
-        const bool may_guess = kLean || (!a.no_guess && !a.keys_out && !a.rec_off_out && a.read_limit == ~0ULL);
         for (unsigned i = 0;; ++i) {
             const int s = i % kStages;
             mbar_wait(&s_full[s], (full_parity >> s) & 1u);
             full_parity ^= 1u << s;
-            if (timing && ct == 0) { const long long now = clock64(); t_wait += now - tm; tm = now; }
+            if (a.timing && ct == 0) { const long long now = clock64(); t_wait += now - tm; tm = now; }
             const unsigned t = s_tile[s];
             if (t == kNoTile) {
                 if (ct == 0) mbar_arrive(&s_counted[s]);
@@ -161,23 +128,64 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     group_sync<kWsGroup>(1);
                 }
             }
-            // Newline mask of this thread's bytes as 32-byte words, MIRRORED: byte k of word q (thread byte
-            // 32q + k) sits at bit 31 - k, so the first newline of a word is its count of leading zeros.
-            constexpr int kWords = G::words;
+            // newline masks of this thread's bytes as 32-bit words in byte order (bit k of word q = byte
+            // 32q + k); segments are read rotated so that the eight lanes of a 16-byte load phase hit
+            // eight different bank groups.
+            constexpr int kWords = kWsPerThread / 32;
             unsigned w[kWords];
             const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * G::seg;
+            if constexpr (G::seg % 8 == 0) {
+                // thread stride is a multiple of 128 bytes: within every group of 8 segments lane l starts at
+                // segment l & 7, so the eight lanes of a load phase hit eight different bank groups
+                constexpr int kGroups = G::seg / 8;
+                unsigned long long mlo[kGroups], mhi[kGroups];
 #pragma unroll
-            for (int q = 0; q < kWords; ++q) {
-                if (2 * q + 1 < G::seg) w[q] = eq_mask32_rev(t4[2 * q], t4[2 * q + 1], a.pat_nl);
-                else w[q] = eq_mask16_rev_hi(t4[2 * q], a.pat_nl);
+                for (int g = 0; g < kGroups; ++g) mlo[g] = 0, mhi[g] = 0;
+                // two iterations in flight; a fraction of the code of the fully unrolled loop (the kernel's
+                // three roles share one instruction cache)
+#pragma unroll 2
+                for (int j = 0; j < 8; ++j) {
+                    const int r = (j + ct) & 7;
+                    // the 16-bit mask lands at bit 16 * (r & 3) of the low or the high 64-bit word: as a
+                    // 32 x 64 -> 64-bit multiply-add (fields never overlap, so + is |), on the multiply pipe
+                    const unsigned long long place = 1ULL << ((r & 3) * 16);
+                    const unsigned long long to_lo = r < 4 ? place : 0ULL, to_hi = r < 4 ? 0ULL : place;
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        const unsigned mg = newline_mask16(t4[8 * g + r], a.pat_nl);
+                        mlo[g] += mg * to_lo;
+                        mhi[g] += mg * to_hi;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    w[4 * g + 0] = static_cast<unsigned>(mlo[g]), w[4 * g + 1] = static_cast<unsigned>(mlo[g] >> 32);
+                    w[4 * g + 2] = static_cast<unsigned>(mhi[g]), w[4 * g + 3] = static_cast<unsigned>(mhi[g] >> 32);
+                }
+            } else {
+                // thread stride 160 bytes = 10 bank groups: lanes 4-7 of a phase start one segment later
+                static_assert(G::seg == 10, "rotation below is written for 10 segments per thread");
+                const bool rot = (ct >> 2) & 1;
+                unsigned m[G::seg];
+#pragma unroll
+                for (int j = 0; j < G::seg; ++j) {
+                    const int r = (j == G::seg - 1) ? (rot ? 0 : j) : j + (rot ? 1 : 0);
+                    m[j] = newline_mask16(t4[r], a.pat_nl);
+                }
+#pragma unroll
+                for (int q = 0; q < kWords; ++q) {
+                    const unsigned lo = rot ? m[(2 * q + G::seg - 1) % G::seg] : m[2 * q];
+                    const unsigned hi = rot ? m[2 * q] : m[2 * q + 1];
+                    w[q] = lo | (hi << 16);
+                }
             }
             {
                 const int nv = static_cast<int>(valid) - ct * kWsPerThread;
                 if (nv < kWsPerThread) {
 #pragma unroll
                     for (int q = 0; q < kWords; ++q) {
-                        const int n = nv - 32 * q;  // bytes of word q that exist: keep the top n bits
-                        w[q] = n <= 0 ? 0u : (n >= 32 ? w[q] : (w[q] & ~(0xFFFFFFFFu >> n)));
+                        const int n = nv - 32 * q;
+                        w[q] = n <= 0 ? 0u : (n >= 32 ? w[q] : (w[q] & ((1u << n) - 1u)));
                     }
                 }
             }
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 uint16_t* const nl = s_nl + s * kWsNlCap;
                 unsigned idx = wbase + incl - cnt;
                 unsigned pos0 = kHalo + ct * kWsPerThread;
-                // A list that does not fit is never read (the tile goes to scan_redo_kernel), so one range
+                // A list that does not fit is never read (the tile goes to scan_redo_r1_kernel), so one range
                 // check per thread is enough.  Straight-line code for the first two newlines of a 32-byte
                 // word -- a third one means lines shorter than 16 bytes -- keeps the warp out of a
                 // data-dependent loop.
@@ -222,20 +230,16 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     };
 #pragma unroll
                     for (int q = 0; q < kWords; ++q) {
-                        // f = index of the highest set bit = 31 - byte offset of the first newline left
                         const unsigned m = w[q];
-                        const unsigned f1 = 31 - __clz(m);              // FLO; 0xFFFFFFFF when m == 0
-                        store_if(nl + idx, pos0 + 31 - f1, m);
-                        unsigned m2 = m & bits_below(f1);               // m == 0 stays 0
-                        const unsigned f2 = 31 - __clz(m2);
-                        store_if(nl + idx + 1, pos0 + 31 - f2, m2);
-                        m2 &= bits_below(f2);
+                        store_if(nl + idx, pos0 + (__ffs(m) - 1), m);
+                        unsigned m2 = m & (m - 1);
+                        store_if(nl + idx + 1, pos0 + (__ffs(m2) - 1), m2);
+                        m2 &= m2 - 1;
                         if (m2) {
                             unsigned k = idx + 2;
                             do {
-                                const unsigned f = 31 - __clz(m2);
-                                nl[k++] = static_cast<uint16_t>(pos0 + 31 - f);
-                                m2 &= ~(1u << f);
+                                nl[k++] = static_cast<uint16_t>(pos0 + (__ffs(m2) - 1));
+                                m2 &= m2 - 1;
                             } while (m2);
                         }
                         idx += __popc(m);
@@ -244,43 +248,29 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 }
                 if (ct == 0 && vnl && total < static_cast<unsigned>(kWsNlCap)) nl[total] = static_cast<uint16_t>(kHalo + valid);
             }
-            unsigned halo_start = kHalo;
             if (warp == 0) {  // start of the line that straddles the tile start (last newline of the halo)
-                if (t != 0) {
+                if (t == 0) {
+                    if (lane == 0) s_halo[s] = kHalo;
+                } else {
                     const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane], a.pat_nl);
                     const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
-                    const int top = 31 - __clz(any);  // -1: no newline in the halo
-                    const unsigned mine = lane * 16 + (31 - __clz(m)) + 1;
-                    halo_start = any ? __shfl_sync(0xFFFFFFFFu, mine, top & 31) : kUnknown;
+                    if (any == 0) {
+                        if (lane == 0) s_halo[s] = kUnknown;
+                    } else if (lane == 31 - __clz(any)) {
+                        s_halo[s] = lane * 16 + (31 - __clz(m)) + 1;
+                    }
                 }
-                if (lane == 0) s_halo[s] = halo_start, s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
+            }
+            if (ct == 0) {
+                s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
             }
             group_sync<kWsGroup>(1);  // list + meta complete (also protects s_cwarp)
-            if (warp == 0) {
-                // Which list entries end header lines?  The reference goes by line COUNT (F:161); in well-formed
-                // FASTQ the answer shows in the tile itself: a line that starts with '@' whose second successor
-                // starts with '+' and fourth with '@' is a header line, and exactly one of the first four lines
-                // may fit.  The extractors work from this guess; the committer checks it against the count.
-                unsigned g = kNoGuess;
-                if (may_guess && total >= 9 && halo_start != kUnknown && total + vnl <= static_cast<unsigned>(kWsNlCap)) {
-                    const uint16_t* const nl = s_nl + s * kWsNlCap;
-                    const unsigned c = lane & 7;  // lane c < 8 looks at the first byte of the tile's line c
-                    const unsigned first = buf[c ? nl[c - 1] + 1u : halo_start];
-                    const unsigned at = __ballot_sync(0xFFFFFFFFu, first == '@') & 0xFFu;
-                    const unsigned plus = __ballot_sync(0xFFFFFFFFu, first == '+') & 0xFFu;
-                    const unsigned hits = at & (plus >> 2) & (at >> 4) & 0xFu;
-                    if (__popc(hits) == 1) g = __ffs(hits) - 1;
-                }
-                if (lane == 0) {
-                    s_guess[s] = g;
-                    mbar_arrive(&s_counted[s]);
-                }
-            }
-            if (timing && ct == 0) { const long long now = clock64(); t_work += now - tm; tm = now; }
+            if (ct == 0) mbar_arrive(&s_counted[s]);
+            if (a.timing && ct == 0) { const long long now = clock64(); t_work += now - tm; tm = now; }
         }
-        if (timing && ct == 0) atomicAdd(&a.timing[0], t_wait), atomicAdd(&a.timing[1], t_work);
+        if (a.timing && ct == 0) atomicAdd(&a.timing[0], t_wait), atomicAdd(&a.timing[1], t_work);
     } else {
-        if constexpr (G::split_regs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kLean ? G::regs_work : 112));
+        if constexpr (G::split_regs) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // =============================== EXTRACTORS + COMMITTER ====================================
         // Batch descriptor words (s_bmeta): local tile index, global tile, first header index of the
         // batch, entries, newlines in the tile, lines (newlines + unterminated last line), guessed j0,
@@ -293,19 +283,19 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
         if (pwarp < kXWarps) {
             // ------------------------- extractor warps -------------------------------------------------
             // Key extraction needs to know WHICH lines of the tile are header lines (line number mod 4) and
-            // nothing else from the look-back.  The counters' guess gives that without waiting for other
-            // CTAs; keys go to the committer, which checks the guess against the newline count before
-            // anything reaches the table.  A wrong guess (input that is not well-formed FASTQ) sends the
-            // tile to scan_redo_kernel; without a guess the extractors ask the committer for the count
+            // nothing else from the look-back.  In well-formed FASTQ that shows in the tile itself (a line
+            // that starts with '@' whose second successor starts with '+' and fourth with '@' is a header
+            // line), so the extractors guess the phase from the text, extract, and hand the keys to the
+            // committer, which checks the guess against the newline count before anything reaches the
+            // table.  A wrong guess (input that is not well-formed FASTQ) sends the tile to
+            // scan_redo_r1_kernel; without a confident guess the extractors ask the committer for the count
             // first.  Either way every tile is tallied by line COUNT, exactly as F:161-169 does.
             // The extractors issue no global atomics, so none of their barrier arrivals waits for one.
             auto emit = [&](unsigned long long o, unsigned long long key, unsigned long long start_g) {
-                if constexpr (!kLean) {
-                    const unsigned long long slot = o - chunk_first_read;
-                    if (slot < a.out_cap) {
-                        if (a.keys_out) a.keys_out[slot] = key;
-                        if (a.rec_off_out) a.rec_off_out[slot] = start_g;
-                    }
+                const unsigned long long slot = o - chunk_first_read;
+                if (slot < a.out_cap) {
+                    if (a.keys_out) a.keys_out[slot] = key;
+                    if (a.rec_off_out) a.rec_off_out[slot] = start_g;
                 }
             };
             auto issue = [&](int s, unsigned ticket) {  // ticket -> stage s, start its bulk copy
@@ -327,7 +317,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     mbar_arrive(&s_full[s]);
                 }
             };
-            const unsigned long long read_limit = kLean ? ~0ULL : a.read_limit;
+            const bool may_guess = !a.no_guess && !a.keys_out && !a.rec_off_out && a.read_limit == ~0ULL;
             unsigned nb = 0;  // batches sent
             // hand one batch to the committer: keys (kEmpty = none), first parse error, descriptor
             auto send = [&](unsigned long long key, int rc, unsigned i, unsigned t, unsigned h0, unsigned n,
@@ -367,12 +357,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             if (pt == 0) {
                 for (int s = 0; s < kStages; ++s) issue(s, static_cast<unsigned>(atomicAdd(&a.status[0], 1ULL)));
             }
-            long long tm = (timing && pt == 0) ? clock64() : 0;
-            unsigned long long tp[4] = {0, 0, 0, 0};
+            long long tm = (a.timing && pt == 0) ? clock64() : 0;
+            unsigned long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             auto tick = [&](int k) {
-                if constexpr (!kLean) {
-                    if (timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
-                }
+                if (a.timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
             };
             for (unsigned i = 0;; ++i) {
                 const int s = i % kStages;
@@ -388,17 +376,27 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(next_ticket) : "l"(a.status) : "memory");
                 }
                 unsigned char* const buf = smem + s * kWsBuf;
-                const unsigned total = s_total[s], vnl = s_vnl[s], guess = s_guess[s];
+                const unsigned total = s_total[s], vnl = s_vnl[s];
                 const unsigned lines = total + vnl;
                 const unsigned halo_start = s_halo[s];
                 const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
                 const uint16_t* const nl = s_nl + s * kWsNlCap;
                 if (lines > static_cast<unsigned>(kWsNlCap)) {
-                    // more newlines than the list holds (lines < 20 bytes on average): scan_redo_kernel
+                    // more newlines than the list holds (lines < 16 bytes on average): scan_redo_r1_kernel
                     send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_DENSE);
                 } else {
-                    const bool guessed = guess != kNoGuess;
-                    unsigned j0 = guess;
+                    // ---- which list entries end header lines? ----
+                    bool guessed = false;
+                    unsigned j0 = 0;
+                    if (may_guess && total >= 9 && halo_start != kUnknown) {
+                        // lane c < 8 looks at the first byte of the tile's line c
+                        const unsigned c = lane & 7;
+                        const unsigned first = buf[c ? nl[c - 1] + 1u : halo_start];
+                        const unsigned at = __ballot_sync(0xFFFFFFFFu, first == '@') & 0xFFu;
+                        const unsigned plus = __ballot_sync(0xFFFFFFFFu, first == '+') & 0xFFu;
+                        const unsigned hits = at & (plus >> 2) & (at >> 4) & 0xFu;
+                        if (__popc(hits) == 1) guessed = true, j0 = __ffs(hits) - 1;
+                    }
                     unsigned long long of = 0;  // first read ordinal owned by the tile (known if !guessed)
                     unsigned flags = BF_FIRST | (guessed ? BF_GUESSED : 0u);
                     if (!guessed) {
@@ -409,24 +407,25 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                         flags = 0;
                     }
                     const unsigned n_owned = lines > j0 ? (lines - j0 + 3) / 4 : 0;
+                    tick(1);
 #pragma unroll 1
                     for (unsigned h0 = 0; h0 < n_owned; h0 += kExt) {
                         const unsigned h = h0 + pt;
-                        bool have = h < n_owned && (guessed || of + h < read_limit);
+                        bool have = h < n_owned && (guessed || of + h < a.read_limit);
                         unsigned long long key = kEmpty, start_g = 0;
                         int rc = 0;
                         if (have) {
                             const unsigned j = j0 + 4 * h;
                             const unsigned sb = j ? nl[j - 1] + 1u : halo_start;
-                            rc = parse_header<kRule, true>(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
+                            rc = parse_header(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
                             if (rc) key = kEmpty;
                             else if (!guessed) emit(of + h, key, start_g);
                         }
-                        tick(1);
+                        tick(6);
                         const unsigned n = n_owned - h0 < static_cast<unsigned>(kExt) ? n_owned - h0 : kExt;
                         send(key, rc, i, t, h0, n, total, lines, j0, flags);
                         flags &= ~static_cast<unsigned>(BF_FIRST);
-                        tick(2);
+                        tick(7);
                     }
                 }
                 group_sync<kExt>(3);  // every extractor is done reading stage s
@@ -434,28 +433,25 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     issue(s, static_cast<unsigned>(next_ticket));
                     tp[3] += 1;
                 }
-                tick(0);
+                tick(2);
             }
-            if (timing && pt == 0) {
-                atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[7], tp[1]), atomicAdd(&a.timing[8], tp[2]);
+            if (a.timing && pt == 0) {
+                atomicAdd(&a.timing[2], tp[0]), atomicAdd(&a.timing[5], tp[1]), atomicAdd(&a.timing[7], tp[6]);
+                atomicAdd(&a.timing[8], tp[7]), atomicAdd(&a.timing[10], tp[2]);
                 atomicAdd(&a.timing[9], tp[3]);
             }
         } else {
             // ------------------------- committer warp --------------------------------------------------
             // Per tile: look-back over the published counts (the only place a CTA waits on other CTAs),
-            // check of the guess, bookkeeping; per batch: update the table.
+            // check of the extractors' guess, bookkeeping; per batch: fold equal keys, update the table.
             // Table updates are deferred in three steps -- slot load, then RED or CAS one batch later,
             // then the RED after a CAS one batch after that -- so no L2 round trip is waited for in line.
             constexpr int kRounds = kExt / 32;
-            const unsigned long long read_limit = kLean ? ~0ULL : a.read_limit;
             unsigned long long p_key[kRounds], p_pos[kRounds], p_slot[kRounds], p_seen[kRounds];
             unsigned long long q_key[kRounds], q_pos[kRounds], q_slot[kRounds], q_old[kRounds];
             unsigned p_cnt[kRounds], q_cnt[kRounds];
 #pragma unroll
-            for (int r = 0; r < kRounds; ++r) {
-                p_cnt[r] = 0, q_cnt[r] = 0, q_slot[r] = 0, q_key[r] = 0, q_old[r] = 0, q_pos[r] = 0;
-                p_key[r] = 0, p_pos[r] = 0, p_slot[r] = 0, p_seen[r] = 0;
-            }
+            for (int r = 0; r < kRounds; ++r) p_cnt[r] = 0, q_cnt[r] = 0, q_slot[r] = 0, q_key[r] = 0, q_old[r] = 0;
             auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
                 atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
                 atomicMin(&a.table[slot].first, pos);
@@ -493,19 +489,17 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     "setp.ne.u32 q, %5, 0;\n\t"
                     "@p atom.global.cas.b64 t, [%1], %2, %3;\n\t"
                     "@q ld.volatile.global.u64 %0, [%1];\n\t}"
-                    : "+l"(q_old[r])
+                    : "=l"(q_old[r])
                     : "l"(&a.table[q_slot[r] & a.table_mask].key), "l"(kEmpty), "l"(q_key[r]), "r"(claim ? 1u : 0u),
                       "r"(look ? 1u : 0u)
                     : "memory");
             };
             unsigned long long my_reads = 0, of = 0;
             bool tile_ok = false;
-            long long tm = (timing && lane == 0) ? clock64() : 0;
+            long long tm = (a.timing && lane == 0) ? clock64() : 0;
             unsigned long long k_wait = 0, k_look = 0, k_commit = 0;
             auto ktick = [&](unsigned long long& acc) {
-                if constexpr (!kLean) {
-                    if (timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
-                }
+                if (a.timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
             };
             for (unsigned nb = 0;; ++nb) {
                 const unsigned b = nb % kBatches;
@@ -523,11 +517,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     tile_ok = !(flags & BF_DENSE) &&
                               (!(flags & BF_GUESSED) || static_cast<unsigned>((4 - (K0 & 3)) & 3) == m[BM_J0]);
                     if (lane == 0) {
-                        if (!kLean || (flags & BF_NEED_PREFIX))
-                            s_prefix[i & 3] = (static_cast<unsigned long long>((i + 1) & 0xFFFFFFu) << 40) | excl;
+                        s_prefix[i & 3] = (static_cast<unsigned long long>((i + 1) & 0xFFFFFFu) << 40) | excl;
                         if (tile_ok) {
                             const unsigned long long o_end = (K0 + m[BM_LINES] + 3) >> 2;
-                            const unsigned long long c_hi = o_end < read_limit ? o_end : read_limit;
+                            const unsigned long long c_hi = o_end < a.read_limit ? o_end : a.read_limit;
                             if (c_hi > of) my_reads += c_hi - of;
                             if (t == a.n_tiles - 1) a.st->line_carry = K0 + m[BM_LINES];
                         } else {
@@ -570,7 +563,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 for (int r = 0; r < kRounds; ++r) finish(r);
             }
             if (lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
-            if (timing && lane == 0) {
+            if (a.timing && lane == 0) {
                 atomicAdd(&a.timing[3], k_look), atomicAdd(&a.timing[4], k_wait), atomicAdd(&a.timing[6], k_commit);
             }
         }
@@ -581,7 +574,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 // not well-formed FASTQ), or more newlines than a tile's position list holds -- tallied strictly by line
 // count, one thread per tile, from the bytes in global memory.  status[] holds every tile's inclusive
 // newline prefix by now.  Slow and exact; the list is empty for ordinary input.
-__global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(64) scan_redo_r1_kernel(const ScanArgs a) {
     const unsigned long long n = a.st->redo_n;
     const unsigned long long L0 = a.st->chunk_l0;
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;

@@ -12,7 +12,7 @@ from frender_b200.engine import C, Context, PackedSheet  # noqa: E402
 reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 spec = synth.make_spec("C2")
-ctx = Context(0, table_log2=22)
+ctx = Context(0, table_log2=int(sys.argv[3]) if len(sys.argv) > 3 else 22)
 h, lib, ck = ctx._h, L.lib, ctx._ck
 pk = lambda rows: np.array([sum(int(c) << (2 * p) for p, c in enumerate(r)) for r in rows], np.uint32)
 i7, i5, cdf = pk(spec.sheet_i7), pk(spec.emit_i5()), np.ascontiguousarray(spec.cdf, np.uint64)
