@@ -313,7 +313,7 @@ def run_b200(args):
     mark = {}
 
     def start_counting():      # the timed steps only: per-class device time and launch count start after warm-up
-        for k in range(L.K_OTHER + 1):
+        for k in range(L.K_NUM):
             ctx.prof_read(k, reset=True)
         mark["launches"] = ctx.launches()
 
@@ -322,7 +322,7 @@ def run_b200(args):
     clk = clocks.stop()
     launches = ctx.launches() - mark["launches"]
     assert got_reads == reads, (got_reads, reads)
-    prof = {k: ctx.prof_read(k, reset=True) for k in range(L.K_OTHER + 1)}
+    prof = {k: ctx.prof_read(k, reset=True) for k in range(L.K_NUM)}
     n_uniq = C.c_uint64()
     ck(lib.frb_total_finish(h, C.byref(n_uniq)))
     if dist:    # the shares are disjoint: the job's unique keys are their sum
@@ -360,7 +360,7 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": scan_ms_per,
                 "step_share": {name: prof[k][0] / args.steps for name, k in
                                (("scan_ms", L.K_SCAN), ("export_sort_merge_ms", L.K_EXPORT),
-                                ("match_ms", L.K_MATCH), ("clear_ms", L.K_OTHER))}}
+                                ("match_ms", L.K_MATCH), ("clear_ms", L.K_OTHER), ("verify_ms", L.K_VERIFY))}}
 
     # ---- end to end: host buffers -> H2D -> kernels -> D2H of per-key results -------------------
     e2e = None

@@ -15,7 +15,8 @@ ERR_CUDA, ERR_ARG, ERR_BAD_HEADER, ERR_BAD_ALPHABET, ERR_KEY_TOO_LONG = -1, -2, 
 ERR_TABLE_FULL, ERR_BAD_LENGTH, ERR_KEY_NOT_FOUND, ERR_NCCL, ERR_IO, ERR_STATE = -6, -7, -8, -9, -10, -11
 RULE_SCAN, RULE_DEMUX = 0, 1
 CARRY = 0xFFFFFFFFFFFFFFFF
-K_SCAN, K_EXPORT, K_MATCH, K_ROUTE, K_OTHER = range(5)
+K_SCAN, K_EXPORT, K_MATCH, K_ROUTE, K_OTHER, K_VERIFY = range(6)
+K_NUM = 6
 READ_TYPES = ("undetermined", "index_hop", "demuxable", "ambiguous")
 
 u64, u32, i32, u8 = C.c_uint64, C.c_uint32, C.c_int32, C.c_uint8

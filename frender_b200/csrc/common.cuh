@@ -28,7 +28,17 @@ struct DevState {
     int pad;
     unsigned long long chunk_l0;    // lines before the chunk the scan kernel last ran on
     unsigned long long redo_n;      // tiles of that chunk left to scan_redo_kernel
+    // speculative (lean) scan path: keys are committed on the text's own line phase and the phase is checked
+    // against the newline count afterwards (scan_verify.cuh)
+    unsigned long long spec_err_pos;  // composite position of the first parse error seen in a guessed tile
+    int spec_err_code;                // ... and its code; promoted to err_code once the guesses are confirmed
+    int spec_bad;                     // a guess of the current chunk was wrong: the chunk is redone by count
 };
+
+// Position of a read inside a file as the speculative path records it: (tile index in the file << 13) | index of
+// the header among the tile's headers.  Order-preserving in the read ordinal; turned into the ordinal itself when
+// the file's table is compacted (first read ordinal of every tile is known once the newline counts are summed).
+constexpr int kCompositeShift = 13;  // a 30 KiB tile holds at most 7680 headers (four empty lines each)
 
 constexpr unsigned long long kEmpty = FRB_EMPTY_KEY;
 constexpr int kMaxSyms = 21;

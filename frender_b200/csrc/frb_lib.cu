@@ -24,6 +24,7 @@
 #include "route_kernel.cuh"
 #include "scan_common.cuh"
 #include "scan_ws_kernel.cuh"
+#include "scan_verify.cuh"
 #include "scan_ws_r1_kernel.cuh"
 #include "synth_kernel.cuh"
 #include "table_kernels.cuh"
@@ -59,6 +60,13 @@ struct frb_ctx {
     unsigned long long* status = nullptr;
     unsigned int* redo = nullptr;  // tiles left to scan_redo_kernel (same capacity as status)
     size_t status_cap = 0;
+    // speculative scan path: first read ordinal of every tile of the current file (composite -> ordinal)
+    unsigned long long* tile_first = nullptr;
+    size_t tile_first_cap = 0;
+    uint64_t file_tiles = 0;            // tiles of the current file scanned so far
+    int file_composite = -1;            // -1 undecided, 0 read ordinals, 1 composite positions in file_tab
+    unsigned long long* block_sums = nullptr;
+    size_t block_sums_cap = 0;
     // host-chunk staging
     unsigned char* stage[kHostStages] = {nullptr, nullptr, nullptr};
     cudaEvent_t stage_copied[kHostStages], stage_done[kHostStages];
@@ -298,7 +306,8 @@ int unsorted_to_sorted_list(frb_ctx* c, unsigned long long* k0, unsigned long lo
 }
 
 // Table -> list sorted by `first`.
-int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out, int first_bits = 64) {
+int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out, int first_bits = 64,
+                         const unsigned long long* tile_first = nullptr) {
     out->n = n;
     if (n == 0) return FRB_OK;
     if (n >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
@@ -310,7 +319,7 @@ int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out, int fi
         ProfScope ps(c, FRB_K_EXPORT);
         CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
         compact_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
-            tab, c->cap, k0, c0, f0, &c->st->scratch, n);
+            tab, c->cap, k0, c0, f0, &c->st->scratch, n, tile_first);
         c->launches++;
         CU(c, cudaGetLastError());
     }
@@ -339,7 +348,6 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         CU(c, cudaMalloc(&c->redo, want * 4));
         c->status_cap = want;
     }
-    CU(c, cudaMemsetAsync(c->status, 0, (n_tiles + 1) * 8, c->compute));
     ScanArgs a{};
     a.data = dev;
     a.nbytes = nbytes;
@@ -369,23 +377,81 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         cudaMemsetAsync(timing, 0, 128, c->compute);
         a.timing = timing;
     }
-    // the lean instantiation serves the tally of whole files: scan rule, no per-read outputs, no -s limit
+    // the lean (speculative) instantiation serves the tally of whole files: scan rule, no per-read outputs, no -s
     const bool lean = lean_ok && !r1 && !a.timing && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
-                      c->cur_limit == ~0ULL && table != nullptr;
-    {
+                      c->cur_limit == ~0ULL && table != nullptr && table == c->file_tab && c->in_file;
+    if (table == c->file_tab && c->in_file) {
+        if (c->file_composite < 0) c->file_composite = lean ? 1 : 0;
+        if (c->file_composite != (lean ? 1 : 0)) return fail(c, FRB_ERR_STATE, "chunks of one file must use one scan mode");
+    }
+    const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTile::ctas));
+    if (!lean) {
+        CU(c, cudaMemsetAsync(c->status, 0, (n_tiles + 1) * 8, c->compute));
         ProfScope ps(c, FRB_K_SCAN);
-        const int grid = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(c->sm_count) * WsTile::ctas));
         if (r1) {
             scan_ws_r1_kernel<R1Trio><<<grid, R1Trio::threads, R1Trio::smem, c->compute>>>(a);
             scan_redo_r1_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
         } else {
-            if (lean) scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
-            else scan_ws_kernel<WsTile, 0><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            scan_ws_kernel<WsTile, 0><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
             // tiles the kernel left out (empty list unless the input is not well-formed FASTQ or has
             // lines shorter than 20 bytes on average)
             scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
         }
         c->launches += 2;
+    } else {
+        // room for the first read ordinal of every tile of the file
+        if (c->file_tiles + n_tiles > c->tile_first_cap) {
+            const size_t want = std::max<size_t>((c->file_tiles + n_tiles) * 2, 1 << 16);
+            unsigned long long* grown = nullptr;
+            CU(c, cudaMalloc(&grown, want * 8));
+            if (c->file_tiles)
+                CU(c, cudaMemcpyAsync(grown, c->tile_first, c->file_tiles * 8, cudaMemcpyDeviceToDevice, c->compute));
+            CU(c, cudaStreamSynchronize(c->compute));
+            if (c->tile_first) CU(c, cudaFree(c->tile_first));
+            c->tile_first = grown;
+            c->tile_first_cap = want;
+        }
+        const unsigned n_blocks = static_cast<unsigned>((n_tiles + kVerifyTiles - 1) / kVerifyTiles);
+        if (n_blocks > c->block_sums_cap) {
+            if (c->block_sums) CU(c, cudaFree(c->block_sums));
+            c->block_sums = nullptr;
+            c->block_sums_cap = 0;
+            const size_t want = std::max<size_t>(n_blocks * 2, 1024);
+            CU(c, cudaMalloc(&c->block_sums, want * 8));
+            c->block_sums_cap = want;
+        }
+        a.tile_base = c->file_tiles;
+        a.tile_first = c->tile_first;
+        a.composite = 1;
+        CU(c, cudaMemsetAsync(c->status, 0, 8, c->compute));           // the ticket counter
+        CU(c, cudaMemsetAsync(&c->st->spec_err_pos, 0, 16, c->compute));  // spec_err_pos, spec_err_code, spec_bad
+        {
+            ProfScope ps(c, FRB_K_SCAN);
+            static const bool regs_b = getenv("FRB_WS_REGS") && atoi(getenv("FRB_WS_REGS")) == 48;
+            if (regs_b) scan_ws_kernel<WsTileB, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            else scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+        }
+        {   // the line phase of every tile by count: checks the guesses, lists the tiles without one
+            ProfScope ps(c, FRB_K_VERIFY);
+            unsigned long long* info = c->status + 1;
+            const unsigned nt = static_cast<unsigned>(n_tiles);
+            spec_sum_kernel<<<n_blocks, kVerifyTiles, 0, c->compute>>>(info, nt, c->block_sums);
+            spec_scan_kernel<<<1, kVerifyTiles, 0, c->compute>>>(c->block_sums, n_blocks, info, nt, a.line_base, a.use_carry, c->st);
+            spec_verify_kernel<<<n_blocks, kVerifyTiles, 0, c->compute>>>(info, nt, c->block_sums, c->st,
+                                                                          c->tile_first + c->file_tiles, c->redo);
+            // a wrong guess (input that is not well-formed FASTQ): take the chunk's guessed keys out of the
+            // table again, forget the positions it may have set, and let scan_redo_kernel redo every tile by
+            // count.  All three return at once for an ordinary chunk.
+            CU(c, cudaMemsetAsync(c->status, 0, 8, c->compute));
+            ScanArgs neg = a;
+            neg.negate = 1;
+            scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(neg);
+            spec_reset_first_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
+                table, c->cap, c->file_tiles << kCompositeShift, c->st);
+            scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
+        }
+        c->file_tiles += n_tiles;
+        c->launches += 7;
     }
     CU(c, cudaGetLastError());
     if (a.timing) {
@@ -469,6 +535,7 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaEventCreate(&c->t1));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTileB, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_r1_kernel<R1Trio>, cudaFuncAttributeMaxDynamicSharedMemorySize, R1Trio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(match_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -485,7 +552,7 @@ void frb_destroy(frb_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& f : c->files) free_list(c, f);
     free_list(c, c->total);
-    cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status), cudaFree(c->redo);
+    cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status), cudaFree(c->redo), cudaFree(c->tile_first), cudaFree(c->block_sums);
     for (auto* p : c->xchg) cudaFree(p);
     for (int i = 0; i < kHostStages; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]), cudaEventDestroy(c->stage_copied[i]), cudaEventDestroy(c->stage_done[i]);
@@ -586,6 +653,8 @@ int frb_scan_begin(frb_ctx* c, uint32_t file_ordinal, uint64_t read_limit) {
     if (file_ordinal >= (1u << 23)) return fail(c, FRB_ERR_ARG, "file ordinal too large");
     c->cur_ordinal = file_ordinal;
     c->cur_limit = read_limit ? read_limit : ~0ULL;
+    c->file_tiles = 0;
+    c->file_composite = -1;
     CU(c, cudaMemsetAsync(c->st, 0, offsetof(DevState, occupied_total), c->compute));
     TRY(clear_table(c, c->file_tab));
     c->in_file = true;
@@ -648,7 +717,8 @@ int frb_scan_end(frb_ctx* c, uint64_t* n_reads, uint64_t* n_unique) {
     KeyList fl;
     fl.reads = c->st_host->n_reads;
     fl.ordinal = c->cur_ordinal;
-    TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl, 40));  // read ordinals of one file
+    // read ordinals of one file stay below 2^40; composite positions become ordinals here
+    TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl, 40, c->file_composite == 1 ? c->tile_first : nullptr));
     c->files.push_back(fl);
     c->total_ready = false;
     if (n_reads) *n_reads = fl.reads;

@@ -32,6 +32,10 @@ struct ScanArgs {
     int use_carry;
     int rule;
     unsigned long long* timing;  // optional: per-role clock64 sums (instrumented instantiation only)
+    unsigned long long* tile_first;  // speculative path: first read ordinal of every tile of the file
+    unsigned long long tile_base;  // speculative path: tiles of this file before the chunk (composite positions)
+    int negate;                  // speculative path: take the chunk's guessed keys out of the table again
+    int composite;               // scan_redo_kernel: record composite positions, leave n_reads / line_carry alone
     unsigned int* redo;          // tiles left to scan_redo_kernel, capacity n_tiles
     unsigned int tile_bytes;     // tile size of the kernel that filled status[] (for scan_redo_kernel)
     int no_guess;                // A-B: never guess the line phase from the text

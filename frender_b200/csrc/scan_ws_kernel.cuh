@@ -17,8 +17,20 @@
 //                          check of the guess against it, bookkeeping; per batch: deferred table updates.
 //                          Tiles whose guess was wrong go to scan_redo_kernel.
 //
-// With 3 CTAs per SM the launch register budget is re-split between the two warpgroups (setmaxnreg):
-// counters 48, extractors + committer 112.
+// Two instantiations:
+//   general (OPT = 0)   every tile's line phase comes from a decoupled look-back over the published newline
+//                       counts (the committer does it; with a guess the extractors do not wait for it, without
+//                       one they do).  Serves per-read outputs (demux), -s, and the clock instrumentation.
+//   WS_LEAN             the tally of whole files.  SPECULATIVE: guessed tiles are extracted and committed at
+//                       once, under composite positions (tile << 13 | header index) that need no prefix; each
+//                       tile leaves its newline count and its guess in status[].  scan_verify.cuh then sums the
+//                       counts, checks every guess against the count, turns tiles without a guess over to
+//                       scan_redo_kernel, and -- when a guess was wrong, i.e. the input is not well-formed
+//                       FASTQ -- has the whole chunk taken out of the table again (negate pass) and redone
+//                       strictly by count.  No CTA ever waits for another CTA, so the three roles of a CTA are
+//                       coupled only through their own two tile stages and the key-batch ring.
+//
+// With 3 CTAs per SM the launch register budget is re-split between the two warpgroups (setmaxnreg).
 //
 // A counter thread owns 15 segments of 16 bytes (240 contiguous bytes).  The odd segment count is what
 // makes the shared-memory loads conflict-free with compile-time register indices: lane l reads segment j at
@@ -36,7 +48,7 @@ constexpr unsigned kNoGuess = 0xFFu;
 
 // Tile geometry.  SEG = 16-byte segments per counter thread (odd: see above), PW = extractor warps,
 // CTAS = resident CTAs per SM the shared memory and registers are budgeted for.
-template <int SEG, int PW, int CTAS, int NLCAP, int STAGES>
+template <int SEG, int PW, int CTAS, int NLCAP, int STAGES, int RC = 56, int RW = 104>
 struct WsGeom {
     static_assert(SEG % 2 == 1, "an odd segment count keeps the 128-bit shared loads conflict-free");
     static constexpr int stages = STAGES;
@@ -55,16 +67,24 @@ struct WsGeom {
     // With 3 CTAs per SM the launch budget (80) is re-split inside the CTA: the counter warpgroup gives
     // registers back (setmaxnreg.dec) and the extractor/committer warpgroup takes them (setmaxnreg.inc).
     static constexpr bool split_regs = CTAS == 3 && threads == 256;
-    static constexpr int regs_count = 56, regs_work = 104;  // their mean is the launch budget (80)
+    static constexpr int regs_count = RC, regs_work = RW;  // their mean is the launch budget (80)
     static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
 using WsTile = WsGeom<15, 3, 3, 1536, 2>;  // 30 KiB tiles, two stages, 3 CTAs per SM
+using WsTileB = WsGeom<15, 3, 3, 1536, 2, 48, 112>;  // A/B: the round-1 register split
 
 // Instantiation flags.
 //   WS_LEAN   the tally of a whole file under the scan rule: no per-read outputs, no -s limit, no clock
 //             instrumentation -- none of those branches exist in the code.  Everything else (demux parse,
 //             -s, timing) runs the general instantiation.
 enum : int { WS_LEAN = 1 };
+
+// status[1 + t] of the speculative path: newlines of the tile (bits 0-19), unterminated last line (bit 20),
+// guessed list index of the first header end (bits 24-31, kNoGuess = none)
+__host__ __device__ __forceinline__ unsigned long long spec_info(unsigned total, unsigned vnl, unsigned guess) {
+    return static_cast<unsigned long long>(total) | (static_cast<unsigned long long>(vnl) << 20) |
+           (static_cast<unsigned long long>(guess) << 24);
+}
 
 // (1 << (f & 31)) - 1 in one instruction (BMSK)
 __device__ __forceinline__ unsigned bits_below(unsigned f) {
@@ -104,7 +124,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __shared__ unsigned char s_lut[256];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long L0 =
+    if constexpr (kLean) {  // negate pass of a chunk whose guesses all held: nothing to take back
+        if (a.negate && *reinterpret_cast<volatile int*>(&a.st->spec_bad) == 0) return;
+    }
+    const unsigned long long L0 = kLean ? 0ULL :
         a.use_carry ? *reinterpret_cast<volatile unsigned long long*>(&a.st->line_carry) : a.line_base;
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     volatile unsigned long long* status = a.status + 1;
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, kLean ? FRB_RULE_SCAN : a.rule);
     if (tid == 0) {
         s_prefix[0] = 0, s_prefix[1] = 0, s_prefix[2] = 0, s_prefix[3] = 0;
-        if (blockIdx.x == 0) a.st->chunk_l0 = L0;
+        if (!kLean && blockIdx.x == 0) a.st->chunk_l0 = L0;
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], 1);
@@ -201,7 +224,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             }
             // the tile's newline count goes out the moment it is known (before the list is built): every later
             // tile's look-back waits for it.  Thread 32: not the thread that arrives on the mbarrier below
-            if (ct == 32) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
+            if (!kLean && ct == 32) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
             // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
             const unsigned vnl = (t == a.n_tiles - 1 && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
             {   // ordered list of newline positions; line numbers come later, from the look-back
@@ -274,6 +297,8 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 if (lane == 0) {
                     s_guess[s] = g;
                     mbar_arrive(&s_counted[s]);
+                    // speculative path: count and guess of the tile for scan_verify.cuh (nobody waits for it)
+                    if (kLean && !a.negate) status[t] = spec_info(total, vnl, g);
                 }
             }
             if (timing && ct == 0) { const long long now = clock64(); t_work += now - tm; tm = now; }
@@ -395,13 +420,15 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 const uint16_t* const nl = s_nl + s * kWsNlCap;
                 if (lines > static_cast<unsigned>(kWsNlCap)) {
                     // more newlines than the list holds (lines < 20 bytes on average): scan_redo_kernel
-                    send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_DENSE);
+                    if (!kLean) send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_DENSE);
+                } else if (kLean && guess == kNoGuess) {
+                    // speculative path: a tile without a guess is tallied by scan_redo_kernel once the counts are in
                 } else {
                     const bool guessed = guess != kNoGuess;
                     unsigned j0 = guess;
                     unsigned long long of = 0;  // first read ordinal owned by the tile (known if !guessed)
                     unsigned flags = BF_FIRST | (guessed ? BF_GUESSED : 0u);
-                    if (!guessed) {
+                    if (!kLean && !guessed) {
                         send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_NEED_PREFIX);
                         const unsigned long long K0 = wait_prefix(i);
                         j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
@@ -457,6 +484,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 p_key[r] = 0, p_pos[r] = 0, p_slot[r] = 0, p_seen[r] = 0;
             }
             auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
+                if (kLean && a.negate) {  // take the keys of a mis-guessed chunk out again
+                    atomicAdd(&a.table[slot].count, 0ULL - static_cast<unsigned long long>(cnt));
+                    return;
+                }
                 atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
                 atomicMin(&a.table[slot].first, pos);
             };
@@ -515,7 +546,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 const unsigned flags = m[BM_FLAGS];
                 if (flags & BF_END) break;
                 const unsigned i = m[BM_I], t = m[BM_T], h0 = m[BM_H0], n = m[BM_N];
-                if (flags & BF_FIRST) {
+                if constexpr (kLean) {
+                    tile_ok = true;  // speculative: checked by scan_verify.cuh after the kernel
+                    of = (a.tile_base + t) << kCompositeShift;
+                } else if (flags & BF_FIRST) {
                     unsigned long long excl;
                     tile_prefix<true>(status, t, m[BM_TOTAL], lane, &excl);
                     const unsigned long long K0 = L0 + excl;
@@ -549,8 +583,14 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 for (int w = 0; w < kXWarps; ++w) err = min(err, s_berr[b][w]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_bfree[b]);  // the batch is in registers
-                if (tile_ok && n && err != 0xFFFFFFFFu && lane == 0)
-                    raise_error(a.st, -static_cast<int>(err & 0xFFu), of + h0 + (err >> 8));
+                if (tile_ok && n && err != 0xFFFFFFFFu && lane == 0) {
+                    if constexpr (kLean) {  // an error of a guessed tile counts once the guesses are confirmed
+                        if (atomicCAS(&a.st->spec_err_code, 0, -static_cast<int>(err & 0xFFu)) == 0)
+                            a.st->spec_err_pos = of + h0 + (err >> 8);
+                    } else {
+                        raise_error(a.st, -static_cast<int>(err & 0xFFu), of + h0 + (err >> 8));
+                    }
+                }
                 if (a.table) {
 #pragma unroll
                     for (int r = 0; r < kRounds; ++r) {
@@ -569,7 +609,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 #pragma unroll
                 for (int r = 0; r < kRounds; ++r) finish(r);
             }
-            if (lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
+            if (!kLean && lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
             if (timing && lane == 0) {
                 atomicAdd(&a.timing[3], k_look), atomicAdd(&a.timing[4], k_wait), atomicAdd(&a.timing[6], k_commit);
             }
@@ -582,12 +622,19 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 // count, one thread per tile, from the bytes in global memory.  status[] holds every tile's inclusive
 // newline prefix by now.  Slow and exact; the list is empty for ordinary input.
 __global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
-    const unsigned long long n = a.st->redo_n;
+    // speculative path: a wrong guess somewhere in the chunk -> every tile is redone (the negate pass took the
+    // guessed keys out again); a parse error of a guessed tile stands once all guesses are confirmed
+    const bool all = a.composite && a.st->spec_bad;
+    if (a.composite && !all && blockIdx.x == 0 && threadIdx.x == 0 && a.st->spec_err_code) {
+        const unsigned long long p = a.st->spec_err_pos;
+        raise_error(a.st, a.st->spec_err_code, a.tile_first[p >> kCompositeShift] + (p & ((1ULL << kCompositeShift) - 1)));
+    }
+    const unsigned long long n = all ? a.n_tiles : a.st->redo_n;
     const unsigned long long L0 = a.st->chunk_l0;
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     for (unsigned long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-        const unsigned t = a.redo[idx];
+        const unsigned t = all ? static_cast<unsigned>(idx) : a.redo[idx];
         const unsigned long long off = static_cast<unsigned long long>(t) * a.tile_bytes;
         const unsigned long long end = off + a.tile_bytes < a.nbytes ? off + a.tile_bytes : a.nbytes;
         unsigned long long k = L0 + (t ? (a.status[t] & kValMask) : 0ULL);  // a.status[1 + (t - 1)]
@@ -601,11 +648,13 @@ __global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
             if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
                 unsigned long long key = 0;
                 const int rc = a.rule == kRuleOffsetsOnly ? 0 : parse_serial(a.data + prev, p - prev, a.rule, &key);
+                const unsigned long long pos =
+                    a.composite ? (((a.tile_base + t) << kCompositeShift) | reads) : a.pos_base + (k >> 2);
                 ++reads;
                 if (rc) {
                     raise_error(a.st, rc, k >> 2);
                 } else {
-                    if (a.table) table_add(a.table, a.table_mask, key, 1, a.pos_base + (k >> 2), &a.st->occupied, a.st);
+                    if (a.table) table_add(a.table, a.table_mask, key, 1, pos, &a.st->occupied, a.st);
                     const unsigned long long slot = (k >> 2) - chunk_first_read;
                     if (slot < a.out_cap) {
                         if (a.keys_out) a.keys_out[slot] = key;
@@ -616,8 +665,10 @@ __global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
             prev = p + 1;
             ++k;
         }
-        if (reads) atomicAdd(&a.st->n_reads, reads);
-        if (t == a.n_tiles - 1) a.st->line_carry = k;
+        if (!a.composite) {  // the speculative path takes both from the summed counts (spec_scan_kernel)
+            if (reads) atomicAdd(&a.st->n_reads, reads);
+            if (t == a.n_tiles - 1) a.st->line_carry = k;
+        }
     }
 }
 

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) count_table_kernel(const Slot* __restrict
     unsigned n = 0;
     for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < cap;
          i += stride)
-        n += tab[i].key != kEmpty ? 1u : 0u;
+        n += (tab[i].key != kEmpty && tab[i].count != 0) ? 1u : 0u;  // count 0: taken back by a negate pass
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, static_cast<unsigned long long>(n));
@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restri
                                                             unsigned long long* __restrict__ counts,
                                                             unsigned long long* __restrict__ first,
                                                             unsigned long long* counter,
-                                                            unsigned long long out_cap) {
+                                                            unsigned long long out_cap,
+                                                            const unsigned long long* __restrict__ tile_first = nullptr) {
     __shared__ unsigned s_warp[8];
     __shared__ unsigned long long s_base;
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restri
          i < cap_up; i += stride) {
         ulonglong4 s = make_ulonglong4(kEmpty, 0, 0, 0);
         if (i < cap) s = reinterpret_cast<const ulonglong4*>(tab)[i];
-        const bool occ = s.x != kEmpty;
+        const bool occ = s.x != kEmpty && s.y != 0;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, occ);
         if (lane == 0) s_warp[warp] = __popc(m);
         __syncthreads();
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restri
             if (idx < out_cap) {
                 keys[idx] = s.x;
                 counts[idx] = s.y;
-                first[idx] = s.z;
+                // composite position (tile << 13 | header index) -> read ordinal
+                first[idx] = tile_first ? tile_first[s.z >> kCompositeShift] + (s.z & ((1ULL << kCompositeShift) - 1)) : s.z;
             }
         }
     }

@@ -193,7 +193,8 @@ int frb_synth_generate(frb_ctx* ctx, uint64_t g0, uint64_t g1, int read_no, void
 #define FRB_K_MATCH 2  /* matcher                      */
 #define FRB_K_ROUTE 3  /* demux route + partition      */
 #define FRB_K_OTHER 4
-#define FRB_K_NUM 5
+#define FRB_K_VERIFY 5 /* line phase of every tile by count (check of the speculative scan) */
+#define FRB_K_NUM 6
 int frb_timer_start(frb_ctx* ctx);            /* CUDA event on the compute stream              */
 int frb_timer_stop(frb_ctx* ctx, float* ms);  /* second event, synchronises, elapsed ms        */
 int frb_prof_enable(frb_ctx* ctx, int on);    /* per-kernel-class event pairs                  */

@@ -149,6 +149,28 @@ def scan_case(name, config, reads, n, rc, tmp, n_samples=None, files=None, sampl
     return out
 
 
+
+def tally_case(name, config, files, tmp, cores=1):
+    """Tally stage only, over several files (config C5: single 6 bp index, file-level partitioning).
+    The reference cannot run its matcher on single-index keys (F:104-107, F:306), so the tally of
+    F:183-207 -- per-file dicts in file order and the merged "total" in first-appearance order -- is
+    what pins this shape."""
+    spec = synth.make_spec(config)
+    case_dir = os.path.join(tmp, name)
+    os.makedirs(case_dir)
+    inputs, paths = {}, []
+    for fname, g0, g1 in files:
+        data = synth.generate_big(spec, g0, g1)
+        p = os.path.join(case_dir, fname)
+        write_gz(p, data)
+        shutil.copy(p, os.path.join(HERE, f"{name}__{fname}"))
+        inputs[fname] = [g0, g1]
+        paths.append(p)
+    counter = quiet(F.tally_barcodes, cores, paths, None)
+    return {"config": config, "files": inputs, "cores": cores,
+            "tally": {k: list(v.items()) for k, v in counter.items()}}
+
+
 def cli_case(tmp):
     """The 3-file KAT of SURVEY Appendix A through the real CLI entry (frender_scan)."""
     d = os.path.join(tmp, "cli")
@@ -284,6 +306,14 @@ def main():
                                         {"i": True, "a": True, "o": "tag"})
     gold["demux"]["c1_short_r2"] = demux_case("c1__demux_short", gold["scan"]["c1"], 3000, tmp, {},
                                               truncate_r2=2000)
+    # the bench shape itself (BASELINE configs[1]): full 384-row sheet, -n 1 -rc
+    gold["scan"]["c2_384"] = scan_case("c2_384", "C2", 20000, 1, True, tmp)
+    # configs[3]: paired demux of that shape into 384 sample sinks + Index-hop / Ambiguous / Undetermined
+    gold["demux"]["c4"] = demux_case("c2_384__demux", gold["scan"]["c2_384"], 5000, tmp, {})
+    # configs[4]: single 6 bp index, many files (tally only: the reference's matcher needs index2)
+    gold["tally"] = {"c5": tally_case(
+        "c5", "C5", [(f"lane{k + 1}_S{k + 1}_L00{k + 1}_R1_001.fastq.gz", 600 * k, 600 * (k + 1)) for k in range(8)],
+        tmp, cores=3)}
     with open(os.path.join(HERE, "golden.json"), "w") as fh:
         json.dump(gold, fh, indent=0, sort_keys=False)
     shutil.rmtree(tmp)
