@@ -308,6 +308,92 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
     return parse_serial(a.data + s_g, e_g - s_g, rule, key_out);
 }
 
+// ---- header parsing in two halves (speculative path) ------------------------------------------------------------
+// The tile buffer is wanted back as early as possible (its refill is a long-latency bulk copy), so an extractor
+// thread first LOADS what its header line needs -- the up to seven 16-byte segments the line touches (space
+// count) into registers, the three segments in front of the line end (the key is in the last 22 bytes) into a
+// private shared-memory scratch -- the stage is released, and the arithmetic runs afterwards.
+struct HeaderRegs {
+    uint4 v[7];       // segments a0 + 16 i of the line, a0 = sb & ~15
+    unsigned sb, eb;  // buffer positions of the line start and of its '\n'
+    bool fast;        // >= 22 bytes, starts inside the staged bytes, ends within 112 bytes of a0
+};
+
+__device__ __forceinline__ void header_load(const unsigned char* buf, unsigned sb, unsigned eb, bool have, bool need5,
+                                            bool need6, HeaderRegs& r, uint4* scratch) {
+    r.sb = sb, r.eb = eb;
+    r.fast = have && sb != kUnknown && eb - sb > static_cast<unsigned>(kMaxSyms) && eb - (sb & ~15u) <= 112u;
+    const unsigned a0 = r.fast ? (sb & ~15u) : 0u;
+    const unsigned last = r.fast ? (eb - a0 - 1u) >> 4 : 0u;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        if ((i == 5 && !need5) || (i == 6 && !need6)) {  // warp-uniform
+            r.v[i] = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        r.v[i] = *reinterpret_cast<const uint4*>(buf + a0 + (static_cast<unsigned>(i) <= last ? 16u * i : 0u));
+    }
+    const unsigned tb = r.fast ? ((eb - 1u) & ~15u) - 32u : 0u;  // >= kHalo - 32 + 16 for a line of >= 22 bytes
+#pragma unroll
+    for (int k = 0; k < 3; ++k) scratch[k] = *reinterpret_cast<const uint4*>(buf + tb + 16u * k);
+}
+
+// Key of a header staged by header_load (scan rule).  Lines the fast path declines go to parse_serial on the
+// bytes in global memory, as in parse_header.
+__device__ __forceinline__ int header_key(const HeaderRegs& r, const uint4* scratch, const unsigned char* lut,
+                                          const ScanArgs& a, unsigned long long tile_off, bool need5, bool need6,
+                                          unsigned long long* key_out) {
+    if (r.fast) {
+        const unsigned a0 = r.sb & ~15u, span = r.eb - a0, last = (span - 1u) >> 4;
+        unsigned acc = 0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            if ((i == 5 && !need5) || (i == 6 && !need6)) continue;
+            const unsigned wt = static_cast<unsigned>(i) <= last ? 0x01010101u : 0u;
+            acc = __dp4a(eq_flags(r.v[i].x, a.pat_sp), wt, acc);
+            acc = __dp4a(eq_flags(r.v[i].y, a.pat_sp), wt, acc);
+            acc = __dp4a(eq_flags(r.v[i].z, a.pat_sp), wt, acc);
+            acc = __dp4a(eq_flags(r.v[i].w, a.pat_sp), wt, acc);
+        }
+        const unsigned head = eq_mask16(r.v[0], a.pat_sp) & ((1u << (r.sb - a0)) - 1u);
+        const unsigned tail = eq_mask16(scratch[2], a.pat_sp) >> (span - 16u * last);  // scratch[2] = segment `last`
+        const int spaces = static_cast<int>((acc >> 7) - __popc(head) - __popc(tail));
+        const unsigned char* const e = reinterpret_cast<const unsigned char*>(scratch) + (((r.eb - 1u) & 15u) + 33u);
+        unsigned delim = 0, lo = 0, hi = 0, top = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxSyms + 1; ++j) {  // closest to the end of the line first
+            const unsigned v = lut[e[-1 - j]];
+            const unsigned code = v & 7u;
+            delim += (v >> 3) << j;
+            if (j < 10) lo += code << (3 * j);
+            else if (j < 20) hi += code << (3 * (j - 10));
+            else if (j == 20) top = code;
+        }
+        if (spaces == 0) return FRB_ERR_BAD_HEADER;
+        if (spaces == 1 && delim != 0) {
+            const int len = __ffs(delim) - 1;  // symbols in the key, <= 21
+            const unsigned long long krev = static_cast<unsigned long long>(lo) |
+                                            (static_cast<unsigned long long>(hi) << 30) |
+                                            (static_cast<unsigned long long>(top) << 60);
+            const unsigned long long want = len ? (kFoldLsb3 & ((1ULL << (3 * len)) - 1ULL)) : 0ULL;
+            if (((krev | (krev >> 1) | (krev >> 2)) & want) != want) return FRB_ERR_BAD_ALPHABET;
+            const unsigned long long rv = __brevll(krev) >> 1;
+            const unsigned long long g = ((rv & kFoldLsb3) << 2) | (rv & (kFoldLsb3 << 1)) | ((rv >> 2) & kFoldLsb3);
+            *key_out = len ? (g >> (3 * (kMaxSyms - len))) : 0ULL;
+            return 0;
+        }
+    }
+    const unsigned long long e_g = tile_off + r.eb - kHalo;
+    unsigned long long s_g;
+    if (r.sb != kUnknown) {
+        s_g = tile_off + r.sb - kHalo;
+    } else {
+        s_g = e_g;
+        while (s_g > 0 && a.data[s_g - 1] != '\n') --s_g;
+    }
+    return parse_serial(a.data + s_g, e_g - s_g, FRB_RULE_SCAN, key_out);
+}
+
 // Decoupled look-back over per-tile newline counts.  The tile's own count was published by the
 // count stage (one pipeline step earlier, see scan_kernel); returns the number of newlines before
 // tile t and publishes the tile's inclusive prefix.  Called by one full warp.

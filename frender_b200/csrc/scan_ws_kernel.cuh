@@ -70,8 +70,8 @@ struct WsGeom {
     static constexpr int regs_count = RC, regs_work = RW;  // their mean is the launch budget (80)
     static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
-using WsTile = WsGeom<15, 3, 3, 1536, 2>;  // 30 KiB tiles, two stages, 3 CTAs per SM
-using WsTileB = WsGeom<15, 3, 3, 1536, 2, 48, 112>;  // A/B: the round-1 register split
+using WsTile = WsGeom<15, 3, 3, 1280, 2>;  // 30 KiB tiles, two stages, 3 CTAs per SM
+using WsTileB = WsGeom<15, 3, 3, 1280, 2, 48, 112>;  // A/B: the round-1 register split
 
 // Instantiation flags.
 //   WS_LEAN   the tally of a whole file under the scan rule: no per-read outputs, no -s limit, no clock
@@ -399,6 +399,70 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     if (timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
                 }
             };
+            if constexpr (kLean) {
+                // Speculative path.  Per tile: load what the header lines need (registers + a private scratch),
+                // give the stage back at once -- its refill is a bulk copy of several thousand cycles, and the
+                // counters can only start on it when it lands -- and do the arithmetic afterwards.  The ticket
+                // for a refill is drawn one tile ahead, so that its round trip is over when the stage is free.
+                __shared__ uint4 s_tail[kExt][3];
+                unsigned long long ticket_have = 0, ticket_next = 0;
+                if (pt == 0) ticket_have = atomicAdd(&a.status[0], 1ULL);
+                for (unsigned i = 0;; ++i) {
+                    const int s = i % kStages;
+                    mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
+                    counted_parity ^= 1u << s;
+                    const unsigned t = s_tile[s];
+                    if (t == kNoTile) {
+                        send(0, 0, i, t, 0, 0, 0, 0, 0, BF_END);
+                        break;
+                    }
+                    if (pt == 0)
+                        asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(ticket_next) : "l"(a.status) : "memory");
+                    unsigned char* const buf = smem + s * kWsBuf;
+                    const unsigned total = s_total[s], vnl = s_vnl[s], guess = s_guess[s];
+                    const unsigned lines = total + vnl;
+                    const unsigned halo_start = s_halo[s];
+                    const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
+                    const uint16_t* const nl = s_nl + s * kWsNlCap;
+                    // no guess (or more newlines than the list holds): scan_redo_kernel takes the tile
+                    const unsigned n_owned = (guess != kNoGuess && lines > guess) ? (lines - guess + 3) / 4 : 0;
+                    bool released = false;
+#pragma unroll 1
+                    for (unsigned h0 = 0; h0 < n_owned; h0 += kExt) {
+                        const unsigned h = h0 + pt;
+                        const bool have = h < n_owned;
+                        unsigned sb = 0, eb = 0;
+                        if (have) {
+                            const unsigned j = guess + 4 * h;
+                            sb = j ? nl[j - 1] + 1u : halo_start;
+                            eb = nl[j];
+                        }
+                        const unsigned segs = (have && sb != kUnknown) ? (eb - (sb & ~15u) + 15u) >> 4 : 0u;
+                        const bool need5 = __any_sync(0xFFFFFFFFu, segs >= 6u && segs <= 7u);
+                        const bool need6 = __any_sync(0xFFFFFFFFu, segs == 7u);
+                        HeaderRegs hr;
+                        header_load(buf, sb, eb, have, need5, need6, hr, s_tail[pt]);
+                        if (h0 + kExt >= n_owned) {  // last pass over this tile: every read of the stage is done
+                            group_sync<kExt>(3);
+                            if (pt == 0) issue(s, static_cast<unsigned>(ticket_have));
+                            released = true;
+                        }
+                        unsigned long long key = kEmpty;
+                        int rc = 0;
+                        if (have) {
+                            rc = header_key(hr, s_tail[pt], s_lut, a, tile_off, need5, need6, &key);
+                            if (rc) key = kEmpty;
+                        }
+                        const unsigned n = n_owned - h0 < static_cast<unsigned>(kExt) ? n_owned - h0 : kExt;
+                        send(key, rc, i, t, h0, n, total, lines, guess, 0);
+                    }
+                    if (!released) {
+                        group_sync<kExt>(3);
+                        if (pt == 0) issue(s, static_cast<unsigned>(ticket_have));
+                    }
+                    ticket_have = ticket_next;
+                }
+            } else
             for (unsigned i = 0;; ++i) {
                 const int s = i % kStages;
                 mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
