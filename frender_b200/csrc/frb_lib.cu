@@ -24,6 +24,7 @@
 #include "route_kernel.cuh"
 #include "scan_common.cuh"
 #include "scan_ws_kernel.cuh"
+#include "scan_spec_kernel.cuh"
 #include "scan_verify.cuh"
 #include "scan_ws_r1_kernel.cuh"
 #include "synth_kernel.cuh"
@@ -427,9 +428,11 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         CU(c, cudaMemsetAsync(&c->st->spec_err_pos, 0, 16, c->compute));  // spec_err_pos, spec_err_code, spec_bad
         {
             ProfScope ps(c, FRB_K_SCAN);
+            static const bool ring = getenv("FRB_SCAN_KERNEL") && strcmp(getenv("FRB_SCAN_KERNEL"), "ring") == 0;
             static const bool regs_b = getenv("FRB_WS_REGS") && atoi(getenv("FRB_WS_REGS")) == 48;
-            if (regs_b) scan_ws_kernel<WsTileB, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
-            else scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            if (ring) scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            else if (regs_b) scan_spec_kernel<WsTileB><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            else scan_spec_kernel<WsTile><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
         }
         {   // the line phase of every tile by count: checks the guesses, lists the tiles without one
             ProfScope ps(c, FRB_K_VERIFY);
@@ -445,7 +448,7 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
             CU(c, cudaMemsetAsync(c->status, 0, 8, c->compute));
             ScanArgs neg = a;
             neg.negate = 1;
-            scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(neg);
+            scan_spec_kernel<WsTile><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(neg);
             spec_reset_first_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
                 table, c->cap, c->file_tiles << kCompositeShift, c->st);
             scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
@@ -535,7 +538,8 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaEventCreate(&c->t1));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTileB, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTileB>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_r1_kernel<R1Trio>, cudaFuncAttributeMaxDynamicSharedMemorySize, R1Trio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(match_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -38,65 +38,15 @@
 // bank groups.  (Round 1 used 16 segments and rotated the segment order per lane at run time, which cost
 // 36 instructions per segment for the dynamic placement of each 16-bit mask against 19 here.)
 #pragma once
-#include "scan_common.cuh"
+#include "scan_count.cuh"
 
 namespace frb {
-
-constexpr int kWsGroup = 128;                 // counter threads
-constexpr unsigned kNoTile = 0xFFFFFFFFu;
-constexpr unsigned kNoGuess = 0xFFu;
-
-// Tile geometry.  SEG = 16-byte segments per counter thread (odd: see above), PW = extractor warps,
-// CTAS = resident CTAs per SM the shared memory and registers are budgeted for.
-template <int SEG, int PW, int CTAS, int NLCAP, int STAGES, int RC = 56, int RW = 104>
-struct WsGeom {
-    static_assert(SEG % 2 == 1, "an odd segment count keeps the 128-bit shared loads conflict-free");
-    static constexpr int stages = STAGES;
-    static constexpr int seg = SEG;
-    static constexpr int per_thread = SEG * 16;
-    static constexpr int words = (per_thread + 31) / 32;     // 32-byte mask words per thread
-    static constexpr int tile = kWsGroup * per_thread;
-    static constexpr int buf = tile + kHalo;
-    static constexpr int nl_cap = NLCAP;
-    static constexpr int xwarps = PW;                        // extractor warps
-    static constexpr int xgroup = PW * 32;
-    static constexpr int threads = kWsGroup + xgroup + 32;  // + the committer warp
-    static constexpr int ctas = CTAS;
-    // per-thread register budget that keeps CTAS resident (registers are allocated per 4 warps)
-    static constexpr int maxreg = (65536 / (CTAS * ((threads + 127) / 128 * 128))) / 8 * 8;
-    // With 3 CTAs per SM the launch budget (80) is re-split inside the CTA: the counter warpgroup gives
-    // registers back (setmaxnreg.dec) and the extractor/committer warpgroup takes them (setmaxnreg.inc).
-    static constexpr bool split_regs = CTAS == 3 && threads == 256;
-    static constexpr int regs_count = RC, regs_work = RW;  // their mean is the launch budget (80)
-    static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
-};
-using WsTile = WsGeom<15, 3, 3, 1280, 2>;  // 30 KiB tiles, two stages, 3 CTAs per SM
-using WsTileB = WsGeom<15, 3, 3, 1280, 2, 48, 112>;  // A/B: the round-1 register split
 
 // Instantiation flags.
 //   WS_LEAN   the tally of a whole file under the scan rule: no per-read outputs, no -s limit, no clock
 //             instrumentation -- none of those branches exist in the code.  Everything else (demux parse,
 //             -s, timing) runs the general instantiation.
 enum : int { WS_LEAN = 1 };
-
-// status[1 + t] of the speculative path: newlines of the tile (bits 0-19), unterminated last line (bit 20),
-// guessed list index of the first header end (bits 24-31, kNoGuess = none)
-__host__ __device__ __forceinline__ unsigned long long spec_info(unsigned total, unsigned vnl, unsigned guess) {
-    return static_cast<unsigned long long>(total) | (static_cast<unsigned long long>(vnl) << 20) |
-           (static_cast<unsigned long long>(guess) << 24);
-}
-
-// (1 << (f & 31)) - 1 in one instruction (BMSK)
-__device__ __forceinline__ unsigned bits_below(unsigned f) {
-    unsigned m;
-    asm("bmsk.wrap.b32 %0, 0, %1;" : "=r"(m) : "r"(f));
-    return m;
-}
-
-template <int N>
-__device__ __forceinline__ void group_sync(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
-}
 
 template <class G, int OPT>
 __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
