@@ -369,17 +369,22 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.no_guess = no_guess;
     a.redo = c->redo;
     a.tile_bytes = static_cast<unsigned>(tile);
+    static const unsigned copy_split = getenv("FRB_COPY_SPLIT") ? static_cast<unsigned>(atoi(getenv("FRB_COPY_SPLIT"))) : 1u;
+    a.copy_split = copy_split;
+    static const unsigned wait_mode = getenv("FRB_WAIT_MODE") ? static_cast<unsigned>(atoi(getenv("FRB_WAIT_MODE"))) : 0u;
+    a.wait_mode = wait_mode;
     a.pat_nl = 0x0A0A0A0Au;
     a.pat_sp = 0x20202020u;
     CU(c, cudaMemsetAsync(&c->st->redo_n, 0, 8, c->compute));
     static unsigned long long* timing = nullptr;
     if (getenv("FRB_SCAN_TIMING")) {
-        if (!timing) cudaMalloc(&timing, 128);
-        cudaMemsetAsync(timing, 0, 128, c->compute);
+        if (!timing) cudaMalloc(&timing, 2048);
+        cudaMemsetAsync(timing, 0, 2048, c->compute);
         a.timing = timing;
     }
     // the lean (speculative) instantiation serves the tally of whole files: scan rule, no per-read outputs, no -s
-    const bool lean = lean_ok && !r1 && !a.timing && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
+    static const bool probe = getenv("FRB_SCAN_TIMING") && strcmp(getenv("FRB_SCAN_TIMING"), "spec") == 0;
+    const bool lean = lean_ok && !r1 && (!a.timing || probe) && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
                       c->cur_limit == ~0ULL && table != nullptr && table == c->file_tab && c->in_file;
     if (table == c->file_tab && c->in_file) {
         if (c->file_composite < 0) c->file_composite = lean ? 1 : 0;
@@ -430,7 +435,8 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
             ProfScope ps(c, FRB_K_SCAN);
             static const bool ring = getenv("FRB_SCAN_KERNEL") && strcmp(getenv("FRB_SCAN_KERNEL"), "ring") == 0;
             static const bool regs_b = getenv("FRB_WS_REGS") && atoi(getenv("FRB_WS_REGS")) == 48;
-            if (ring) scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            if (probe) scan_spec_kernel<WsTile, true><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+            else if (ring) scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
             else if (regs_b) scan_spec_kernel<WsTileB><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
             else scan_spec_kernel<WsTile><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
         }
@@ -458,11 +464,27 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     }
     CU(c, cudaGetLastError());
     if (a.timing) {
-        unsigned long long h[16];
+        unsigned long long h[256];
         cudaStreamSynchronize(c->compute);
-        cudaMemcpy(h, a.timing, 128, cudaMemcpyDeviceToHost);
-        const char* names[9] = {"C:wait-bytes", "C:count", "X:wait+refill", "K:lookback", "K:wait-batch", "-", "K:commit",
-                                "X:parse_header", "X:send"};
+        cudaMemcpy(h, a.timing, 2048, cudaMemcpyDeviceToHost);
+        if (probe) {
+            const char* hn[4] = {"X0 wake-up lag", "X1 wake-up lag", "X2 wake-up lag", "issue->count-start"};
+            for (int w = 0; w < 3; ++w)
+                fprintf(stderr, "PHASES X%d per tile: loads+arrive %.0f parse %.0f finish %.0f fold+slot-load %.0f  waiting %.0f\n", w,
+                        (double)h[160 + 8 * w] / (double)h[9], (double)h[161 + 8 * w] / (double)h[9],
+                        (double)h[162 + 8 * w] / (double)h[9], (double)h[163 + 8 * w] / (double)h[9],
+                        (double)h[164 + 8 * w] / (double)h[9]);
+            for (int k = 0; k < 4; ++k) {
+                fprintf(stderr, "HIST %s (500-cycle bins):", hn[k]);
+                for (int b = 0; b < 32; ++b) fprintf(stderr, " %llu", h[16 + 32 * k + b]);
+                fprintf(stderr, "\n");
+            }
+        }
+        const char* names_ws[9] = {"C:wait-bytes", "C:count", "X:wait+refill", "K:lookback", "K:wait-batch", "-", "K:commit",
+                                   "X:parse_header", "X:send"};
+        const char* names_spec[9] = {"issue->count-start", "count", "counted->released", "released->driver", "counted->seen",
+                                     "-", "-", "-", "-"};
+        const char** names = probe ? names_spec : names_ws;
         double sum = 0;
         for (int i = 0; i < 9; ++i) sum += static_cast<double>(h[i]);
         const double tiles = h[9] ? static_cast<double>(h[9]) : 1.0;
@@ -539,6 +561,7 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTile, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTileB>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_ws_r1_kernel<R1Trio>, cudaFuncAttributeMaxDynamicSharedMemorySize, R1Trio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -34,6 +34,8 @@ struct ScanArgs {
     unsigned long long* timing;  // optional: per-role clock64 sums (instrumented instantiation only)
     unsigned long long* tile_first;  // speculative path: first read ordinal of every tile of the file
     unsigned long long tile_base;  // speculative path: tiles of this file before the chunk (composite positions)
+    unsigned int copy_split;     // bulk copies per tile (0/1 = one)
+    unsigned int wait_mode;      // A-B: bit 0 counters, bit 1 extractors, bit 2 driver poll (test_wait) instead of try_wait
     int negate;                  // speculative path: take the chunk's guessed keys out of the table again
     int composite;               // scan_redo_kernel: record composite positions, leave n_reads / line_carry alone
     unsigned int* redo;          // tiles left to scan_redo_kernel, capacity n_tiles
@@ -62,6 +64,19 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+// Arrival without release semantics, issued only once `dep` is available.  A releasing arrival waits for the
+// arriving thread's outstanding global loads and atomics; the extractors always have some in flight (table
+// updates), and what the arrival has to order -- their shared-memory loads of the tile stage against the bulk
+// copy that refills it -- is ordered by the register dependency: `dep` is computed from the loaded values, so
+// the loads have returned when the arrival issues.
+__device__ __forceinline__ void mbar_arrive_relaxed_after(unsigned long long* bar, unsigned dep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0x9E3779B9;\n\t"
+        "@p mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];\n\t"
+        "@!p mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];\n\t}"
+        ::"r"(smem_addr(bar)), "r"(dep)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     // whole spin loop in one asm block (the form ptxas knows), then an explicit warp reconvergence:
     // lanes leave the loop at different times and the warp-collective code that follows
@@ -77,6 +92,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
     // not __syncwarp(): nvcc sees straight-line code here and drops it
     asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+}
+// The same wait as a pure poll (mbarrier.test_wait never suspends the thread).
+__device__ __forceinline__ void mbar_spin(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FRB_SPIN_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FRB_SPUN_%=;\n\t"
+        "bra FRB_SPIN_%=;\n\t"
+        "FRB_SPUN_%=:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_spin_one(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FRB_SPIN1_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FRB_SPUN1_%=;\n\t"
+        "bra FRB_SPIN1_%=;\n\t"
+        "FRB_SPUN1_%=:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
 }
 // non-blocking probe: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
@@ -319,8 +358,8 @@ struct HeaderRegs {
     bool fast;        // >= 22 bytes, starts inside the staged bytes, ends within 112 bytes of a0
 };
 
-__device__ __forceinline__ void header_load(const unsigned char* buf, unsigned sb, unsigned eb, bool have, bool need5,
-                                            bool need6, HeaderRegs& r, uint4* scratch) {
+__device__ __forceinline__ unsigned header_load(const unsigned char* buf, unsigned sb, unsigned eb, bool have, bool need5,
+                                                bool need6, HeaderRegs& r, uint4* scratch) {
     r.sb = sb, r.eb = eb;
     r.fast = have && sb != kUnknown && eb - sb > static_cast<unsigned>(kMaxSyms) && eb - (sb & ~15u) <= 112u;
     const unsigned a0 = r.fast ? (sb & ~15u) : 0u;
@@ -334,8 +373,17 @@ __device__ __forceinline__ void header_load(const unsigned char* buf, unsigned s
         r.v[i] = *reinterpret_cast<const uint4*>(buf + a0 + (static_cast<unsigned>(i) <= last ? 16u * i : 0u));
     }
     const unsigned tb = r.fast ? ((eb - 1u) & ~15u) - 32u : 0u;  // >= kHalo - 32 + 16 for a line of >= 22 bytes
+    unsigned dep = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) scratch[k] = *reinterpret_cast<const uint4*>(buf + tb + 16u * k);
+    for (int k = 0; k < 3; ++k) {
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + tb + 16u * k);
+        scratch[k] = v;
+        dep ^= v.x;
+    }
+    // one register of every load: when `dep` is available, every load of the stage has returned
+#pragma unroll
+    for (int i = 0; i < 7; ++i) dep ^= r.v[i].x;
+    return dep;
 }
 
 // Key of a header staged by header_load (scan rule).  Lines the fast path declines go to parse_serial on the

@@ -77,9 +77,10 @@ struct TileMeta {
 // are complete in warp 0.
 template <class G, bool kPublish>
 __device__ __forceinline__ TileMeta count_tile(const ScanArgs& a, unsigned char* buf, uint16_t* nl, unsigned* s_cwarp,
-                                               unsigned t, bool may_guess, volatile unsigned long long* status) {
+                                               unsigned t, bool may_guess, volatile unsigned long long* status,
+                                               int ct = threadIdx.x) {  // ct: index among the 128 counter threads
     constexpr int kWsTile = G::tile, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
-    const int ct = threadIdx.x, lane = ct & 31, warp = ct >> 5;
+    const int lane = ct & 31, warp = ct >> 5;
     const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
     const unsigned long long left = a.nbytes - tile_off;
     const unsigned valid = static_cast<unsigned>(left < kWsTile ? left : kWsTile);

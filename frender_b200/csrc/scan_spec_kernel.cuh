@@ -11,29 +11,31 @@
 // by count.  The result is the reference's for every input; what the speculation buys is that no CTA ever waits
 // for another CTA.
 //
-// Persistent CTAs (three per SM) claim 30 KiB tiles from a global ticket counter.  Inside a CTA:
+// Persistent CTAs (three per SM) claim 30 KiB tiles from a global ticket counter (SMs differ in speed by some
+// ten percent -- a static tile-to-CTA map was measured 12 % slower).  Inside a CTA:
 //
 //   warps 0-3  COUNTERS    wait for the tile's bytes (TMA mbarrier); newline mask, scan, newline list, guess
 //                          (count_tile); signal counted[stage]; leave count + guess in status[].
 //   warps 4-6  EXTRACTORS  one thread per header line: LOAD what the line needs (registers + a private
-//                          scratch), arrive on released[stage], then retire the table updates of the previous
-//                          tile (atomics), count spaces, extract + pack the key, fold equal keys of the warp, and
+//                          scratch), arrive on released[stage], then count spaces, extract + pack the key, fold
+//                          equal keys of the warp, retire the table updates of the previous tile (atomics), and
 //                          load the key's home slot for the next tile's update.  The three warps never wait for
 //                          each other.
 //   warp  7    DRIVER      one thread: when a stage is released, bulk-copy the next tile (ticket drawn one
 //                          step ahead) into it.
 //
 // A stage is busy from the start of its copy until the extractors have LOADED their lines, not until they
-// have parsed them: the copy of the next tile (several thousand cycles) runs under the parsing.  Table updates
-// are deferred by one tile per step (slot load -> RED or CAS -> RED), so no L2 / DRAM round trip is waited for
-// in line; the atomics are issued right after the arrival on released[], a whole tile ahead of the next one, so
-// that no arrival (release semantics) waits for them.
+// have parsed them: the copy of the next tile (2-3 thousand cycles) runs under the parsing.  Table updates are
+// deferred by one tile per step (slot load -> RED or CAS -> RED), so no L2 / DRAM round trip is waited for in
+// line.  The arrival on released[] is a relaxed one ordered by a register dependency on the stage loads: a
+// releasing arrival would wait for the atomics and slot loads the thread has in flight.
 #pragma once
 #include "scan_count.cuh"
 
 namespace frb {
 
-template <class G>
+// kProbe: clock instrumentation of the stage cycle (issue -> landed+counters free -> counted -> released -> issue)
+template <class G, bool kProbe = false>
 __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_kernel(const ScanArgs a) {
     constexpr int kStages = G::stages;
     constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap;
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
     __shared__ unsigned s_cwarp[kWsGroup / 32];
     __shared__ unsigned char s_lut[256];
     __shared__ uint4 s_tail[kExt][3];
+    __shared__ long long s_clk[kStages][3];  // kProbe: issue, counted, released
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // negate pass of a chunk whose guesses all held: nothing to take back
@@ -66,19 +69,34 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
 
     if (warp < kWsGroup / 32) {
         if constexpr (G::split_regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::regs_count));
+        const int ct = tid;
         // =============================== COUNTERS ================================================
         unsigned full_parity = 0;  // bit s
         for (unsigned i = 0;; ++i) {
             const int s = i % kStages;
-            mbar_wait(&s_full[s], (full_parity >> s) & 1u);
+            if (a.wait_mode & 1u) mbar_spin(&s_full[s], (full_parity >> s) & 1u);
+            else mbar_wait(&s_full[s], (full_parity >> s) & 1u);
             full_parity ^= 1u << s;
             const unsigned t = s_tile[s];
             if (t == kNoTile) {
-                if (tid == 0) mbar_arrive(&s_counted[s]);
+                if (ct == 0) mbar_arrive(&s_counted[s]);
                 break;
             }
-            const TileMeta m = count_tile<G, false>(a, smem + s * kWsBuf, s_nl + s * kWsNlCap, s_cwarp, t, true, nullptr);
-            if (tid == 0) {
+            long long c0 = 0;
+            if (kProbe && ct == 0) {
+                c0 = clock64();
+                atomicAdd(&a.timing[0], static_cast<unsigned long long>(c0 - s_clk[s][0]));  // issue -> counters start
+                const unsigned long long d = static_cast<unsigned long long>(c0 - s_clk[s][0]);
+                atomicAdd(&a.timing[16 + 96 + (d / 500 < 31 ? d / 500 : 31)], 1ULL);
+            }
+            const TileMeta m = count_tile<G, false>(a, smem + s * kWsBuf, s_nl + s * kWsNlCap, s_cwarp, t, true, nullptr, ct);
+            if (ct == 0) {
+                if (kProbe) {
+                    const long long c1 = clock64();
+                    atomicAdd(&a.timing[1], static_cast<unsigned long long>(c1 - c0));  // count
+                    atomicAdd(&a.timing[9], 1ULL);
+                    s_clk[s][1] = c1;
+                }
                 s_meta[s] = m;
                 mbar_arrive(&s_counted[s]);
                 // count and guess of the tile for scan_verify.cuh (nobody waits for it)
@@ -104,6 +122,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                 const unsigned long long left = a.nbytes - off;
                 const unsigned avail = static_cast<unsigned>(left < kWsTile ? left : kWsTile) + halo;
                 const unsigned bulk = avail & ~15u;
+                if (kProbe) s_clk[s][0] = clock64();
                 if (bulk) {
                     mbar_expect_tx(&s_full[s], bulk);
                     bulk_g2s(smem + s * kWsBuf + (kHalo - halo), a.data + off - halo, bulk, &s_full[s]);
@@ -120,12 +139,16 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                 const int s = i % kStages;
                 mbar_wait_one(&s_released[s], (rel_parity >> s) & 1u);
                 rel_parity ^= 1u << s;
+                if (kProbe) atomicAdd(&a.timing[3], static_cast<unsigned long long>(clock64() - s_clk[s][2]));  // released -> driver
                 more = issue(s, next);
                 // the ticket after this one: its round trip is over long before the next stage is released
                 if (more) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(next) : "l"(a.status) : "memory");
             }
             return;
         }
+        auto give_back = [&](int s, unsigned i, unsigned dep) {
+            if (lane == 0) mbar_arrive_relaxed_after(&s_released[s], dep);
+        };
         // =============================== EXTRACTORS ==============================================
         // Deferred table update, three steps, each using a memory result requested one tile earlier:
         //   p: key -> load of its home slot's key
@@ -176,12 +199,25 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                 : "memory");
         };
         unsigned counted_parity = 0;
+        unsigned long long ph[4] = {0, 0, 0, 0};  // kProbe: per-phase clocks of this warp
+        long long pc = 0;
+        unsigned long long ph_wait = 0;
         for (unsigned i = 0;; ++i) {
             const int s = i % kStages;
-            mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
+            const long long wait_start = kProbe ? clock64() : 0;
+            if (a.wait_mode & 2u) mbar_spin(&s_counted[s], (counted_parity >> s) & 1u);
+            else mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
             counted_parity ^= 1u << s;
             const unsigned t = s_tile[s];
             if (t == kNoTile) break;
+            if (kProbe && lane == 0) {  // wake-up lag: seen - max(counted, start of the wait), histogram per warp
+                const long long now = clock64();
+                const long long from = s_clk[s][1] > wait_start ? s_clk[s][1] : wait_start;
+                const unsigned long long d = static_cast<unsigned long long>(now - from);
+                if (pt == 0) atomicAdd(&a.timing[4], static_cast<unsigned long long>(now - s_clk[s][1]));
+                atomicAdd(&a.timing[16 + 32 * pwarp + (d / 500 < 31 ? d / 500 : 31)], 1ULL);
+                ph_wait += static_cast<unsigned long long>(now - wait_start);
+            }
             unsigned char* const buf = smem + s * kWsBuf;
             const TileMeta m = s_meta[s];
             const unsigned lines = m.total + m.vnl, guess = m.guess;
@@ -204,14 +240,27 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                 const unsigned segs = (have && sb != kUnknown) ? (eb - (sb & ~15u) + 15u) >> 4 : 0u;
                 const bool need5 = __any_sync(0xFFFFFFFFu, segs >= 6u && segs <= 7u);
                 const bool need6 = __any_sync(0xFFFFFFFFu, segs == 7u);
+                auto ptick = [&](int k) {
+                    if (kProbe && lane == 0) {
+                        const long long now = clock64();
+                        ph[k] += static_cast<unsigned long long>(now - pc);
+                        pc = now;
+                    }
+                };
+                if (kProbe && lane == 0) pc = clock64();
                 HeaderRegs hr;
-                header_load(buf, sb, eb, have, need5, need6, hr, s_tail[pt]);
+                unsigned dep = header_load(buf, sb, eb, have, need5, need6, hr, s_tail[pt]);
                 if (h0 + kExt >= n_owned) {  // last pass over this tile: this warp is done reading the stage
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_released[s]);
+                    dep = __reduce_xor_sync(0xFFFFFFFFu, dep);  // every lane's loads
+                    if (kProbe && pt == 0) {
+                        const long long r = clock64();
+                        atomicAdd(&a.timing[2], static_cast<unsigned long long>(r - s_clk[s][1]));  // counted -> released
+                        s_clk[s][2] = r;
+                    }
+                    give_back(s, i, dep);
                     released = true;
                 }
-                finish();  // table updates of the previous pass / tile: a whole tile ahead of the next arrival
+                ptick(0);
                 unsigned long long key = kEmpty;
                 if (have) {
                     const int rc = header_key(hr, s_tail[pt], s_lut, a, tile_off, need5, need6, &key);
@@ -220,6 +269,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                         if (atomicCAS(&a.st->spec_err_code, 0, rc) == 0) a.st->spec_err_pos = pos0 + h;
                     }
                 }
+                ptick(1);
+                // table updates of the previous pass / tile: their slot loads were issued a whole tile ago
+                finish();
+                ptick(2);
                 // fold equal keys of the warp: the lowest lane (lowest read ordinal) carries the count
                 const unsigned grp = __ballot_sync(0xFFFFFFFFu, key != kEmpty);
                 if (key != kEmpty) {
@@ -230,14 +283,17 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                         p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
                     }
                 }
+                ptick(3);
             }
-            if (!released) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_released[s]);
-            }
+            if (!released) give_back(s, i, 0u);
         }
         finish();
         finish();  // retires a compare-and-swap issued by the call above
+        if (kProbe && lane == 0)
+        {
+            for (int k = 0; k < 4; ++k) atomicAdd(&a.timing[160 + 8 * pwarp + k], ph[k]);
+            atomicAdd(&a.timing[160 + 8 * pwarp + 4], ph_wait);
+        }
     }
 }
 

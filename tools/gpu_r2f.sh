@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+FRB_SCAN_TIMING=spec timeout 300 python tools/prof_scan.py 40000000 3 24 2>&1 | tail -4 | tee gpurun_out/f_probe.log
