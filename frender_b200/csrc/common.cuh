@@ -11,8 +11,9 @@ namespace frb {
 // and its count/first updates touch a single sector.
 struct __align__(32) Slot {
     unsigned long long key;    // packed key, FRB_EMPTY_KEY when free
+    unsigned long long first;  // smallest read position seen      (dict insertion order, F:176); next to the key so
+                               // that one 16-byte load shows whether an update can lower it at all
     unsigned long long count;  // reads carrying the key           (dict value, F:172-177)
-    unsigned long long first;  // smallest read position seen      (dict insertion order, F:176)
     unsigned long long aux;    // unused
 };
 

@@ -158,20 +158,21 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
         //   swap);  taken by another key -> load of the next slot            (q)
         //   q: the loaded key is ours -> count / first update; anything else (lost race, two other keys in a row)
         //   -> the in-line probe loop.  Nobody knows who won a slot: occupied slots are counted when the file ends.
-        unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0;
+        unsigned long long p_key = 0, p_pos = 0, p_slot = 0, p_seen = 0, p_first = 0;
         unsigned long long q_key = 0, q_pos = 0, q_slot = 0, q_old = 0;
         unsigned p_cnt = 0, q_cnt = 0;
-        auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
+        // seen_first: a value `first` has had (it only ever falls): an update that cannot lower it is left out
+        auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos, unsigned long long seen_first) {
             if (a.negate) {  // take the keys of a mis-guessed chunk out again
                 atomicAdd(&a.table[slot].count, 0ULL - static_cast<unsigned long long>(cnt));
                 return;
             }
             atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
-            atomicMin(&a.table[slot].first, pos);
+            if (pos < seen_first) atomicMin(&a.table[slot].first, pos);
         };
         auto finish = [&]() {
             if (q_cnt) {
-                if (q_old == q_key) bump(q_slot, q_cnt, q_pos);
+                if (q_old == q_key) bump(q_slot, q_cnt, q_pos, ~0ULL);
                 else table_add(a.table, a.table_mask, q_key, a.negate ? 0ULL - q_cnt : static_cast<unsigned long long>(q_cnt),
                                a.negate ? ~0ULL : q_pos, &a.st->occupied, a.st);
                 q_cnt = 0;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
             const bool look = p_cnt && p_seen != p_key;  // claim or re-probe: a q set is born
             if (p_cnt) {
                 if (p_seen == p_key) {
-                    bump(p_slot, p_cnt, p_pos);
+                    bump(p_slot, p_cnt, p_pos, p_first);
                 } else {
                     q_key = p_key, q_pos = p_pos, q_cnt = p_cnt;
                     q_slot = claim ? p_slot : ((p_slot + 1) & a.table_mask);
@@ -280,7 +281,11 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
                     if (lane == __ffs(same) - 1) {
                         p_key = key, p_pos = pos0 + h, p_cnt = __popc(same);
                         p_slot = hash64(key) & a.table_mask;
-                        p_seen = *reinterpret_cast<volatile unsigned long long*>(&a.table[p_slot].key);
+                        // key and first of the home slot in one 16-byte load
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];"
+                                     : "=l"(p_seen), "=l"(p_first)
+                                     : "l"(&a.table[p_slot].key)
+                                     : "memory");
                     }
                 }
                 ptick(3);

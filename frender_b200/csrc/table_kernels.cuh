@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(256) clear_table_kernel(Slot* tab, unsigned lo
     ulonglong4* t4 = reinterpret_cast<ulonglong4*>(tab);
     for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < cap;
          i += stride)
-        t4[i] = make_ulonglong4(kEmpty, 0ULL, ~0ULL, 0ULL);
+        t4[i] = make_ulonglong4(kEmpty, ~0ULL, 0ULL, 0ULL);  // key, first, count, aux
 }
 
 // Number of occupied slots (the unique keys of a file).  The scan kernel does not keep this count: knowing who
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restri
          i < cap_up; i += stride) {
         ulonglong4 s = make_ulonglong4(kEmpty, 0, 0, 0);
         if (i < cap) s = reinterpret_cast<const ulonglong4*>(tab)[i];
-        const bool occ = s.x != kEmpty && s.y != 0;
+        const bool occ = s.x != kEmpty && s.z != 0;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, occ);
         if (lane == 0) s_warp[warp] = __popc(m);
         __syncthreads();
@@ -62,9 +62,9 @@ __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restri
             const unsigned long long idx = s_base + before + __popc(m & ((1u << lane) - 1u));
             if (idx < out_cap) {
                 keys[idx] = s.x;
-                counts[idx] = s.y;
+                counts[idx] = s.z;
                 // composite position (tile << 13 | header index) -> read ordinal
-                first[idx] = tile_first ? tile_first[s.z >> kCompositeShift] + (s.z & ((1ULL << kCompositeShift) - 1)) : s.z;
+                first[idx] = tile_first ? tile_first[s.y >> kCompositeShift] + (s.y & ((1ULL << kCompositeShift) - 1)) : s.y;
             }
         }
     }
