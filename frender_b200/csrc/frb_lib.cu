@@ -26,7 +26,6 @@
 #include "scan_ws_kernel.cuh"
 #include "scan_spec_kernel.cuh"
 #include "scan_verify.cuh"
-#include "scan_ws_r1_kernel.cuh"
 #include "synth_kernel.cuh"
 #include "table_kernels.cuh"
 
@@ -332,10 +331,9 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
                 uint64_t out_cap = ~0ULL) {
     if (nbytes == 0) return FRB_OK;
     if (reinterpret_cast<uintptr_t>(dev) & 15) return fail(c, FRB_ERR_ARG, "chunk pointer must be 16-byte aligned");
-    // FRB_SCAN_KERNEL=r1: the round-1 kernel (same-box A/B); FRB_SCAN_LEAN=0: general instantiation everywhere
-    static const bool r1 = getenv("FRB_SCAN_KERNEL") && strcmp(getenv("FRB_SCAN_KERNEL"), "r1") == 0;
-    static const bool lean_ok = !(getenv("FRB_SCAN_LEAN") && atoi(getenv("FRB_SCAN_LEAN")) == 0);
-    const uint64_t tile = static_cast<uint64_t>(r1 ? R1Trio::tile : WsTile::tile);
+    // FRB_SCAN_SPEC=0: the general (look-back) kernel everywhere -- A/B switch
+    static const bool lean_ok = !(getenv("FRB_SCAN_SPEC") && atoi(getenv("FRB_SCAN_SPEC")) == 0);
+    const uint64_t tile = static_cast<uint64_t>(WsTile::tile);
     const uint64_t n_tiles = (nbytes + tile - 1) / tile;
     if (n_tiles >= 0xFFFFFFFFULL || nbytes >= (1ULL << 40)) return fail(c, FRB_ERR_ARG, "chunk too large");
     if (n_tiles + 1 > c->status_cap) {
@@ -369,10 +367,6 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.no_guess = no_guess;
     a.redo = c->redo;
     a.tile_bytes = static_cast<unsigned>(tile);
-    static const unsigned copy_split = getenv("FRB_COPY_SPLIT") ? static_cast<unsigned>(atoi(getenv("FRB_COPY_SPLIT"))) : 1u;
-    a.copy_split = copy_split;
-    static const unsigned wait_mode = getenv("FRB_WAIT_MODE") ? static_cast<unsigned>(atoi(getenv("FRB_WAIT_MODE"))) : 0u;
-    a.wait_mode = wait_mode;
     a.pat_nl = 0x0A0A0A0Au;
     a.pat_sp = 0x20202020u;
     CU(c, cudaMemsetAsync(&c->st->redo_n, 0, 8, c->compute));
@@ -384,7 +378,7 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     }
     // the lean (speculative) instantiation serves the tally of whole files: scan rule, no per-read outputs, no -s
     static const bool probe = getenv("FRB_SCAN_TIMING") && strcmp(getenv("FRB_SCAN_TIMING"), "spec") == 0;
-    const bool lean = lean_ok && !r1 && (!a.timing || probe) && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
+    const bool lean = lean_ok && (!a.timing || probe) && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
                       c->cur_limit == ~0ULL && table != nullptr && table == c->file_tab && c->in_file;
     if (table == c->file_tab && c->in_file) {
         if (c->file_composite < 0) c->file_composite = lean ? 1 : 0;
@@ -394,15 +388,10 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     if (!lean) {
         CU(c, cudaMemsetAsync(c->status, 0, (n_tiles + 1) * 8, c->compute));
         ProfScope ps(c, FRB_K_SCAN);
-        if (r1) {
-            scan_ws_r1_kernel<R1Trio><<<grid, R1Trio::threads, R1Trio::smem, c->compute>>>(a);
-            scan_redo_r1_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
-        } else {
-            scan_ws_kernel<WsTile, 0><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
-            // tiles the kernel left out (empty list unless the input is not well-formed FASTQ or has
-            // lines shorter than 20 bytes on average)
-            scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
-        }
+        scan_ws_kernel<WsTile><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
+        // tiles the kernel left out (empty list unless the input is not well-formed FASTQ or has lines shorter
+        // than 24 bytes on average)
+        scan_redo_kernel<<<c->sm_count, 64, 0, c->compute>>>(a);
         c->launches += 2;
     } else {
         // room for the first read ordinal of every tile of the file
@@ -436,8 +425,6 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
             static const bool ring = getenv("FRB_SCAN_KERNEL") && strcmp(getenv("FRB_SCAN_KERNEL"), "ring") == 0;
             static const bool regs_b = getenv("FRB_WS_REGS") && atoi(getenv("FRB_WS_REGS")) == 48;
             if (probe) scan_spec_kernel<WsTile, true><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
-            else if (ring) scan_ws_kernel<WsTile, WS_LEAN><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
-            else if (regs_b) scan_spec_kernel<WsTileB><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
             else scan_spec_kernel<WsTile><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
         }
         {   // the line phase of every tile by count: checks the guesses, lists the tiles without one
@@ -558,12 +545,9 @@ int frb_create(int device, uint32_t table_log2, frb_ctx** out) {
     CU(c, cudaMallocHost(&c->st_host, sizeof(DevState)));
     CU(c, cudaEventCreate(&c->t0));
     CU(c, cudaEventCreate(&c->t1));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, WS_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
+    CU(c, cudaFuncSetAttribute(scan_ws_kernel<WsTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
     CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTile, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
-    CU(c, cudaFuncSetAttribute(scan_spec_kernel<WsTileB>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsTile::smem));
-    CU(c, cudaFuncSetAttribute(scan_ws_r1_kernel<R1Trio>, cudaFuncAttributeMaxDynamicSharedMemorySize, R1Trio::smem));
     CU(c, cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(match_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(c, cudaFuncSetAttribute(match_idx1_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

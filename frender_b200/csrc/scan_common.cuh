@@ -34,8 +34,6 @@ struct ScanArgs {
     unsigned long long* timing;  // optional: per-role clock64 sums (instrumented instantiation only)
     unsigned long long* tile_first;  // speculative path: first read ordinal of every tile of the file
     unsigned long long tile_base;  // speculative path: tiles of this file before the chunk (composite positions)
-    unsigned int copy_split;     // bulk copies per tile (0/1 = one)
-    unsigned int wait_mode;      // A-B: bit 0 counters, bit 1 extractors, bit 2 driver poll (test_wait) instead of try_wait
     int negate;                  // speculative path: take the chunk's guessed keys out of the table again
     int composite;               // scan_redo_kernel: record composite positions, leave n_reads / line_carry alone
     unsigned int* redo;          // tiles left to scan_redo_kernel, capacity n_tiles
@@ -92,30 +90,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
     // not __syncwarp(): nvcc sees straight-line code here and drops it
     asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
-}
-// The same wait as a pure poll (mbarrier.test_wait never suspends the thread).
-__device__ __forceinline__ void mbar_spin(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "FRB_SPIN_%=:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra FRB_SPUN_%=;\n\t"
-        "bra FRB_SPIN_%=;\n\t"
-        "FRB_SPUN_%=:\n\t}"
-        ::"r"(smem_addr(bar)), "r"(parity)
-        : "memory");
-    asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_spin_one(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "FRB_SPIN1_%=:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra FRB_SPUN1_%=;\n\t"
-        "bra FRB_SPIN1_%=;\n\t"
-        "FRB_SPUN1_%=:\n\t}"
-        ::"r"(smem_addr(bar)), "r"(parity)
-        : "memory");
 }
 // non-blocking probe: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {

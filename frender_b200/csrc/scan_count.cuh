@@ -40,7 +40,6 @@ struct WsGeom {
     static constexpr int smem = STAGES * buf + STAGES * nl_cap * (int)sizeof(uint16_t);
 };
 using WsTile = WsGeom<15, 3, 3, 1280, 2>;  // 30 KiB tiles, two stages, 3 CTAs per SM
-using WsTileB = WsGeom<15, 3, 3, 1280, 2, 48, 112>;  // A/B: the round-1 register split
 
 // status[1 + t] of the speculative path: newlines of the tile (bits 0-19), unterminated last line (bit 20),
 // guessed list index of the first header end (bits 24-31, kNoGuess = none)

@@ -74,8 +74,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
         unsigned full_parity = 0;  // bit s
         for (unsigned i = 0;; ++i) {
             const int s = i % kStages;
-            if (a.wait_mode & 1u) mbar_spin(&s_full[s], (full_parity >> s) & 1u);
-            else mbar_wait(&s_full[s], (full_parity >> s) & 1u);
+            mbar_wait(&s_full[s], (full_parity >> s) & 1u);
             full_parity ^= 1u << s;
             const unsigned t = s_tile[s];
             if (t == kNoTile) {
@@ -206,8 +205,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_spec_k
         for (unsigned i = 0;; ++i) {
             const int s = i % kStages;
             const long long wait_start = kProbe ? clock64() : 0;
-            if (a.wait_mode & 2u) mbar_spin(&s_counted[s], (counted_parity >> s) & 1u);
-            else mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
+            mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
             counted_parity ^= 1u << s;
             const unsigned t = s_tile[s];
             if (t == kNoTile) break;

@@ -1,57 +1,30 @@
-// Hot path A: fused read-name parse + 3-bit key packing + unique-combination count, warp-specialised.
-// Replaces scan_file's loop (reference frender.py:161-177): "every 4th line from the start of the file",
-// key = 2nd space token's last ':' field (F:169) or, for demux, the last ':' field of the whole line (F:778).
+// Hot path A, general form: read-name parse + 3-bit key packing (+ unique-combination count) with the exact read
+// ordinal of every header known BEFORE anything is written.  Serves what the speculative tally kernel
+// (scan_spec_kernel.cuh) does not: per-read outputs for the demux router (keys under the demux rule F:778, record
+// offsets), the -s head sample (F:163-165) and the clock instrumentation.
 //
-// Persistent CTAs (three per SM) claim tiles from a global ticket counter; a tile and the 512 bytes in front
-// of it arrive in shared memory by one bulk copy (cp.async.bulk + mbarrier), two stages deep, so every input
-// byte crosses HBM once.  Inside a CTA three roles meet only through shared-memory mbarriers:
+// Every tile's line phase comes from a decoupled look-back over the newline counts the counters publish:
 //
-//   warps 0-3  COUNTERS    for tile i: wait for its bytes (TMA mbarrier), 15 x 16 bytes per thread ->
-//                          newline mask, group scan, ordered newline-position list in shared memory,
-//                          start of the line that straddles the tile start, publish the tile's newline
-//                          count, guess of the line phase from the text, signal `counted[stage]`.
-//   warps 4-6  EXTRACTORS  for tile i: one thread per (guessed) header line: key extraction, fold inside
-//                          the warp, key batch into a shared-memory ring for the committer; thread 0 then
-//                          refills the stage (ticket + bulk copy).  No global atomics besides the ticket.
-//   warp  7    COMMITTER   per tile: look-back over the published counts (the only wait on other CTAs),
-//                          check of the guess against it, bookkeeping; per batch: deferred table updates.
-//                          Tiles whose guess was wrong go to scan_redo_kernel.
+//   warps 0-3  COUNTERS    count_tile (scan_count.cuh): newline mask, scan, newline list, guess; publish the tile's
+//                          newline count at once, signal `counted[stage]`.
+//   warps 4-6  EXTRACTORS  one thread per header line: key extraction, fold inside the warp, key batch into a
+//                          shared-memory ring for the committer; thread 0 then refills the stage (ticket + bulk
+//                          copy).  With a guess they do not wait for the look-back, without one (always the case
+//                          when per-read outputs or -s are on) they ask the committer for the count first.
+//   warp  7    COMMITTER   per tile: look-back over the published counts (the only wait on other CTAs), check of
+//                          a guess against it, bookkeeping; per batch: deferred table updates.  Tiles whose guess
+//                          was wrong go to scan_redo_kernel.
 //
-// Two instantiations:
-//   general (OPT = 0)   every tile's line phase comes from a decoupled look-back over the published newline
-//                       counts (the committer does it; with a guess the extractors do not wait for it, without
-//                       one they do).  Serves per-read outputs (demux), -s, and the clock instrumentation.
-//   WS_LEAN             the tally of whole files.  SPECULATIVE: guessed tiles are extracted and committed at
-//                       once, under composite positions (tile << 13 | header index) that need no prefix; each
-//                       tile leaves its newline count and its guess in status[].  scan_verify.cuh then sums the
-//                       counts, checks every guess against the count, turns tiles without a guess over to
-//                       scan_redo_kernel, and -- when a guess was wrong, i.e. the input is not well-formed
-//                       FASTQ -- has the whole chunk taken out of the table again (negate pass) and redone
-//                       strictly by count.  No CTA ever waits for another CTA, so the three roles of a CTA are
-//                       coupled only through their own two tile stages and the key-batch ring.
-//
-// With 3 CTAs per SM the launch register budget is re-split between the two warpgroups (setmaxnreg).
-//
-// A counter thread owns 15 segments of 16 bytes (240 contiguous bytes).  The odd segment count is what
-// makes the shared-memory loads conflict-free with compile-time register indices: lane l reads segment j at
-// bank group (15 l + j) mod 8 = (j - l) mod 8, so the eight lanes of a 128-bit load phase hit eight different
-// bank groups.  (Round 1 used 16 segments and rotated the segment order per lane at run time, which cost
-// 36 instructions per segment for the dynamic placement of each 16-bit mask against 19 here.)
+// With 3 CTAs per SM the launch register budget is re-split between the two warpgroups (setmaxnreg): counters 48,
+// extractors + committer 112.
 #pragma once
 #include "scan_count.cuh"
 
 namespace frb {
 
-// Instantiation flags.
-//   WS_LEAN   the tally of a whole file under the scan rule: no per-read outputs, no -s limit, no clock
-//             instrumentation -- none of those branches exist in the code.  Everything else (demux parse,
-//             -s, timing) runs the general instantiation.
-enum : int { WS_LEAN = 1 };
-
-template <class G, int OPT>
+template <class G>
 __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
-    constexpr bool kLean = (OPT & WS_LEAN) != 0;
-    constexpr int kRule = kLean ? FRB_RULE_SCAN : kRuleRuntime;
+    constexpr int kRule = kRuleRuntime;
     constexpr int kStages = G::stages;
     constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
     constexpr int kExt = G::xgroup, kXWarps = G::xwarps;
@@ -74,19 +47,16 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __shared__ unsigned char s_lut[256];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if constexpr (kLean) {  // negate pass of a chunk whose guesses all held: nothing to take back
-        if (a.negate && *reinterpret_cast<volatile int*>(&a.st->spec_bad) == 0) return;
-    }
-    const unsigned long long L0 = kLean ? 0ULL :
+    const unsigned long long L0 =
         a.use_carry ? *reinterpret_cast<volatile unsigned long long*>(&a.st->line_carry) : a.line_base;
     const unsigned long long chunk_first_read = (L0 + 3) >> 2;
     volatile unsigned long long* status = a.status + 1;
-    const bool timing = !kLean && a.timing != nullptr;
+    const bool timing = a.timing != nullptr;
 
-    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, kLean ? FRB_RULE_SCAN : a.rule);
+    for (int i = tid; i < 256; i += G::threads) s_lut[i] = lut_entry(i, a.rule);
     if (tid == 0) {
         s_prefix[0] = 0, s_prefix[1] = 0, s_prefix[2] = 0, s_prefix[3] = 0;
-        if (!kLean && blockIdx.x == 0) a.st->chunk_l0 = L0;
+        if (blockIdx.x == 0) a.st->chunk_l0 = L0;
 #pragma unroll
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], 1);
@@ -102,7 +72,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
     __syncthreads();
 
     if (warp < kWsGroup / 32) {
-        if constexpr (G::split_regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kLean ? G::regs_count : 48));
+        if constexpr (G::split_regs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
         // =============================== COUNTERS ================================================
         const int ct = tid;
         unsigned full_parity = 0;  // bit s
@@ -110,7 +80,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
         unsigned long long t_wait = 0, t_work = 0;
         // may the line phase be guessed from the text at all?  (per-read outputs and -s need the exact
         // read ordinal before extraction)
-        const bool may_guess = kLean || (!a.no_guess && !a.keys_out && !a.rec_off_out && a.read_limit == ~0ULL);
+        const bool may_guess = !a.no_guess && !a.keys_out && !a.rec_off_out && a.read_limit == ~0ULL;
         for (unsigned i = 0;; ++i) {
             const int s = i % kStages;
             mbar_wait(&s_full[s], (full_parity >> s) & 1u);
@@ -121,141 +91,20 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 if (ct == 0) mbar_arrive(&s_counted[s]);
                 break;
             }
-            unsigned char* const buf = smem + s * kWsBuf;
-            const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
-            const unsigned long long left = a.nbytes - tile_off;
-            const unsigned valid = static_cast<unsigned>(left < kWsTile ? left : kWsTile);
-            {   // bytes past the last 16-byte multiple of the bulk copy (final tile only)
-                const unsigned halo = t ? kHalo : 0;
-                const unsigned avail = valid + halo, bulk = avail & ~15u;
-                if (avail != bulk) {
-                    if (ct < static_cast<int>(avail - bulk))
-                        buf[(kHalo - halo) + bulk + ct] = a.data[tile_off - halo + bulk + ct];
-                    group_sync<kWsGroup>(1);
-                }
-            }
-            // Newline mask of this thread's bytes as 32-byte words, MIRRORED: byte k of word q (thread byte
-            // 32q + k) sits at bit 31 - k, so the first newline of a word is its count of leading zeros.
-            constexpr int kWords = G::words;
-            unsigned w[kWords];
-            const uint4* t4 = reinterpret_cast<const uint4*>(buf + kHalo) + ct * G::seg;
-#pragma unroll
-            for (int q = 0; q < kWords; ++q) {
-                if (2 * q + 1 < G::seg) w[q] = eq_mask32_rev(t4[2 * q], t4[2 * q + 1], a.pat_nl);
-                else w[q] = eq_mask16_rev_hi(t4[2 * q], a.pat_nl);
-            }
-            {
-                const int nv = static_cast<int>(valid) - ct * kWsPerThread;
-                if (nv < kWsPerThread) {
-#pragma unroll
-                    for (int q = 0; q < kWords; ++q) {
-                        const int n = nv - 32 * q;  // bytes of word q that exist: keep the top n bits
-                        w[q] = n <= 0 ? 0u : (n >= 32 ? w[q] : (w[q] & ~(0xFFFFFFFFu >> n)));
-                    }
-                }
-            }
-            unsigned cnt = 0;
-#pragma unroll
-            for (int q = 0; q < kWords; ++q) cnt += __popc(w[q]);
-            unsigned incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += n;
-            }
-            if (lane == 31) s_cwarp[warp] = incl;
-            group_sync<kWsGroup>(1);
-            unsigned wbase = 0, total = 0;
-#pragma unroll
-            for (int k = 0; k < kWsGroup / 32; ++k) {
-                const unsigned v = s_cwarp[k];
-                if (k < warp) wbase += v;
-                total += v;
-            }
-            // the tile's newline count goes out the moment it is known (before the list is built): every later
-            // tile's look-back waits for it.  Thread 32: not the thread that arrives on the mbarrier below
-            if (!kLean && ct == 32) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
-            // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
-            const unsigned vnl = (t == a.n_tiles - 1 && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
-            {   // ordered list of newline positions; line numbers come later, from the look-back
-                uint16_t* const nl = s_nl + s * kWsNlCap;
-                unsigned idx = wbase + incl - cnt;
-                unsigned pos0 = kHalo + ct * kWsPerThread;
-                // A list that does not fit is never read (the tile goes to scan_redo_kernel), so one range
-                // check per thread is enough.  Straight-line code for the first two newlines of a 32-byte
-                // word -- a third one means lines shorter than 16 bytes -- keeps the warp out of a
-                // data-dependent loop.
-                if (wbase + incl <= static_cast<unsigned>(kWsNlCap)) {
-                    // predicated stores (no branch) for the first two newlines of a word; a third is rare
-                    auto store_if = [](uint16_t* p, unsigned value, unsigned cond) {
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}"
-                            ::"r"(smem_addr(p)), "h"(static_cast<unsigned short>(value)), "r"(cond)
-                            : "memory");
-                    };
-#pragma unroll
-                    for (int q = 0; q < kWords; ++q) {
-                        // f = index of the highest set bit = 31 - byte offset of the first newline left
-                        const unsigned m = w[q];
-                        const unsigned f1 = 31 - __clz(m);              // FLO; 0xFFFFFFFF when m == 0
-                        store_if(nl + idx, pos0 + 31 - f1, m);
-                        unsigned m2 = m & bits_below(f1);               // m == 0 stays 0
-                        const unsigned f2 = 31 - __clz(m2);
-                        store_if(nl + idx + 1, pos0 + 31 - f2, m2);
-                        m2 &= bits_below(f2);
-                        if (m2) {
-                            unsigned k = idx + 2;
-                            do {
-                                const unsigned f = 31 - __clz(m2);
-                                nl[k++] = static_cast<uint16_t>(pos0 + 31 - f);
-                                m2 &= ~(1u << f);
-                            } while (m2);
-                        }
-                        idx += __popc(m);
-                        pos0 += 32;
-                    }
-                }
-                if (ct == 0 && vnl && total < static_cast<unsigned>(kWsNlCap)) nl[total] = static_cast<uint16_t>(kHalo + valid);
-            }
-            unsigned halo_start = kHalo;
-            if (warp == 0) {  // start of the line that straddles the tile start (last newline of the halo)
-                if (t != 0) {
-                    const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane], a.pat_nl);
-                    const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
-                    const int top = 31 - __clz(any);  // -1: no newline in the halo
-                    const unsigned mine = lane * 16 + (31 - __clz(m)) + 1;
-                    halo_start = any ? __shfl_sync(0xFFFFFFFFu, mine, top & 31) : kUnknown;
-                }
-                if (lane == 0) s_halo[s] = halo_start, s_total[s] = total, s_valid[s] = valid, s_vnl[s] = vnl;
-            }
-            group_sync<kWsGroup>(1);  // list + meta complete (also protects s_cwarp)
-            if (warp == 0) {
-                // Which list entries end header lines?  The reference goes by line COUNT (F:161); in well-formed
-                // FASTQ the answer shows in the tile itself: a line that starts with '@' whose second successor
-                // starts with '+' and fourth with '@' is a header line, and exactly one of the first four lines
-                // may fit.  The extractors work from this guess; the committer checks it against the count.
-                unsigned g = kNoGuess;
-                if (may_guess && total >= 9 && halo_start != kUnknown && total + vnl <= static_cast<unsigned>(kWsNlCap)) {
-                    const uint16_t* const nl = s_nl + s * kWsNlCap;
-                    const unsigned c = lane & 7;  // lane c < 8 looks at the first byte of the tile's line c
-                    const unsigned first = buf[c ? nl[c - 1] + 1u : halo_start];
-                    const unsigned at = __ballot_sync(0xFFFFFFFFu, first == '@') & 0xFFu;
-                    const unsigned plus = __ballot_sync(0xFFFFFFFFu, first == '+') & 0xFFu;
-                    const unsigned hits = at & (plus >> 2) & (at >> 4) & 0xFu;
-                    if (__popc(hits) == 1) g = __ffs(hits) - 1;
-                }
-                if (lane == 0) {
-                    s_guess[s] = g;
-                    mbar_arrive(&s_counted[s]);
-                    // speculative path: count and guess of the tile for scan_verify.cuh (nobody waits for it)
-                    if (kLean && !a.negate) status[t] = spec_info(total, vnl, g);
-                }
+            // the tile's newline count goes out the moment it is known (inside count_tile): every later tile's
+            // look-back waits for it
+            const TileMeta m = count_tile<G, true>(a, smem + s * kWsBuf, s_nl + s * kWsNlCap, s_cwarp, t, may_guess, status);
+            if (ct == 0) {
+                const unsigned long long left = a.nbytes - static_cast<unsigned long long>(t) * kWsTile;
+                s_halo[s] = m.halo, s_total[s] = m.total, s_vnl[s] = m.vnl, s_guess[s] = m.guess;
+                s_valid[s] = static_cast<unsigned>(left < kWsTile ? left : kWsTile);
+                mbar_arrive(&s_counted[s]);
             }
             if (timing && ct == 0) { const long long now = clock64(); t_work += now - tm; tm = now; }
         }
         if (timing && ct == 0) atomicAdd(&a.timing[0], t_wait), atomicAdd(&a.timing[1], t_work);
     } else {
-        if constexpr (G::split_regs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kLean ? G::regs_work : 112));
+        if constexpr (G::split_regs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(112));
         // =============================== EXTRACTORS + COMMITTER ====================================
         // Batch descriptor words (s_bmeta): local tile index, global tile, first header index of the
         // batch, entries, newlines in the tile, lines (newlines + unterminated last line), guessed j0,
@@ -275,12 +124,10 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             // first.  Either way every tile is tallied by line COUNT, exactly as F:161-169 does.
             // The extractors issue no global atomics, so none of their barrier arrivals waits for one.
             auto emit = [&](unsigned long long o, unsigned long long key, unsigned long long start_g) {
-                if constexpr (!kLean) {
-                    const unsigned long long slot = o - chunk_first_read;
-                    if (slot < a.out_cap) {
-                        if (a.keys_out) a.keys_out[slot] = key;
-                        if (a.rec_off_out) a.rec_off_out[slot] = start_g;
-                    }
+                const unsigned long long slot = o - chunk_first_read;
+                if (slot < a.out_cap) {
+                    if (a.keys_out) a.keys_out[slot] = key;
+                    if (a.rec_off_out) a.rec_off_out[slot] = start_g;
                 }
             };
             auto issue = [&](int s, unsigned ticket) {  // ticket -> stage s, start its bulk copy
@@ -302,7 +149,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     mbar_arrive(&s_full[s]);
                 }
             };
-            const unsigned long long read_limit = kLean ? ~0ULL : a.read_limit;
+            const unsigned long long read_limit = a.read_limit;
             unsigned nb = 0;  // batches sent
             // hand one batch to the committer: keys (kEmpty = none), first parse error, descriptor
             auto send = [&](unsigned long long key, int rc, unsigned i, unsigned t, unsigned h0, unsigned n,
@@ -345,74 +192,8 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             long long tm = (timing && pt == 0) ? clock64() : 0;
             unsigned long long tp[4] = {0, 0, 0, 0};
             auto tick = [&](int k) {
-                if constexpr (!kLean) {
-                    if (timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
-                }
+                if (timing && pt == 0) { const long long now = clock64(); tp[k] += now - tm; tm = now; }
             };
-            if constexpr (kLean) {
-                // Speculative path.  Per tile: load what the header lines need (registers + a private scratch),
-                // give the stage back at once -- its refill is a bulk copy of several thousand cycles, and the
-                // counters can only start on it when it lands -- and do the arithmetic afterwards.  The ticket
-                // for a refill is drawn one tile ahead, so that its round trip is over when the stage is free.
-                __shared__ uint4 s_tail[kExt][3];
-                unsigned long long ticket_have = 0, ticket_next = 0;
-                if (pt == 0) ticket_have = atomicAdd(&a.status[0], 1ULL);
-                for (unsigned i = 0;; ++i) {
-                    const int s = i % kStages;
-                    mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
-                    counted_parity ^= 1u << s;
-                    const unsigned t = s_tile[s];
-                    if (t == kNoTile) {
-                        send(0, 0, i, t, 0, 0, 0, 0, 0, BF_END);
-                        break;
-                    }
-                    if (pt == 0)
-                        asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(ticket_next) : "l"(a.status) : "memory");
-                    unsigned char* const buf = smem + s * kWsBuf;
-                    const unsigned total = s_total[s], vnl = s_vnl[s], guess = s_guess[s];
-                    const unsigned lines = total + vnl;
-                    const unsigned halo_start = s_halo[s];
-                    const unsigned long long tile_off = static_cast<unsigned long long>(t) * kWsTile;
-                    const uint16_t* const nl = s_nl + s * kWsNlCap;
-                    // no guess (or more newlines than the list holds): scan_redo_kernel takes the tile
-                    const unsigned n_owned = (guess != kNoGuess && lines > guess) ? (lines - guess + 3) / 4 : 0;
-                    bool released = false;
-#pragma unroll 1
-                    for (unsigned h0 = 0; h0 < n_owned; h0 += kExt) {
-                        const unsigned h = h0 + pt;
-                        const bool have = h < n_owned;
-                        unsigned sb = 0, eb = 0;
-                        if (have) {
-                            const unsigned j = guess + 4 * h;
-                            sb = j ? nl[j - 1] + 1u : halo_start;
-                            eb = nl[j];
-                        }
-                        const unsigned segs = (have && sb != kUnknown) ? (eb - (sb & ~15u) + 15u) >> 4 : 0u;
-                        const bool need5 = __any_sync(0xFFFFFFFFu, segs >= 6u && segs <= 7u);
-                        const bool need6 = __any_sync(0xFFFFFFFFu, segs == 7u);
-                        HeaderRegs hr;
-                        header_load(buf, sb, eb, have, need5, need6, hr, s_tail[pt]);
-                        if (h0 + kExt >= n_owned) {  // last pass over this tile: every read of the stage is done
-                            group_sync<kExt>(3);
-                            if (pt == 0) issue(s, static_cast<unsigned>(ticket_have));
-                            released = true;
-                        }
-                        unsigned long long key = kEmpty;
-                        int rc = 0;
-                        if (have) {
-                            rc = header_key(hr, s_tail[pt], s_lut, a, tile_off, need5, need6, &key);
-                            if (rc) key = kEmpty;
-                        }
-                        const unsigned n = n_owned - h0 < static_cast<unsigned>(kExt) ? n_owned - h0 : kExt;
-                        send(key, rc, i, t, h0, n, total, lines, guess, 0);
-                    }
-                    if (!released) {
-                        group_sync<kExt>(3);
-                        if (pt == 0) issue(s, static_cast<unsigned>(ticket_have));
-                    }
-                    ticket_have = ticket_next;
-                }
-            } else
             for (unsigned i = 0;; ++i) {
                 const int s = i % kStages;
                 mbar_wait(&s_counted[s], (counted_parity >> s) & 1u);
@@ -434,15 +215,13 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 const uint16_t* const nl = s_nl + s * kWsNlCap;
                 if (lines > static_cast<unsigned>(kWsNlCap)) {
                     // more newlines than the list holds (lines < 20 bytes on average): scan_redo_kernel
-                    if (!kLean) send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_DENSE);
-                } else if (kLean && guess == kNoGuess) {
-                    // speculative path: a tile without a guess is tallied by scan_redo_kernel once the counts are in
+                    send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_DENSE);
                 } else {
                     const bool guessed = guess != kNoGuess;
                     unsigned j0 = guess;
                     unsigned long long of = 0;  // first read ordinal owned by the tile (known if !guessed)
                     unsigned flags = BF_FIRST | (guessed ? BF_GUESSED : 0u);
-                    if (!kLean && !guessed) {
+                    if (!guessed) {
                         send(0, 0, i, t, 0, 0, total, lines, 0, BF_FIRST | BF_NEED_PREFIX);
                         const unsigned long long K0 = wait_prefix(i);
                         j0 = static_cast<unsigned>((4 - (K0 & 3)) & 3);
@@ -488,7 +267,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             // Table updates are deferred in three steps -- slot load, then RED or CAS one batch later,
             // then the RED after a CAS one batch after that -- so no L2 round trip is waited for in line.
             constexpr int kRounds = kExt / 32;
-            const unsigned long long read_limit = kLean ? ~0ULL : a.read_limit;
+            const unsigned long long read_limit = a.read_limit;
             unsigned long long p_key[kRounds], p_pos[kRounds], p_slot[kRounds], p_seen[kRounds];
             unsigned long long q_key[kRounds], q_pos[kRounds], q_slot[kRounds], q_old[kRounds];
             unsigned p_cnt[kRounds], q_cnt[kRounds];
@@ -498,10 +277,6 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 p_key[r] = 0, p_pos[r] = 0, p_slot[r] = 0, p_seen[r] = 0;
             }
             auto bump = [&](unsigned long long slot, unsigned cnt, unsigned long long pos) {
-                if (kLean && a.negate) {  // take the keys of a mis-guessed chunk out again
-                    atomicAdd(&a.table[slot].count, 0ULL - static_cast<unsigned long long>(cnt));
-                    return;
-                }
                 atomicAdd(&a.table[slot].count, static_cast<unsigned long long>(cnt));
                 atomicMin(&a.table[slot].first, pos);
             };
@@ -548,9 +323,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
             long long tm = (timing && lane == 0) ? clock64() : 0;
             unsigned long long k_wait = 0, k_look = 0, k_commit = 0;
             auto ktick = [&](unsigned long long& acc) {
-                if constexpr (!kLean) {
-                    if (timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
-                }
+                if (timing && lane == 0) { const long long now = clock64(); acc += now - tm; tm = now; }
             };
             for (unsigned nb = 0;; ++nb) {
                 const unsigned b = nb % kBatches;
@@ -560,10 +333,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 const unsigned flags = m[BM_FLAGS];
                 if (flags & BF_END) break;
                 const unsigned i = m[BM_I], t = m[BM_T], h0 = m[BM_H0], n = m[BM_N];
-                if constexpr (kLean) {
-                    tile_ok = true;  // speculative: checked by scan_verify.cuh after the kernel
-                    of = (a.tile_base + t) << kCompositeShift;
-                } else if (flags & BF_FIRST) {
+                if (flags & BF_FIRST) {
                     unsigned long long excl;
                     tile_prefix<true>(status, t, m[BM_TOTAL], lane, &excl);
                     const unsigned long long K0 = L0 + excl;
@@ -571,8 +341,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                     tile_ok = !(flags & BF_DENSE) &&
                               (!(flags & BF_GUESSED) || static_cast<unsigned>((4 - (K0 & 3)) & 3) == m[BM_J0]);
                     if (lane == 0) {
-                        if (!kLean || (flags & BF_NEED_PREFIX))
-                            s_prefix[i & 3] = (static_cast<unsigned long long>((i + 1) & 0xFFFFFFu) << 40) | excl;
+                        s_prefix[i & 3] = (static_cast<unsigned long long>((i + 1) & 0xFFFFFFu) << 40) | excl;
                         if (tile_ok) {
                             const unsigned long long o_end = (K0 + m[BM_LINES] + 3) >> 2;
                             const unsigned long long c_hi = o_end < read_limit ? o_end : read_limit;
@@ -598,12 +367,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_bfree[b]);  // the batch is in registers
                 if (tile_ok && n && err != 0xFFFFFFFFu && lane == 0) {
-                    if constexpr (kLean) {  // an error of a guessed tile counts once the guesses are confirmed
-                        if (atomicCAS(&a.st->spec_err_code, 0, -static_cast<int>(err & 0xFFu)) == 0)
-                            a.st->spec_err_pos = of + h0 + (err >> 8);
-                    } else {
-                        raise_error(a.st, -static_cast<int>(err & 0xFFu), of + h0 + (err >> 8));
-                    }
+                    raise_error(a.st, -static_cast<int>(err & 0xFFu), of + h0 + (err >> 8));
                 }
                 if (a.table) {
 #pragma unroll
@@ -623,7 +387,7 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 #pragma unroll
                 for (int r = 0; r < kRounds; ++r) finish(r);
             }
-            if (!kLean && lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
+            if (lane == 0 && my_reads) atomicAdd(&a.st->n_reads, my_reads);
             if (timing && lane == 0) {
                 atomicAdd(&a.timing[3], k_look), atomicAdd(&a.timing[4], k_wait), atomicAdd(&a.timing[6], k_commit);
             }
