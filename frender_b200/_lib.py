@@ -54,6 +54,7 @@ SIGNATURES = {
     "frb_total_load": (C.c_int, [vp, vp, vp, u64]),
     "frb_total_merge": (C.c_int, [vp, vp, vp, vp, u64]),
     "frb_reset": (C.c_int, [vp]),
+    "frb_resize_tables": (C.c_int, [vp, u32]),
     "frb_sheet_load": (C.c_int, [vp, vp, vp, vp, u32, u32, u32]),
     "frb_match": (C.c_int, [vp, u32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frb_route_load": (C.c_int, [vp, vp, vp, u64, u32]),

@@ -166,8 +166,10 @@ class ScanTables:
 
 
 def _scan_worker(rank, n_ranks, device, ident, jobs, sample, table_log2, conn):
-    """One process per GPU (FRENDER_GPUS > 1): scan this rank's files, merge the per-rank tables over
-    NCCL, send the per-file lists (and, from rank 0, the merged total) to the parent."""
+    """One process per GPU (FRENDER_GPUS > 1): scan this rank's files, report, and -- once the parent has heard
+    from every rank that its scans went through -- merge the per-rank tables over NCCL and send the per-file
+    lists (and, from rank 0, the merged total) to the parent.  A rank that fails never enters the collective,
+    and neither does anybody else: the parent only says "go" when all ranks are ready for it."""
     try:
         ctx = Context(device, table_log2=table_log2)
         ctx.nccl_init(ident, rank, n_ranks)
@@ -177,12 +179,18 @@ def _scan_worker(rank, n_ranks, device, ident, jobs, sample, table_log2, conn):
             reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
             fk, fc, _ = ctx.file_arrays(k)
             out.append((ordinal, reads, uniq, fk, fc))
+        conn.send(("scanned", None, None))
+        if not conn.recv():                     # another rank failed: no collective
+            return
         ctx.allmerge()
         total = ctx.total_arrays()[:2] if rank == 0 else None
         conn.send(("ok", out, total))
         ctx.close()
     except BaseException as exc:            # forwarded: the parent re-raises
-        conn.send(("error", repr(exc), None))
+        try:
+            conn.send(("error", repr(exc), None))
+        except OSError:
+            pass
     finally:
         conn.close()
 
@@ -236,9 +244,12 @@ def scan_files_concurrent(files, sample, streams, device, table_log2, main_ctx):
     return per_file, main_ctx.total_arrays()[:2]
 
 
-def scan_files_multi_gpu(files, sample, n_gpus, table_log2):
-    """File-level sharding over n_gpus GPUs: file i goes to rank i % n_gpus."""
+def scan_files_multi_gpu(files, sample, n_gpus, table_log2, worker=_scan_worker):
+    """File-level sharding over n_gpus GPUs: file i goes to rank i % n_gpus.  The parent listens to
+    all ranks at once (and to their exit): the first failure, or a rank that dies, ends the job with that rank's
+    error instead of leaving the others in a collective that can never complete."""
     import multiprocessing as mp
+    from multiprocessing.connection import wait
 
     from .shard import assign
     mpc = mp.get_context("spawn")
@@ -246,19 +257,52 @@ def scan_files_multi_gpu(files, sample, n_gpus, table_log2):
     jobs = list(enumerate(files))
     procs, pipes = [], []
     for rank in range(n_gpus):
-        parent, child = mpc.Pipe(duplex=False)
-        p = mpc.Process(target=_scan_worker, args=(rank, n_gpus, rank, ident, assign(jobs, rank, n_gpus), sample,
-                                                   table_log2, child))
+        parent, child = mpc.Pipe(duplex=True)
+        p = mpc.Process(target=worker, args=(rank, n_gpus, rank, ident, assign(jobs, rank, n_gpus), sample,
+                                             table_log2, child))
         p.start()
+        child.close()
         procs.append(p)
         pipes.append(parent)
-    per_file, total = {}, None
-    for rank, conn in enumerate(pipes):
-        status, payload, tot = conn.recv()
-        if status != "ok":
-            for p in procs:
+
+    def stop_all(message):
+        for conn in pipes:
+            try:
+                conn.send(False)
+            except OSError:
+                pass
+        for p in procs:
+            p.join(timeout=5)
+            if p.is_alive():
                 p.terminate()
-            raise SystemExit(f"GPU worker {rank} failed: {payload}")
+        raise SystemExit(message)
+
+    def collect(expect):
+        """one message of kind `expect` from every rank"""
+        got = {}
+        while len(got) < n_gpus:
+            pending = [r for r in range(n_gpus) if r not in got]
+            ready = wait([pipes[r] for r in pending] + [procs[r].sentinel for r in pending])
+            for r in pending:
+                if pipes[r] in ready:
+                    try:
+                        status, payload, tot = pipes[r].recv()
+                    except EOFError:
+                        stop_all(f"GPU worker {r} exited without a result")
+                    if status != expect:
+                        stop_all(f"GPU worker {r} failed: {payload}")
+                    got[r] = (payload, tot)
+                elif procs[r].sentinel in ready and not pipes[r].poll():
+                    stop_all(f"GPU worker {r} exited without a result")
+        return got
+
+    collect("scanned")
+    for conn in pipes:
+        conn.send(True)
+    results = collect("ok")
+    per_file, total = {}, None
+    for rank in range(n_gpus):
+        payload, tot = results[rank]
         for ordinal, reads, uniq, fk, fc in payload:
             per_file[ordinal] = (reads, uniq, fk, fc)
         if tot is not None:
@@ -322,6 +366,48 @@ def report_rc_call_info(rc_calls, indexes, out_csv_name):
         w.writerows(rows)
 
 
+def initial_table_log2(files):
+    """Slots of the unique-key tables for these inputs: FRENDER_TABLE_LOG2, or from the compressed size (about
+    70 bytes of .fastq.gz per read; a lane's unique index pairs are a few percent of its reads; load <= 1/4)."""
+    env = os.environ.get("FRENDER_TABLE_LOG2")
+    if env:
+        return int(env)
+    biggest = max((os.path.getsize(str(f)) for f in files), default=0)
+    total = sum(os.path.getsize(str(f)) for f in files)
+    expected_unique = max(biggest, total // 2) // 70 // 12
+    log2 = 16
+    while (1 << log2) < 4 * expected_unique and log2 < 28:
+        log2 += 1
+    return log2
+
+
+def tally_files(ctx, files, names, sample, cores, n_gpus):
+    """tally_barcodes (F:183-207) over the three ways of spreading the files: ranks, `-c` streams, one by one."""
+    if n_gpus > 1:
+        per_file, total = scan_files_multi_gpu(files, sample, n_gpus, ctx.table_log2)
+        for ordinal, name in enumerate(names):
+            reads, uniq = per_file[ordinal][:2]
+            print(f"Tallying barcodes from {name}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
+                  f"in {reads} reads.")
+        tables = ScanTables(names, total, [per_file[i][2:] for i in range(len(names))])
+        ctx.load_total_arrays(*total)
+    elif cores > 1 and len(files) > 1:
+        streams = min(cores, len(files), int(os.environ.get("FRENDER_MAX_STREAMS", "16")))
+        per_file, total = scan_files_concurrent(files, sample, streams, ctx.device, ctx.table_log2, ctx)
+        for ordinal, name in enumerate(names):
+            reads, uniq = per_file[ordinal][:2]
+            print(f"Tallying barcodes from {name}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
+                  f"in {reads} reads.")
+        tables = ScanTables(names, total, [per_file[i][2:4] for i in range(len(names))])
+    else:
+        for ordinal, path in enumerate(files):
+            print(f"Tallying barcodes from {names[ordinal]}...", end="")
+            reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
+            print(f"found {uniq} new barcode{'' if uniq == 1 else 's'} in {reads} reads.")
+        tables = ScanTables.from_ctx(ctx, names)
+    return tables
+
+
 def frender_scan(args, ctx=None):
     num_subs, rc_mode = args.n, args.rc
     cores = get_cores(args.c)
@@ -355,39 +441,29 @@ def frender_scan(args, ctx=None):
     files = parse_files(files, just_r1=True)
 
     own_ctx = ctx is None
-    ctx = ctx or Context(int(os.environ.get("FRENDER_DEVICE", "0")),
-                         table_log2=int(os.environ.get("FRENDER_TABLE_LOG2", "24")))
+    ctx = ctx or Context(int(os.environ.get("FRENDER_DEVICE", "0")), table_log2=initial_table_log2(files))
     try:
         # ---- tally (F:183-207) -----------------------------------------------------------------
         print(f"Scanning {len(files)} files on GPU {ctx.device} with {cores} inflate stream{'' if cores == 1 else 's'}...")
         if sample:
             assert sample >= 1, "Number of reads to sample must be ≥ 1!"
             print(f"Sampling {sample} reads from the head of each file...")
-        ctx.reset()
         names = [os.path.basename(str(path)) for path in files]
         n_gpus = min(int(os.environ.get("FRENDER_GPUS", "1")), max(len(files), 1))
-        if n_gpus > 1:
-            per_file, total = scan_files_multi_gpu(files, sample, n_gpus, ctx.table_log2)
-            for ordinal, name in enumerate(names):
-                reads, uniq = per_file[ordinal][:2]
-                print(f"Tallying barcodes from {name}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
-                      f"in {reads} reads.")
-            tables = ScanTables(names, total, [per_file[i][2:] for i in range(len(names))])
-            ctx.load_total_arrays(*total)
-        elif cores > 1 and len(files) > 1:
-            streams = min(cores, len(files), int(os.environ.get("FRENDER_MAX_STREAMS", "16")))
-            per_file, total = scan_files_concurrent(files, sample, streams, ctx.device, ctx.table_log2, ctx)
-            for ordinal, name in enumerate(names):
-                reads, uniq = per_file[ordinal][:2]
-                print(f"Tallying barcodes from {name}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
-                      f"in {reads} reads.")
-            tables = ScanTables(names, total, [per_file[i][2:4] for i in range(len(names))])
-        else:
-            for ordinal, path in enumerate(files):
-                print(f"Tallying barcodes from {names[ordinal]}...", end="")
-                reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
-                print(f"found {uniq} new barcode{'' if uniq == 1 else 's'} in {reads} reads.")
-            tables = ScanTables.from_ctx(ctx, names)
+        while True:
+            # A dict never refuses a key (F:172-177): when the unique-key tables turn out too small for the
+            # input they are re-created four times as large and the tally starts over.
+            try:
+                ctx.reset()
+                tables = tally_files(ctx, files, names, sample, cores, n_gpus)
+                break
+            except (FrbError, SystemExit) as exc:
+                full = (isinstance(exc, FrbError) and exc.code == _lib.ERR_TABLE_FULL) or "unique-key table full" in str(exc)
+                if not full or ctx.table_log2 + 2 > 32:
+                    raise
+                print(f"\nunique-key tables of 2^{ctx.table_log2} slots are full: tallying again with "
+                      f"2^{ctx.table_log2 + 2}")
+                ctx.resize_tables(ctx.table_log2 + 2)
         print("Scanning complete! Analyzing barcodes...")
 
         # ---- matcher (F:610-630) ---------------------------------------------------------------

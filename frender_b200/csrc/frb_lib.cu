@@ -218,7 +218,7 @@ int device_error_check(frb_ctx* c) {  // compute stream must be idle
         case FRB_ERR_KEY_TOO_LONG:
             return fail(c, code, "read %llu: index field longer than 21 symbols", pos);
         case FRB_ERR_TABLE_FULL:
-            return fail(c, code, "unique-key table full (2^%u slots); recreate the context with a larger table",
+            return fail(c, code, "unique-key table full (2^%u slots): frb_resize_tables / FRENDER_TABLE_LOG2 for a larger one",
                         c->log2);
         case FRB_ERR_BAD_LENGTH:
             return fail(c, code, "Barcode %s doesn't match the index lengths of the sample sheet (%u+%u)", keytxt,
@@ -580,6 +580,24 @@ void frb_destroy(frb_ctx* c) {
     cudaEventDestroy(c->t0), cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->compute), cudaStreamDestroy(c->copy);
     delete c;
+}
+
+int frb_resize_tables(frb_ctx* c, uint32_t table_log2) {
+    CU(c, cudaSetDevice(c->device));
+    if (table_log2 < 10 || table_log2 > 32) return fail(c, FRB_ERR_ARG, "table_log2 must be in [10, 32]");
+    TRY(frb_reset(c));  // forgets every file and the total: a table cannot be re-hashed under a running tally
+    CU(c, cudaStreamSynchronize(c->compute));
+    CU(c, cudaFree(c->file_tab));
+    CU(c, cudaFree(c->total_tab));
+    c->file_tab = c->total_tab = nullptr;
+    c->log2 = table_log2;
+    c->cap = 1ULL << table_log2;
+    CU(c, cudaMalloc(&c->file_tab, c->cap * sizeof(Slot)));
+    CU(c, cudaMalloc(&c->total_tab, c->cap * sizeof(Slot)));
+    TRY(clear_table(c, c->total_tab));
+    c->total_tab_clean = true;
+    CU(c, cudaStreamSynchronize(c->compute));
+    return FRB_OK;
 }
 
 int frb_sync(frb_ctx* c) {
@@ -1113,7 +1131,7 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
         static const bool sweep_only = getenv("FRB_MATCH") && strcmp(getenv("FRB_MATCH"), "sweep") == 0;
         const unsigned parts = n_subs + 1;
         const unsigned slots = static_cast<unsigned long long>(c->rows) * parts * 2 <= 2048 ? 2048u : 4096u;
-        const bool cand = !sweep_only && c->l2 > 0 && parts_usable(c->l1, n_subs, c->rows, slots) &&
+        const bool cand = !sweep_only && c->rows > 0 && c->l2 > 0 && parts_usable(c->l1, n_subs, c->rows, slots) &&
                           parts_usable(c->l2, n_subs, c->rows, slots);
         if (!reuse) {
             CU(c, cudaMemsetAsync(c->work_n, 0, 8, c->compute));

@@ -121,6 +121,13 @@ class Context:
         self.file_names = []
         self._sharded = False
 
+    def resize_tables(self, table_log2):
+        """New unique-key tables of 2^table_log2 slots; forgets every file scanned so far."""
+        self._ck(lib.frb_resize_tables(self._h, table_log2))
+        self.table_log2 = table_log2
+        self.file_names = []
+        self._sharded = False
+
     def scan_gz(self, path, ordinal, sample=None):
         """One fastq.gz through the inflate -> H2D -> kernel pipeline (scan_file, F:154-181).
         Returns (reads, unique keys, decompressed bytes)."""

@@ -126,6 +126,9 @@ int frb_total_load(frb_ctx* ctx, const uint64_t* keys, const uint64_t* counts, u
 int frb_total_merge(frb_ctx* ctx, const uint64_t* keys, const uint64_t* counts, const uint64_t* first_pos,
                     uint64_t n);
 int frb_reset(frb_ctx* ctx); /* forget all files and the total                                 */
+/* Re-create both unique-key tables with 2^table_log2 slots (implies frb_reset): the host's answer to
+ * FRB_ERR_TABLE_FULL -- a Python dict never refuses a key (F:172-177), so the CLI resizes and tallies again. */
+int frb_resize_tables(frb_ctx* ctx, uint32_t table_log2);
 
 /* ---- hot path B: mismatch matcher + index-2 orientation ------------------------------------
  * Replaces get_indexes_of_approx_matches F:214-234, analyze_barcode F:237-291,

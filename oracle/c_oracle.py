@@ -24,6 +24,11 @@ def load():
     lib.oracle_classify.restype = C.c_int
     lib.oracle_classify.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int)]
+    lib.oracle_classify_rc.restype = C.c_int
+    lib.oracle_classify_rc.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.oracle_revcomp_sheet.restype = None
+    lib.oracle_revcomp_sheet.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
     return lib
 
 
@@ -58,3 +63,35 @@ def classify_all(keys, indexes, max_subs):
             raise AssertionError(f"Barcode {k} doesn't match length of supplied barcode")
         res.append(tuple(out))
     return res
+
+
+def classify_all_rc(keys, indexes, max_subs):
+    """First pass of `-rc` (F:294-351) for every key:
+    [(m1_row, m2_row, type, sample_row, m2rc_row, rc_type, rc_sample_row)]."""
+    lib = load()
+    rows = len(indexes["id"])
+    l1, l2 = len(indexes["idx1"][0]), len(indexes["idx2"][0])
+    a = "".join(indexes["idx1"]).encode()
+    b = "".join(indexes["idx2"]).encode()
+    brc = C.create_string_buffer(len(b) + 1)
+    lib.oracle_revcomp_sheet(b, rows, l2, brc)
+    first = {}
+    group = (C.c_int * rows)(*[first.setdefault(name, len(first)) for name in indexes["id"]])
+    out = (C.c_int * 7)()
+    res = []
+    for k in keys:
+        if lib.oracle_classify_rc(k.encode(), a, b, brc.raw[:len(b)], group, rows, l1, l2, max_subs, out):
+            raise AssertionError(f"Barcode {k} doesn't match length of supplied barcode")
+        res.append(tuple(out))
+    return res
+
+
+def rc_calls(keys, counts, first_pass, indexes):
+    """call_rc_mode_per_id (F:354-388) from classify_all_rc's rows: {name: (use_rc, reads_f, reads_rc)}."""
+    acc = {name: [0, 0] for name in indexes["id"]}
+    for n, rec in zip(counts, first_pass):
+        if rec[3] >= 0:
+            acc[indexes["id"][rec[3]]][0] += int(n)
+        if rec[6] >= 0:
+            acc[indexes["id"][rec[6]]][1] += int(n)
+    return {name: (f < r, f, r) for name, (f, r) in acc.items()}

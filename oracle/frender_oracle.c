@@ -159,3 +159,46 @@ int oracle_classify(const char* key, const char* idx1, const char* idx2, int row
     }
     return 0;
 }
+
+/* Reverse complement of a fixed-width string (F:210-211): translate ATGCNatgcn, reverse; other bytes unchanged. */
+static void revcomp(const char* in, int len, char* out) {
+    for (int i = 0; i < len; ++i) {
+        char c = in[len - 1 - i];
+        switch (c) {
+            case 'A': c = 'T'; break;
+            case 'T': c = 'A'; break;
+            case 'G': c = 'C'; break;
+            case 'C': c = 'G'; break;
+            case 'a': c = 't'; break;
+            case 't': c = 'a'; break;
+            case 'g': c = 'c'; break;
+            case 'c': c = 'g'; break;
+            default: break; /* N, n and everything else */
+        }
+        out[i] = c;
+    }
+}
+
+/* analyze_barcodes_with_rc (F:294-351) for one key: forward classification into out[0..3] as oracle_classify,
+ * reverse-complement classification into out[4] (first rc-idx2 match row or -1), out[5] (rc read type), out[6]
+ * (rc sample row); out[0] takes the rc pass's idx1 row when the forward pass left it empty (F:319-323).
+ * `group[r]` = dense id of row r's sample NAME: two demuxable verdicts with different names turn both
+ * ambiguous (F:336-349).  `idx2_rc` = rows of reverse-complemented idx2 (oracle_revcomp_sheet).            */
+int oracle_classify_rc(const char* key, const char* idx1, const char* idx2, const char* idx2_rc, const int* group,
+                       int rows, int l1, int l2, int max_subs, int* out) {
+    int fwd[4], rc[4];
+    if (oracle_classify(key, idx1, idx2, rows, l1, l2, max_subs, fwd)) return -1;
+    if (oracle_classify(key, idx1, idx2_rc, rows, l1, l2, max_subs, rc)) return -1;
+    if (fwd[0] < 0) fwd[0] = rc[0];
+    if (fwd[2] == 2 && rc[2] == 2 && group[fwd[3]] != group[rc[3]]) {
+        fwd[2] = rc[2] = 3;
+        fwd[3] = rc[3] = -1;
+    }
+    out[0] = fwd[0], out[1] = fwd[1], out[2] = fwd[2], out[3] = fwd[3];
+    out[4] = rc[1], out[5] = rc[2], out[6] = rc[3];
+    return 0;
+}
+
+void oracle_revcomp_sheet(const char* idx2, int rows, int l2, char* out) {
+    for (int r = 0; r < rows; ++r) revcomp(idx2 + (size_t)r * l2, l2, out + (size_t)r * l2);
+}

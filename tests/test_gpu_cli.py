@@ -40,7 +40,7 @@ def test_cli_three_file_kat(golden, tmp_path, capsys):
     assert "S1\tCCCC\t3\tGGGG\t0\tforward" in out
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "sampled"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "sampled", "c2_384"])
 def test_cli_scan_csv_bytes(golden, golden_dir, tmp_path, name):
     """Byte-identical scan-results CSV (and index-2-calls CSV) on the single-file cases."""
     case = golden["scan"][name]
@@ -78,7 +78,7 @@ def test_cli_scan_multi_file_prefix(golden, golden_dir, tmp_path, cores):
     assert (tmp_path / out).read_bytes() == unb64(case["scan_csv"])
 
 
-@pytest.mark.parametrize("name", ["c1", "c1_ia", "c1_short_r2"])
+@pytest.mark.parametrize("name", ["c1", "c1_ia", "c1_short_r2", "c4"])
 @pytest.mark.parametrize("chunk_mb", ["64", "0"])
 def test_cli_demux_streams(golden, tmp_path, name, chunk_mb, monkeypatch):
     """Same sink files, same decompressed bytes as the reference's demux (F:733-814)."""
@@ -125,3 +125,17 @@ def test_cli_demux_unknown_key(golden, tmp_path):
     with pytest.raises(SystemExit, match="Couldn't find barcode GGGG\\+TTTT in supplied frender result file!"):
         run_cli(["demux", "-r", str(tmp_path / "r.csv"), "-d", str(tmp_path / "o"),
                  str(tmp_path / "x_R1_001.fastq.gz"), str(tmp_path / "x_R2_001.fastq.gz")], tmp_path)
+
+
+def test_cli_scan_grows_a_full_table(golden, golden_dir, tmp_path, monkeypatch, capsys):
+    """More unique keys than table slots: the reference's dict never refuses a key (F:172-177); the CLI re-creates
+    the tables four times as large and tallies again.  Same CSV bytes as the reference."""
+    case = golden["scan"]["c2_384"]                      # 2614 unique keys
+    (fname, _), = case["files"].items()
+    dst = tmp_path / fname
+    dst.write_bytes(open(os.path.join(golden_dir, f"c2_384__{fname}"), "rb").read())
+    (tmp_path / "SampleSheet.csv").write_text(case["sheet_csv"])
+    monkeypatch.setenv("FRENDER_TABLE_LOG2", "10")       # 1024 slots
+    run_cli(["scan", "-n", "1", "-rc", "-b", str(tmp_path / "SampleSheet.csv"), str(dst)], tmp_path)
+    assert "tallying again with 2^12" in capsys.readouterr().out
+    assert (tmp_path / f"frender-scan-results_1-mismatches_{fname}.csv").read_bytes() == unb64(case["scan_csv"])

@@ -40,12 +40,14 @@ def scan_resident(ctx, dbuf, nbytes):
 
 
 def test_c_oracle_at_3m_reads():
-    """3 M reads of the C2 lane: counts and first-appearance order against the C oracle, forward
-    classification of every unique key against the C oracle."""
+    """3 M reads of the C2 lane, the bench shape itself (384-row sheet, -n 1 -rc): counts and first-appearance
+    order against the C oracle; BOTH matcher passes of every unique key -- the forward + reverse-complement
+    first pass with its per-sample orientation sums (F:294-388) and the oriented second pass (F:618-630) --
+    against the C oracle (itself pinned on the reference's c2_384 golden case)."""
     import c_oracle
     import frender_b200._lib as L
     from frender_b200 import synth
-    from frender_b200.engine import C, Context, unpack_keys
+    from frender_b200.engine import C, Context, reverse_complement, unpack_keys
     reads = 3_000_000
     spec = synth.make_spec("C2")
     ctx = Context(0, table_log2=21)
@@ -61,11 +63,27 @@ def test_c_oracle_at_3m_reads():
     assert names == list(want) and counts.tolist() == list(want.values())
     assert (np.diff(first.astype(np.int64)) > 0).all()
     idx = spec.indexes()
-    ctx.load_sheet(idx)
-    res = ctx.match(1, False)
-    ref = np.array(c_oracle.classify_all(names, idx, 1), np.int32)
-    assert (res["m1"] == ref[:, 0]).all() and (res["m2"] == ref[:, 1]).all()
-    assert (res["type"] == ref[:, 2]).all() and (res["srow"] == ref[:, 3]).all()
+    assert len(idx["id"]) == 384
+    sheet = ctx.load_sheet(idx)
+    # pass 1: forward and reverse-complement i5 together
+    res = ctx.match(1, True)
+    ref = np.array(c_oracle.classify_all_rc(names, idx, 1), np.int32)
+    for col, name in enumerate(("m1", "m2", "type", "srow", "m2rc", "type_rc", "srow_rc")):
+        got = res[name].astype(np.int32)
+        if name == "m1":   # the rc pass's idx1 row fills an empty forward one (F:319-323); same row either way
+            pass
+        assert (got == ref[:, col]).all(), name
+    calls = c_oracle.rc_calls(names, counts.tolist(), ref.tolist(), idx)
+    got_calls = ctx.rc_calls(res)
+    assert {k: (v["call"], v["reads_f"], v["reads_rc"]) for k, v in got_calls.items()} == calls
+    assert any(v[0] for v in calls.values()) and not all(v[0] for v in calls.values())
+    # pass 2: every row's idx2 in the orientation its sample was called in
+    use = np.array([calls[name][0] for name in idx["id"]], np.uint8)
+    oriented = dict(idx, idx2=[reverse_complement(s) if u else s for s, u in zip(idx["idx2"], use)])
+    res2 = ctx.match(1, False, use)
+    ref2 = np.array(c_oracle.classify_all(names, oriented, 1), np.int32)
+    assert (res2["m1"] == ref2[:, 0]).all() and (res2["m2"] == ref2[:, 1]).all()
+    assert (res2["type"] == ref2[:, 2]).all() and (res2["srow"] == ref2[:, 3]).all()
     ctx.close()
 
 

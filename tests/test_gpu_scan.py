@@ -61,7 +61,7 @@ def test_tally_edges(ctx, golden, tmp_path):
             assert [list(x) for x in got["total"].items()] == case["total"], name
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "multi", "sampled"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "multi", "sampled", "c2_384"])
 def test_scan_stages_golden(ctx, golden, golden_dir, name):
     """tally -> first pass -> orientation call -> second pass against the reference's outputs."""
     from frender_b200.engine import tally_barcodes
@@ -284,3 +284,35 @@ def test_single_index_c5(ctx, tmp_path):
         exp = O.match_single_index(key, idx["idx1"], idx["id"], 1)
         assert (rec["matched_idx1"], rec["read_type"], rec["sample_name"]) == \
                (exp["matched_idx1"], exp["read_type"], exp["sample_name"]), key
+
+
+@pytest.mark.parametrize("streams", [1, 4])
+def test_tally_c5_golden(ctx, golden, golden_dir, streams):
+    """BASELINE configs[4] shape against what the REFERENCE tallied (F:183-207): eight single-index files,
+    per-file dicts in file order and "total" in first-appearance order; also through the `-c N` path (N files
+    scanned at the same time on N contexts of this GPU)."""
+    from frender_b200.cli import ScanTables, scan_files_concurrent
+    from frender_b200.engine import tally_barcodes, unpack_keys
+    case = golden["tally"]["c5"]
+    files = [os.path.join(golden_dir, f"c5__{f}") for f in case["files"]]
+    if streams == 1:
+        got = tally_barcodes(1, files, ctx=ctx)
+        got = {k.split("__", 1)[-1]: list(v.items()) for k, v in got.items()}
+    else:
+        per_file, total = scan_files_concurrent(files, None, streams, 0, 16, ctx)
+        got = {"total": list(zip(unpack_keys(total[0]), total[1].tolist()))}
+        for i, f in enumerate(case["files"]):
+            got[f] = list(zip(unpack_keys(per_file[i][2]), per_file[i][3].tolist()))
+    assert list(got) == list(case["tally"])
+    assert {k: [list(x) for x in v] for k, v in got.items()} == case["tally"]
+
+
+def test_empty_sheet_is_all_undetermined(ctx):
+    """A sheet with no rows: get_indexes_of_approx_matches returns [] (F:220-234), so every key is undetermined
+    (F:280-284) whatever -n is."""
+    from frender_b200.engine import process
+    idx = {"id": [], "idx1": [], "idx2": []}
+    for n in (0, 1):
+        got = process(1, {"ACGTACGT+TTTTAAAA": 3, "NNNNNNNN+ACGTACGT": 1}, idx, n, False, ctx=ctx)
+        assert [v["read_type"] for v in got.values()] == ["undetermined", "undetermined"]
+        assert all(v["matched_idx1"] == "" and v["sample_name"] == "" for v in got.values())

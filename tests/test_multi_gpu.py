@@ -147,3 +147,28 @@ def test_cli_scan_file_sharding_two_gpus(tmp_path, monkeypatch):
     main(["scan", "-n", "1", "-rc", "-p", case["prefix"], "-o", "m", "-b", str(tmp_path / "SampleSheet.csv")] + files)
     out = [f for f in os.listdir(tmp_path) if f.startswith("frender-scan-results_")][0]
     assert (tmp_path / out).read_bytes() == unb64(case["scan_csv"])
+
+
+def _failing_worker(rank, n_ranks, device, ident, jobs, sample, table_log2, conn):
+    """Stands in for cli._scan_worker on a box without GPUs: rank 1 fails its scan, rank 0 succeeds and must not
+    be left waiting for a collective."""
+    try:
+        if rank == 1:
+            raise RuntimeError("bad header in file of rank 1")
+        conn.send(("scanned", None, None))
+        if not conn.recv():
+            return
+        conn.send(("ok", [], None))
+    except BaseException as exc:
+        conn.send(("error", repr(exc), None))
+    finally:
+        conn.close()
+
+
+def test_multi_gpu_worker_failure_ends_the_job(monkeypatch):
+    """A rank whose scan fails (any rank, not just rank 0) ends the whole job with its message; nobody enters the
+    collective (the workers wait for the parent's go)."""
+    import frender_b200.cli as cli
+    monkeypatch.setattr(cli.Context, "nccl_unique_id", staticmethod(lambda: b"\0" * 128))
+    with pytest.raises(SystemExit, match="GPU worker 1 failed: .*bad header"):
+        cli.scan_files_multi_gpu(["a", "b", "c"], None, 2, 12, worker=_failing_worker)

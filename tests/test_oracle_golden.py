@@ -55,7 +55,7 @@ def test_tally_edges(golden, tmp_path):
             assert [list(x) for x in got["total"].items()] == case["total"], name
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "multi", "sampled"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c2n0", "c3", "multi", "sampled", "c2_384"])
 def test_scan_stages(golden, golden_dir, name):
     case = golden["scan"][name]
     files = [os.path.join(golden_dir, f"{name}__{f}") for f in case["files"]]
@@ -102,7 +102,7 @@ def test_synth_matches_fixture(golden, golden_dir):
     assert [list(x) for x in tally.items()] == case["tally"]["total"]
 
 
-@pytest.mark.parametrize("name", ["c1", "c1_ia", "c1_short_r2"])
+@pytest.mark.parametrize("name", ["c1", "c1_ia", "c1_short_r2", "c4"])
 def test_demux_streams(golden, tmp_path, name):
     case = golden["demux"][name]
     scan = golden["scan"][case["scan_case"]]
@@ -129,3 +129,14 @@ def test_demux_streams(golden, tmp_path, name):
     for fname, want in case["sinks"].items():
         assert len(got[fname]) == want["bytes"], fname
         assert hashlib.sha256(got[fname]).hexdigest() == want["sha256"], fname
+
+
+def test_tally_c5_many_files(golden, golden_dir):
+    """BASELINE configs[4] shape: single 6 bp index, eight files; per-file dicts and "total" of F:183-207."""
+    case = golden["tally"]["c5"]
+    files = [os.path.join(golden_dir, f"c5__{f}") for f in case["files"]]
+    for cores in (1, 2):
+        counter = O.tally_barcodes(cores, files)
+        counter = {k.split("__", 1)[-1]: v for k, v in counter.items()}
+        assert list(counter) == list(case["tally"])
+        assert {k: [list(x) for x in v.items()] for k, v in counter.items()} == case["tally"]
