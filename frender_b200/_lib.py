@@ -15,8 +15,8 @@ ERR_CUDA, ERR_ARG, ERR_BAD_HEADER, ERR_BAD_ALPHABET, ERR_KEY_TOO_LONG = -1, -2, 
 ERR_TABLE_FULL, ERR_BAD_LENGTH, ERR_KEY_NOT_FOUND, ERR_NCCL, ERR_IO, ERR_STATE = -6, -7, -8, -9, -10, -11
 RULE_SCAN, RULE_DEMUX = 0, 1
 CARRY = 0xFFFFFFFFFFFFFFFF
-K_SCAN, K_EXPORT, K_MATCH, K_ROUTE, K_OTHER, K_VERIFY = range(6)
-K_NUM = 6
+K_SCAN, K_EXPORT, K_MATCH, K_ROUTE, K_OTHER, K_VERIFY, K_INFLATE = range(7)
+K_NUM = 7
 READ_TYPES = ("undetermined", "index_hop", "demuxable", "ambiguous")
 
 u64, u32, i32, u8 = C.c_uint64, C.c_uint32, C.c_int32, C.c_uint8
@@ -46,6 +46,7 @@ SIGNATURES = {
     "frb_scan_chunk_dev": (C.c_int, [vp, vp, u64, u64, C.c_int, vp, vp]),
     "frb_scan_end": (C.c_int, [vp, P(u64), P(u64)]),
     "frb_scan_gz": (C.c_int, [vp, C.c_char_p, u32, u64, P(u64), P(u64), P(u64)]),
+    "frb_gz_inflate": (C.c_int, [vp, C.c_char_p, vp, u64, P(u64), P(C.c_int)]),
     "frb_file_count": (C.c_int, [vp, P(u32)]),
     "frb_file_size": (C.c_int, [vp, u32, P(u64), P(u64)]),
     "frb_file_export": (C.c_int, [vp, u32, vp, vp, vp, u64]),

@@ -1,0 +1,286 @@
+// Host side of the device inflate (gz_kernels.cuh), included by frb_lib.cu.
+//
+// A .gz file is read in pieces of compressed bytes; every piece goes to the device as it is (a fifth of the
+// bytes a host-inflated file would send), is inflated there by thousands of warps at once and handed on where
+// it lies -- the scan kernel reads it from HBM.  Anything the device path does not take (a block start that
+// turned out false, blocks larger than the chunk stride, '\r' in the text, staging overflow) makes
+// gz_device_inflate return FRB_GZ_RETRY_HOST and the caller inflates that file with zlib as before.
+namespace {
+
+constexpr int FRB_GZ_RETRY_HOST = 1000;   // internal status: use the host (zlib) path for this file
+constexpr int FRB_GZ_RETRY_SPACE = 1001;  // internal status: a chunk's staging area was too small
+
+struct GzBuffers {
+    unsigned char* comp = nullptr;        // piece of the compressed file (+ overlap, padded to words)
+    unsigned char* host = nullptr;        // pinned twin
+    size_t comp_cap = 0;
+    unsigned short* stage = nullptr;      // 16-bit symbols, one area per chunk
+    size_t stage_syms = 0;
+    gz::Chunk* chunks = nullptr;
+    gz::Chunk* chunks_host = nullptr;     // pinned (first / last entries only are looked at)
+    size_t chunk_cap = 0;
+    unsigned char* windows = nullptr;     // 32 KiB in front of every chunk
+    unsigned short* maps = nullptr;       // per chunk: window in front of its group -> window behind it
+    unsigned char* group_win = nullptr;   // 32 KiB in front of every group of chunks
+    int* prev_found = nullptr;
+    unsigned char* win[2] = {nullptr, nullptr};  // 32 KiB in front of / behind the piece
+    unsigned char* out[2] = {nullptr, nullptr};  // inflated text, two pieces in flight (carry area in front)
+    size_t out_cap = 0;
+    unsigned long long* scalars = nullptr;       // device: total symbols, last newline end; [2] as unsigned: bad, cr, fail
+    unsigned long long* scalars_host = nullptr;  // pinned
+};
+
+struct GzConfig {
+    size_t piece = 128u << 20;   // compressed bytes per piece
+    size_t stride = 32u << 10;   // compressed bytes per chunk (one warp)
+    size_t expand = 12;          // staging symbols per compressed byte
+    size_t carry = 4u << 20;     // room for an unfinished line in front of a piece's text
+};
+
+GzConfig gz_config() {
+    GzConfig g;
+    if (const char* e = getenv("FRB_GZ_PIECE_MB")) g.piece = static_cast<size_t>(atoi(e)) << 20;
+    if (const char* e = getenv("FRB_GZ_STRIDE_KB")) g.stride = static_cast<size_t>(atoi(e)) << 10;
+    if (const char* e = getenv("FRB_GZ_EXPAND")) g.expand = static_cast<size_t>(atoi(e));
+    return g;
+}
+
+void gz_free(GzBuffers& b) {
+    cudaFree(b.comp), cudaFreeHost(b.host), cudaFree(b.stage), cudaFree(b.chunks), cudaFreeHost(b.chunks_host);
+    cudaFree(b.maps), cudaFree(b.group_win), cudaFree(b.prev_found);
+    cudaFree(b.windows), cudaFree(b.win[0]), cudaFree(b.win[1]), cudaFree(b.out[0]), cudaFree(b.out[1]);
+    cudaFree(b.scalars), cudaFreeHost(b.scalars_host);
+    b = GzBuffers{};
+}
+
+int gz_ensure(frb_ctx* c, GzBuffers& b, const GzConfig& g, size_t piece_bytes) {
+    const size_t comp_cap = piece_bytes + 2 * g.stride + 64;
+    const size_t n_chunks = (piece_bytes + g.stride - 1) / g.stride + 1;
+    const size_t stage_syms = std::max<size_t>((n_chunks - 1) * g.stride * g.expand, 32u << 20);  // >= 64 MB of symbols
+    const size_t out_cap = g.carry + stage_syms + 64;
+    if (comp_cap <= b.comp_cap && n_chunks <= b.chunk_cap && stage_syms <= b.stage_syms && out_cap <= b.out_cap) return FRB_OK;
+    CU(c, cudaStreamSynchronize(c->compute));
+    gz_free(b);
+    CU(c, cudaMalloc(&b.comp, comp_cap));
+    CU(c, cudaMallocHost(&b.host, comp_cap));
+    CU(c, cudaMalloc(&b.stage, stage_syms * 2));
+    CU(c, cudaMalloc(&b.chunks, n_chunks * sizeof(gz::Chunk)));
+    CU(c, cudaMallocHost(&b.chunks_host, n_chunks * sizeof(gz::Chunk)));
+    CU(c, cudaMalloc(&b.windows, n_chunks * gz::kWindow));
+    CU(c, cudaMalloc(&b.maps, n_chunks * gz::kWindow * 2));
+    CU(c, cudaMalloc(&b.group_win, (n_chunks / gz::kGroup + 1) * gz::kWindow));
+    CU(c, cudaMalloc(&b.prev_found, n_chunks * sizeof(int)));
+    for (int i = 0; i < 2; ++i) {
+        CU(c, cudaMalloc(&b.win[i], gz::kWindow));
+        CU(c, cudaMalloc(&b.out[i], out_cap));
+    }
+    CU(c, cudaMalloc(&b.scalars, 64));
+    CU(c, cudaMallocHost(&b.scalars_host, 64));
+    b.comp_cap = comp_cap, b.chunk_cap = n_chunks, b.stage_syms = stage_syms, b.out_cap = out_cap;
+    CU(c, cudaFuncSetAttribute(gz::gz_tailmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * gz::kWindow));
+    CU(c, cudaFuncSetAttribute(gz::gz_groupwin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * gz::kWindow));
+    return FRB_OK;
+}
+
+// FRB_GZ_TIMING=1: device time of every step of a piece on stderr
+struct GzTimer {
+    frb_ctx* c;
+    bool on;
+    cudaEvent_t ev[8];
+    explicit GzTimer(frb_ctx* ctx) : c(ctx), on(getenv("FRB_GZ_TIMING") != nullptr) {
+        if (on)
+            for (auto& e : ev) cudaEventCreate(&e);
+    }
+    ~GzTimer() {
+        if (on)
+            for (auto& e : ev) cudaEventDestroy(e);
+    }
+    void mark(int k) {
+        if (on) cudaEventRecord(ev[k], c->compute);
+    }
+    void report(int piece, size_t n_in, uint64_t n_sym, unsigned n_chunks) {
+        if (!on) return;
+        float t[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 7; ++k)
+            if (k != 5) cudaEventElapsedTime(&t[k], ev[k], ev[k + 1]);
+        fprintf(stderr, "gz piece %d: %zu -> %llu bytes, %u chunks: find %.2f link %.2f decode %.2f offsets %.2f window %.2f "
+                        "resolve %.2f ms\n", piece, n_in, (unsigned long long)n_sym, n_chunks, t[0], t[1], t[2], t[3], t[4], t[6]);
+    }
+};
+
+// gzip member header in host memory (RFC 1952): bytes of the header, 0 = not gzip / incomplete
+size_t gz_host_header(const unsigned char* d, size_t n) {
+    if (n < 10 || d[0] != 0x1f || d[1] != 0x8b || d[2] != 8 || (d[3] & 0xE0)) return 0;
+    const unsigned flg = d[3];
+    size_t pos = 10;
+    if (flg & 4) {
+        if (pos + 2 > n) return 0;
+        pos += 2 + (d[pos] | (d[pos + 1] << 8));
+    }
+    for (int k = 0; k < 2; ++k)
+        if (flg & (8 << k)) {
+            while (pos < n && d[pos]) ++pos;
+            ++pos;
+        }
+    if (flg & 2) pos += 2;
+    return pos <= n ? pos : 0;
+}
+
+// Inflate `path` on the device piece by piece; every piece of text (cut behind its last complete line, the rest
+// carried into the next piece; the last piece whole) goes to `sink(dev_ptr, nbytes, last)`, 16-byte aligned,
+// valid until the sink of the piece after next is called.  FRB_GZ_RETRY_HOST: nothing usable happened (the
+// sink may already have been called -- the caller starts the file over).
+template <typename Sink>
+int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const char* path, uint64_t* raw_bytes, Sink&& sink) {
+    FILE* fh = fopen(path, "rb");
+    if (!fh) return fail(c, FRB_ERR_IO, "cannot open %s", path);
+    struct Closer {
+        FILE* f;
+        ~Closer() { fclose(f); }
+    } closer{fh};
+    fseek(fh, 0, SEEK_END);
+    const uint64_t file_bytes = static_cast<uint64_t>(ftell(fh));
+    fseek(fh, 0, SEEK_SET);
+    if (file_bytes < 18) return FRB_GZ_RETRY_HOST;  // smaller than an empty member: let zlib say what it is
+    const size_t piece = std::min<uint64_t>(g.piece, (file_bytes + 3) & ~3ull);
+    TRY(gz_ensure(c, b, g, piece));
+    unsigned char head[1024];
+    const size_t got_head = fread(head, 1, sizeof head, fh);
+    const size_t hdr = gz_host_header(head, got_head);
+    if (!hdr) return FRB_GZ_RETRY_HOST;
+
+    uint64_t file_pos = 0;                 // file offset of the piece buffer's first byte (multiple of 4)
+    uint64_t start_bit_abs = hdr * 8ull;   // where the next piece's first chunk starts (absolute bit in the file)
+    bool member_start = true;
+    size_t carry_len = 0;                  // bytes of an unfinished line in front of the next piece's text
+    int ob = 0;                            // output buffer in use
+    uint64_t total_out = 0;
+    CU(c, cudaMemsetAsync(b.win[0], 0, gz::kWindow, c->compute));
+    for (int piece_no = 0;; ++piece_no) {
+        // ---- compressed bytes of the piece (+ overlap) -----------------------------------------------------
+        const uint64_t want_end = std::min<uint64_t>(file_pos + piece + 2 * g.stride, file_bytes);
+        const size_t n_in = static_cast<size_t>(want_end - file_pos);
+        fseek(fh, static_cast<long>(file_pos), SEEK_SET);
+        if (fread(b.host, 1, n_in, fh) != n_in) return fail(c, FRB_ERR_IO, "%s: read error", path);
+        memset(b.host + n_in, 0, 64);
+        const bool last_piece = file_pos + piece >= file_bytes;
+        CU(c, cudaMemcpyAsync(b.comp, b.host, n_in + 64, cudaMemcpyHostToDevice, c->compute));
+        const size_t body = last_piece ? n_in : piece;
+        const unsigned n_chunks = static_cast<unsigned>((body + g.stride - 1) / g.stride);
+        const uint64_t rel_start = start_bit_abs - file_pos * 8;
+        const unsigned first_chunk = static_cast<unsigned>((rel_start >> 3) / g.stride);  // chunk holding the start
+        if (first_chunk >= n_chunks) return FRB_GZ_RETRY_HOST;
+        // ---- chunk table --------------------------------------------------------------------------------
+        CU(c, cudaMemsetAsync(b.chunks, 0, (n_chunks + 1) * sizeof(gz::Chunk), c->compute));
+        gz::Chunk first{};
+        first.start_bit = rel_start, first.found = 1, first.member_start = member_start ? 1u : 0u;
+        b.chunks_host[0] = first;
+        CU(c, cudaMemcpyAsync(b.chunks + first_chunk, b.chunks_host, sizeof(gz::Chunk), cudaMemcpyHostToDevice, c->compute));
+        CU(c, cudaMemsetAsync(b.scalars, 0, 64, c->compute));
+        unsigned* const flags = reinterpret_cast<unsigned*>(b.scalars + 2);  // bad, cr, fail
+        const unsigned search_from = first_chunk + 1, search_to = n_chunks + (last_piece ? 0u : 1u);
+        GzTimer tm(c);
+        {
+            ProfScope ps(c, FRB_K_INFLATE);
+            tm.mark(0);
+            if (search_to > search_from)
+                gz::gz_find_kernel<<<search_to - search_from, gz::kFindThreads, 0, c->compute>>>(
+                    b.comp, n_in, b.chunks, search_to, g.stride, 0, search_from);
+            tm.mark(1);
+            // every chunk of this piece an equal share of the staging area
+            gz::gz_link_kernel<<<1, 32, 0, c->compute>>>(b.chunks, n_chunks, b.stage_syms / n_chunks / 16 * 16,
+                                                         last_piece ? 0 : 1, flags + 2);
+            tm.mark(2);
+            gz::gz_decode_kernel<<<(n_chunks + gz::kDecodeWarps - 1) / gz::kDecodeWarps, gz::kDecodeWarps * 32, 0, c->compute>>>(
+                b.comp, n_in, b.chunks, n_chunks, b.stage);
+            tm.mark(3);
+            gz::gz_offsets_kernel<<<1, 1024, 0, c->compute>>>(b.chunks, n_chunks, b.scalars, flags);
+            tm.mark(4);
+            gz::gz_tailmap_kernel<<<(n_chunks + gz::kGroup - 1) / gz::kGroup, 1024, 4 * gz::kWindow, c->compute>>>(
+                b.chunks, n_chunks, b.stage, b.maps, b.prev_found);
+            gz::gz_groupwin_kernel<<<1, 1024, 2 * gz::kWindow, c->compute>>>(b.chunks, n_chunks, b.maps, b.win[piece_no & 1],
+                                                                            b.group_win, b.win[(piece_no + 1) & 1]);
+            gz::gz_windows_kernel<<<n_chunks, 256, 0, c->compute>>>(b.chunks, b.maps, b.prev_found, b.group_win, b.windows);
+            tm.mark(5);
+            c->launches += 7;
+        }
+        CU(c, cudaMemcpyAsync(b.scalars_host, b.scalars, 64, cudaMemcpyDeviceToHost, c->compute));
+        CU(c, cudaMemcpyAsync(b.chunks_host + 1, b.chunks + n_chunks, sizeof(gz::Chunk), cudaMemcpyDeviceToHost, c->compute));
+        CU(c, cudaStreamSynchronize(c->compute));
+        const unsigned* hflags = reinterpret_cast<const unsigned*>(b.scalars_host + 2);
+        const uint64_t n_sym = b.scalars_host[0];
+        if (hflags[0] != 0xFFFFFFFFu) {  // a chunk failed: which way?
+            gz::Chunk bad;
+            CU(c, cudaMemcpy(&bad, b.chunks + hflags[0], sizeof bad, cudaMemcpyDeviceToHost));
+            if (getenv("FRB_GZ_VERBOSE"))
+                fprintf(stderr, "gz: piece %d chunk %u of %u: status %d, start %llu stop %llu end %llu, %u symbols (cap %u)\n",
+                        piece_no, hflags[0], n_chunks, bad.status, bad.start_bit, bad.stop_bit, bad.end_bit, bad.n_out,
+                        bad.stage_cap);
+            // corrupt or truncated data in the piece the stream really ends in is an error of the file, not of the
+            // chunking (every earlier chunk met its successor exactly)
+            if (bad.status == gz::GZ_ERR_TRUNC && last_piece) return fail(c, FRB_ERR_IO, "%s: unexpected end of file", path);
+            return bad.status == gz::GZ_ERR_SPACE ? FRB_GZ_RETRY_SPACE : FRB_GZ_RETRY_HOST;
+        }
+        if (hflags[2]) return FRB_GZ_RETRY_HOST;  // no block start found behind the piece
+        if (carry_len + n_sym + 64 > b.out_cap) return FRB_GZ_RETRY_HOST;
+        // ---- symbols -> text behind the carried line ---------------------------------------------------------
+        unsigned char* const text = b.out[ob] + carry_len;
+        {
+            ProfScope ps(c, FRB_K_INFLATE);
+            const unsigned per_chunk_blocks = static_cast<unsigned>(std::max<size_t>(1, g.stride * 4 / 4096));
+            tm.mark(6);
+            gz::gz_resolve_kernel<<<dim3(per_chunk_blocks, n_chunks), 256, 0, c->compute>>>(b.chunks, b.stage, b.windows, text,
+                                                                                         n_sym);
+            tm.mark(7);
+            gz::gz_text_kernel<<<c->sm_count * 2, 1024, 0, c->compute>>>(text, n_sym, b.scalars + 1, flags + 1);
+            c->launches += 2;
+        }
+        CU(c, cudaMemcpyAsync(b.scalars_host, b.scalars, 64, cudaMemcpyDeviceToHost, c->compute));
+        CU(c, cudaStreamSynchronize(c->compute));
+        tm.report(piece_no, n_in, n_sym, n_chunks);
+        if (hflags[1]) return FRB_GZ_RETRY_HOST;  // '\r' in the text: universal newlines are the host path's job
+        total_out += n_sym;
+        const uint64_t have = carry_len + n_sym;
+        uint64_t usable = have;
+        if (!last_piece) {
+            const uint64_t nl = b.scalars_host[1];  // end of the last complete line inside the new text
+            if (nl == 0) {
+                if (have > g.carry) return FRB_GZ_RETRY_HOST;  // a line longer than the carry area
+                usable = 0;
+            } else {
+                usable = carry_len + nl;
+            }
+        }
+        if (usable || last_piece) TRY(sink(b.out[ob], usable, last_piece));
+        if (last_piece) break;
+        // ---- next piece ---------------------------------------------------------------------------------
+        const size_t tail = static_cast<size_t>(have - usable);
+        if (tail > g.carry) return FRB_GZ_RETRY_HOST;
+        if (tail) CU(c, cudaMemcpyAsync(b.out[ob ^ 1], b.out[ob] + usable, tail, cudaMemcpyDeviceToDevice, c->compute));
+        carry_len = tail;
+        ob ^= 1;
+        start_bit_abs = file_pos * 8 + b.chunks_host[1].start_bit;
+        file_pos = (start_bit_abs >> 3) & ~3ull;
+        member_start = false;
+    }
+    if (raw_bytes) *raw_bytes = total_out;
+    return FRB_OK;
+}
+
+// A stream that expands more than the staging areas allow (long runs) is tried again with larger ones while the
+// memory for them is there; the sink must be able to start over (`restart()` is called before every new attempt).
+template <typename Sink, typename Restart>
+int gz_device_inflate(frb_ctx* c, GzBuffers& b, const char* path, uint64_t* raw_bytes, Sink&& sink, Restart&& restart) {
+    GzConfig g = gz_config();
+    for (;;) {
+        const int rc = gz_device_inflate_once(c, b, g, path, raw_bytes, sink);
+        if (rc != FRB_GZ_RETRY_SPACE) return rc;
+        g.expand *= 8;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (g.expand > 1100 || g.piece * g.expand * 3 > free_b + b.stage_syms * 2) return FRB_GZ_RETRY_HOST;
+        TRY(restart());
+    }
+}
+
+}  // namespace

@@ -20,6 +20,7 @@
 #include <zlib.h>
 
 #include "common.cuh"
+#include "gz_kernels.cuh"
 #include "match_kernel.cuh"
 #include "route_kernel.cuh"
 #include "scan_common.cuh"
@@ -111,6 +112,8 @@ struct frb_ctx {
     uint64_t route_cap = 0;
     uint32_t n_sinks = 0;
     RouteBufs rb;
+    // device inflate (frb_gz.inl)
+    struct GzBuffersHolder* gzbuf = nullptr;
     // synth
     SynthArgs synth{};
     unsigned *synth_i7 = nullptr, *synth_i5 = nullptr;
@@ -129,6 +132,7 @@ struct frb_ctx {
     double prof_ms[FRB_K_NUM] = {0};
     uint64_t prof_n[FRB_K_NUM] = {0};
     uint64_t launches = 0;
+    uint64_t gz_device_files = 0;  // files inflated on the device
     std::string err;
 };
 
@@ -496,6 +500,11 @@ int ensure_stages(frb_ctx* c) {
 
 }  // namespace
 
+#include "frb_gz.inl"
+struct GzBuffersHolder {
+    GzBuffers b;
+};
+
 // ============================================================================================
 extern "C" {
 
@@ -574,6 +583,10 @@ void frb_destroy(frb_ctx* c) {
     cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
     cudaFree(c->type), cudaFree(c->typerc), cudaFree(c->work), cudaFree(c->work_n), cudaFree(c->cub_tmp), cudaFree(c->route_tab);
     route_free(c->rb);
+    if (c->gzbuf) {
+        gz_free(c->gzbuf->b);
+        delete c->gzbuf;
+    }
     cudaFree(c->synth_i7), cudaFree(c->synth_i5), cudaFree(c->synth_cdf), cudaFree(c->synth_len), cudaFree(c->synth_off);
     for (auto& p : c->prof_pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     for (auto& p : c->prof_free) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
@@ -923,8 +936,8 @@ size_t normalize_cr(unsigned char* buf, size_t n, bool* pending, bool at_eof) {
 }
 }  // namespace
 
-int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t read_limit, uint64_t* n_reads,
-                uint64_t* n_unique, uint64_t* raw_bytes) {
+static int scan_gz_host(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t read_limit, uint64_t* n_reads,
+                        uint64_t* n_unique, uint64_t* raw_bytes) {
     CU(c, cudaSetDevice(c->device));
     TRY(ensure_stages(c));
     for (int i = 0; i < kHostStages; ++i)
@@ -932,6 +945,10 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
     gzFile gz = gzopen(path, "rb");
     if (!gz) return fail(c, FRB_ERR_IO, "cannot open %s", path);
     gzbuffer(gz, 1 << 20);
+    if (gzdirect(gz)) {  // zlib would pass such a file through as it is; gzip.open raises BadGzipFile (F:159)
+        gzclose(gz);
+        return fail(c, FRB_ERR_IO, "%s: not a gzipped file", path);
+    }
     TRY(frb_scan_begin(c, file_ordinal, read_limit));
 
     struct Item {
@@ -962,11 +979,13 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
             size_t have = tail.size();
             if (have) memcpy(buf, tail.data(), have);
             tail.clear();
-            if (cr_pending) buf[have++] = '\r', cr_pending = false;
             bool eof = false;
             while (have < c->stage_cap) {
-                const unsigned want = static_cast<unsigned>(std::min<size_t>(c->stage_cap - have, 1u << 30));
-                const int got = gzread(gz, buf + have, want);
+                // a '\r' held back at the end of the last piece: it is a line end of its own unless this piece
+                // begins with '\n' ("\r\n" split across two reads); one byte of room is kept for it
+                const unsigned want = static_cast<unsigned>(std::min<size_t>(c->stage_cap - have - (cr_pending ? 1 : 0), 1u << 30));
+                if (want == 0) break;
+                const int got = gzread(gz, buf + have + (cr_pending ? 1 : 0), want);
                 if (got < 0) {
                     int errnum = 0;
                     io_err = gzerror(gz, &errnum);
@@ -977,12 +996,20 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
                     eof = true;
                     break;
                 }
-                if (memchr(buf + have, '\r', got)) {
+                unsigned char* piece = buf + have + (cr_pending ? 1 : 0);
+                size_t n_piece = static_cast<size_t>(got);
+                if (cr_pending) {  // emit the line end; a leading '\n' of this piece belongs to it
+                    buf[have++] = '\n';
+                    cr_pending = false;
+                    if (piece[0] == '\n') ++piece, --n_piece;
+                    if (piece != buf + have) memmove(buf + have, piece, n_piece);
+                    piece = buf + have;
+                }
+                if (memchr(piece, '\r', n_piece)) {
                     // rare path: translate this piece (a trailing '\r' waits for its successor)
-                    size_t m = normalize_cr(buf + have, got, &cr_pending, false);
-                    have += m;
+                    have += normalize_cr(piece, n_piece, &cr_pending, false);
                 } else {
-                    have += got;
+                    have += n_piece;
                 }
             }
             if (eof && cr_pending) buf[have++] = '\n', cr_pending = false;
@@ -1039,7 +1066,15 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
     }
     cv.notify_all();
     reader.join();
-    gzclose(gz);
+    {   // a stream cut short only shows here: gzread() returns 0 at the end of the bytes there are, zlib reports
+        // Z_BUF_ERROR through gzerror / gzclose (gzip.open raises EOFError for such a file, F:159)
+        int errnum = 0;
+        const char* msg = gzerror(gz, &errnum);
+        if (io_err.empty() && errnum != Z_OK && errnum != Z_STREAM_END && !(read_limit && errnum == Z_BUF_ERROR && stop))
+            io_err = msg ? msg : "gzip error";
+        const int closed = gzclose(gz);
+        if (io_err.empty() && closed != Z_OK && !read_limit) io_err = closed == Z_BUF_ERROR ? "unexpected end of file" : "gzip error";
+    }
     if (rc == FRB_OK && !io_err.empty()) rc = fail(c, FRB_ERR_IO, "%s: %s", path, io_err.c_str());
     if (rc != FRB_OK) {
         c->in_file = false;
@@ -1048,6 +1083,69 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
     }
     if (raw_bytes) *raw_bytes = total_raw;
     return frb_scan_end(c, n_reads, n_unique);
+}
+
+// Whole .gz file: inflated on the device when the stream allows it (frb_gz.inl), else by zlib on a host thread.
+int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t read_limit, uint64_t* n_reads,
+                uint64_t* n_unique, uint64_t* raw_bytes) {
+    CU(c, cudaSetDevice(c->device));
+    static const bool device_ok = !(getenv("FRB_GZ_DEVICE") && atoi(getenv("FRB_GZ_DEVICE")) == 0);
+    if (device_ok && !read_limit) {  // -s reads a head sample only: the host path stops early
+        if (!c->gzbuf) c->gzbuf = new GzBuffersHolder();
+        TRY(frb_scan_begin(c, file_ordinal, 0));
+        bool first = true;
+        uint64_t raw = 0;
+        const int rc = gz_device_inflate(
+            c, c->gzbuf->b, path, &raw,
+            [&](unsigned char* dev, uint64_t n, bool) {
+                const int r = launch_scan(c, dev, n, first ? 0 : FRB_CARRY, FRB_RULE_SCAN, nullptr, nullptr, c->file_tab, 0);
+                first = false;
+                return r;
+            },
+            [&]() {  // start the file over (larger staging areas)
+                c->in_file = false;
+                first = true;
+                CU(c, cudaStreamSynchronize(c->compute));
+                CU(c, cudaMemsetAsync(&c->st->err_code, 0, sizeof(int), c->compute));
+                return frb_scan_begin(c, file_ordinal, 0);
+            });
+        if (rc == FRB_OK) {
+            c->gz_device_files++;
+            if (raw_bytes) *raw_bytes = raw;
+            return frb_scan_end(c, n_reads, n_unique);
+        }
+        c->in_file = false;
+        CU(c, cudaStreamSynchronize(c->compute));
+        if (rc != FRB_GZ_RETRY_HOST) return rc;
+        CU(c, cudaMemsetAsync(&c->st->err_code, 0, sizeof(int), c->compute));  // errors of the abandoned attempt
+    }
+    return scan_gz_host(c, path, file_ordinal, read_limit, n_reads, n_unique, raw_bytes);
+}
+
+// Test / tooling entry: inflate a .gz on the device into host memory.  *used_device = 0 when the device path
+// declined the stream (nothing is written then).
+int frb_gz_inflate(frb_ctx* c, const char* path, void* host_out, uint64_t cap, uint64_t* nbytes, int* used_device) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->gzbuf) c->gzbuf = new GzBuffersHolder();
+    uint64_t off = 0, raw = 0;
+    *nbytes = 0, *used_device = 0;
+    const int rc = gz_device_inflate(
+        c, c->gzbuf->b, path, &raw,
+        [&](unsigned char* dev, uint64_t n, bool) {
+            if (off + n > cap) return fail(c, FRB_ERR_ARG, "frb_gz_inflate: output buffer too small");
+            CU(c, cudaMemcpyAsync(static_cast<unsigned char*>(host_out) + off, dev, n, cudaMemcpyDeviceToHost, c->compute));
+            CU(c, cudaStreamSynchronize(c->compute));
+            off += n;
+            return FRB_OK;
+        },
+        [&]() {
+            off = 0;
+            return FRB_OK;
+        });
+    if (rc == FRB_GZ_RETRY_HOST) return FRB_OK;
+    if (rc != FRB_OK) return rc;
+    *nbytes = off, *used_device = 1;
+    return FRB_OK;
 }
 
 // ---- hot path B -----------------------------------------------------------------------------

@@ -137,6 +137,14 @@ class Context:
         self.file_names.append(os.path.basename(str(path)))
         return reads.value, uniq.value, raw.value
 
+    def gz_inflate(self, path, cap):
+        """A .gz file inflated on the device (tests, tools).  Returns the bytes, or None when the device path
+        declined the stream (frb_scan_gz then inflates it with zlib on a host thread)."""
+        out = np.empty(max(cap, 1), np.uint8)
+        n, used = C.c_uint64(), C.c_int()
+        self._ck(lib.frb_gz_inflate(self._h, os.fsencode(str(path)), _ptr(out), cap, C.byref(n), C.byref(used)))
+        return out[:n.value].tobytes() if used.value else None
+
     def scan_bytes(self, data, ordinal=0, sample=None, rule=_lib.RULE_SCAN, name=None, chunk=None):
         """Decompressed FASTQ bytes from host memory, optionally fed in `chunk`-sized pieces cut
         at line ends.  Returns (reads, unique keys)."""

@@ -112,6 +112,10 @@ int frb_scan_end(frb_ctx* ctx, uint64_t* n_reads, uint64_t* n_unique);
  * double buffers, H2D overlapped with the kernels): begin + chunks + end. Replaces F:159-177. */
 int frb_scan_gz(frb_ctx* ctx, const char* path, uint32_t file_ordinal, uint64_t read_limit,
                 uint64_t* n_reads, uint64_t* n_unique, uint64_t* raw_bytes);
+/* A .gz file inflated on the device into host memory (tests, tools).  *used_device = 0: the device path declined
+ * the stream (blocks larger than a chunk, '\r' in the text, ...) and nothing was written; frb_scan_gz falls back
+ * to zlib on a host thread for such a file.                                                                */
+int frb_gz_inflate(frb_ctx* ctx, const char* path, void* host_out, uint64_t cap, uint64_t* nbytes, int* used_device);
 /* Per-file results (index = order of frb_scan_end calls) and the merged "total".            */
 int frb_file_count(frb_ctx* ctx, uint32_t* n_files);
 int frb_file_size(frb_ctx* ctx, uint32_t file_idx, uint64_t* n_unique, uint64_t* n_reads);
@@ -197,7 +201,8 @@ int frb_synth_generate(frb_ctx* ctx, uint64_t g0, uint64_t g1, int read_no, void
 #define FRB_K_ROUTE 3  /* demux route + partition      */
 #define FRB_K_OTHER 4
 #define FRB_K_VERIFY 5 /* line phase of every tile by count (check of the speculative scan) */
-#define FRB_K_NUM 6
+#define FRB_K_INFLATE 6 /* device-side gzip inflate */
+#define FRB_K_NUM 7
 int frb_timer_start(frb_ctx* ctx);            /* CUDA event on the compute stream              */
 int frb_timer_stop(frb_ctx* ctx, float* ms);  /* second event, synchronises, elapsed ms        */
 int frb_prof_enable(frb_ctx* ctx, int on);    /* per-kernel-class event pairs                  */
