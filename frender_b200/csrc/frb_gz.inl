@@ -11,8 +11,9 @@ constexpr int FRB_GZ_RETRY_HOST = 1000;   // internal status: use the host (zlib
 constexpr int FRB_GZ_RETRY_SPACE = 1001;  // internal status: a chunk's staging area was too small
 
 struct GzBuffers {
-    unsigned char* comp = nullptr;        // piece of the compressed file (+ overlap, padded to words)
-    unsigned char* host = nullptr;        // pinned twin
+    unsigned char* comp[2] = {nullptr, nullptr};  // pieces of the compressed file (+ overlap, padded to words)
+    unsigned char* host[2] = {nullptr, nullptr};  // pinned twins: a reader thread fills one while the other is in use
+    cudaEvent_t copied[2] = {nullptr, nullptr};   // H2D of the piece done
     size_t comp_cap = 0;
     unsigned short* stage = nullptr;      // 16-bit symbols, one area per chunk
     size_t stage_syms = 0;
@@ -46,7 +47,11 @@ GzConfig gz_config() {
 }
 
 void gz_free(GzBuffers& b) {
-    cudaFree(b.comp), cudaFreeHost(b.host), cudaFree(b.stage), cudaFree(b.chunks), cudaFreeHost(b.chunks_host);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(b.comp[i]), cudaFreeHost(b.host[i]);
+        if (b.copied[i]) cudaEventDestroy(b.copied[i]);
+    }
+    cudaFree(b.stage), cudaFree(b.chunks), cudaFreeHost(b.chunks_host);
     cudaFree(b.maps), cudaFree(b.group_win), cudaFree(b.prev_found);
     cudaFree(b.windows), cudaFree(b.win[0]), cudaFree(b.win[1]), cudaFree(b.out[0]), cudaFree(b.out[1]);
     cudaFree(b.scalars), cudaFreeHost(b.scalars_host);
@@ -54,15 +59,18 @@ void gz_free(GzBuffers& b) {
 }
 
 int gz_ensure(frb_ctx* c, GzBuffers& b, const GzConfig& g, size_t piece_bytes) {
-    const size_t comp_cap = piece_bytes + 2 * g.stride + 64;
+    const size_t comp_cap = piece_bytes + 3 * g.stride + 64;
     const size_t n_chunks = (piece_bytes + g.stride - 1) / g.stride + 1;
     const size_t stage_syms = std::max<size_t>((n_chunks - 1) * g.stride * g.expand, 32u << 20);  // >= 64 MB of symbols
     const size_t out_cap = g.carry + stage_syms + 64;
     if (comp_cap <= b.comp_cap && n_chunks <= b.chunk_cap && stage_syms <= b.stage_syms && out_cap <= b.out_cap) return FRB_OK;
     CU(c, cudaStreamSynchronize(c->compute));
     gz_free(b);
-    CU(c, cudaMalloc(&b.comp, comp_cap));
-    CU(c, cudaMallocHost(&b.host, comp_cap));
+    for (int i = 0; i < 2; ++i) {
+        CU(c, cudaMalloc(&b.comp[i], comp_cap));
+        CU(c, cudaMallocHost(&b.host[i], comp_cap));
+        CU(c, cudaEventCreateWithFlags(&b.copied[i], cudaEventDisableTiming));
+    }
     CU(c, cudaMalloc(&b.stage, stage_syms * 2));
     CU(c, cudaMalloc(&b.chunks, n_chunks * sizeof(gz::Chunk)));
     CU(c, cudaMallocHost(&b.chunks_host, n_chunks * sizeof(gz::Chunk)));
@@ -142,14 +150,71 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
     const uint64_t file_bytes = static_cast<uint64_t>(ftell(fh));
     fseek(fh, 0, SEEK_SET);
     if (file_bytes < 18) return FRB_GZ_RETRY_HOST;  // smaller than an empty member: let zlib say what it is
+    // Pieces begin at fixed file offsets k * piece (so that they can be read ahead); the last one takes up to a
+    // piece and a half rather than leaving a small rest for a launch of its own.
     const size_t piece = std::min<uint64_t>(g.piece, (file_bytes + 3) & ~3ull);
-    TRY(gz_ensure(c, b, g, piece));
+    std::vector<std::pair<uint64_t, uint64_t>> plan;  // (file offset, nominal bytes)
+    for (uint64_t off = 0; off < file_bytes;) {
+        const uint64_t left = file_bytes - off;
+        const uint64_t take = left <= piece + piece / 2 ? left : piece;
+        plan.emplace_back(off, take);
+        off += take;
+    }
+    TRY(gz_ensure(c, b, g, plan.size() > 1 ? piece + piece / 2 : piece));
     unsigned char head[1024];
     const size_t got_head = fread(head, 1, sizeof head, fh);
     const size_t hdr = gz_host_header(head, got_head);
     if (!hdr) return FRB_GZ_RETRY_HOST;
 
-    uint64_t file_pos = 0;                 // file offset of the piece buffer's first byte (multiple of 4)
+    // ---- reader thread: piece k of the file into pinned buffer k & 1, then to the device on the copy stream ---
+    std::mutex mu;
+    std::condition_variable cv;
+    int filled = 0;        // pieces read and queued for copying
+    int released = 0;      // pieces whose buffers the consumer is done with
+    bool quit = false;
+    std::string io_err;
+    std::thread reader([&] {
+        cudaSetDevice(c->device);
+        for (size_t k = 0; k < plan.size(); ++k) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || static_cast<int>(k) < released + 2; });
+                if (quit) return;
+            }
+            const uint64_t off = plan[k].first;
+            const uint64_t end = std::min<uint64_t>(off + plan[k].second + 3 * g.stride, file_bytes);
+            const size_t n = static_cast<size_t>(end - off);
+            unsigned char* const hb = b.host[k & 1];
+            bool ok = fseek(fh, static_cast<long>(off), SEEK_SET) == 0 && fread(hb, 1, n, fh) == n;
+            memset(hb + n, 0, 64);
+            if (ok) {
+                ok = cudaMemcpyAsync(b.comp[k & 1], hb, n + 64, cudaMemcpyHostToDevice, c->copy) == cudaSuccess &&
+                     cudaEventRecord(b.copied[k & 1], c->copy) == cudaSuccess;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!ok) io_err = "read error";
+                ++filled;
+            }
+            cv.notify_all();
+            if (!ok) return;
+        }
+    });
+    struct Joiner {
+        std::thread& t;
+        std::mutex& mu;
+        std::condition_variable& cv;
+        bool& quit;
+        ~Joiner() {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                quit = true;
+            }
+            cv.notify_all();
+            t.join();
+        }
+    } joiner{reader, mu, cv, quit};
+
     uint64_t start_bit_abs = hdr * 8ull;   // where the next piece's first chunk starts (absolute bit in the file)
     bool member_start = true;
     size_t carry_len = 0;                  // bytes of an unfinished line in front of the next piece's text
@@ -158,14 +223,17 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
     CU(c, cudaMemsetAsync(b.win[0], 0, gz::kWindow, c->compute));
     for (int piece_no = 0;; ++piece_no) {
         // ---- compressed bytes of the piece (+ overlap) -----------------------------------------------------
-        const uint64_t want_end = std::min<uint64_t>(file_pos + piece + 2 * g.stride, file_bytes);
-        const size_t n_in = static_cast<size_t>(want_end - file_pos);
-        fseek(fh, static_cast<long>(file_pos), SEEK_SET);
-        if (fread(b.host, 1, n_in, fh) != n_in) return fail(c, FRB_ERR_IO, "%s: read error", path);
-        memset(b.host + n_in, 0, 64);
-        const bool last_piece = file_pos + piece >= file_bytes;
-        CU(c, cudaMemcpyAsync(b.comp, b.host, n_in + 64, cudaMemcpyHostToDevice, c->compute));
-        const size_t body = last_piece ? n_in : piece;
+        const uint64_t file_pos = plan[piece_no].first;
+        const bool last_piece = static_cast<size_t>(piece_no) + 1 == plan.size();
+        const size_t n_in = static_cast<size_t>(std::min<uint64_t>(file_pos + plan[piece_no].second + 3 * g.stride, file_bytes) - file_pos);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return filled > piece_no || !io_err.empty(); });
+            if (!io_err.empty()) return fail(c, FRB_ERR_IO, "%s: %s", path, io_err.c_str());
+        }
+        unsigned char* const comp = b.comp[piece_no & 1];
+        CU(c, cudaStreamWaitEvent(c->compute, b.copied[piece_no & 1], 0));
+        const size_t body = last_piece ? n_in : static_cast<size_t>(plan[piece_no].second);
         const unsigned n_chunks = static_cast<unsigned>((body + g.stride - 1) / g.stride);
         const uint64_t rel_start = start_bit_abs - file_pos * 8;
         const unsigned first_chunk = static_cast<unsigned>((rel_start >> 3) / g.stride);  // chunk holding the start
@@ -185,14 +253,14 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
             tm.mark(0);
             if (search_to > search_from)
                 gz::gz_find_kernel<<<search_to - search_from, gz::kFindThreads, 0, c->compute>>>(
-                    b.comp, n_in, b.chunks, search_to, g.stride, 0, search_from);
+                    comp, n_in, b.chunks, search_to, g.stride, 0, search_from, last_piece ? 0xFFFFFFFFu : n_chunks);
             tm.mark(1);
             // every chunk of this piece an equal share of the staging area
             gz::gz_link_kernel<<<1, 32, 0, c->compute>>>(b.chunks, n_chunks, b.stage_syms / n_chunks / 16 * 16,
                                                          last_piece ? 0 : 1, flags + 2);
             tm.mark(2);
             gz::gz_decode_kernel<<<(n_chunks + gz::kDecodeWarps - 1) / gz::kDecodeWarps, gz::kDecodeWarps * 32, 0, c->compute>>>(
-                b.comp, n_in, b.chunks, n_chunks, b.stage);
+                comp, n_in, b.chunks, n_chunks, b.stage);
             tm.mark(3);
             gz::gz_offsets_kernel<<<1, 1024, 0, c->compute>>>(b.chunks, n_chunks, b.scalars, flags);
             tm.mark(4);
@@ -207,6 +275,11 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         CU(c, cudaMemcpyAsync(b.scalars_host, b.scalars, 64, cudaMemcpyDeviceToHost, c->compute));
         CU(c, cudaMemcpyAsync(b.chunks_host + 1, b.chunks + n_chunks, sizeof(gz::Chunk), cudaMemcpyDeviceToHost, c->compute));
         CU(c, cudaStreamSynchronize(c->compute));
+        {   // the decode kernel was the last reader of the compressed piece: its buffers may be refilled
+            std::lock_guard<std::mutex> lk(mu);
+            released = piece_no + 1;
+        }
+        cv.notify_all();
         const unsigned* hflags = reinterpret_cast<const unsigned*>(b.scalars_host + 2);
         const uint64_t n_sym = b.scalars_host[0];
         if (hflags[0] != 0xFFFFFFFFu) {  // a chunk failed: which way?
@@ -260,7 +333,6 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         carry_len = tail;
         ob ^= 1;
         start_bit_abs = file_pos * 8 + b.chunks_host[1].start_bit;
-        file_pos = (start_bit_abs >> 3) & ~3ull;
         member_start = false;
     }
     if (raw_bytes) *raw_bytes = total_out;

@@ -269,7 +269,8 @@ __device__ inline bool plausible_block_start(const unsigned char* __restrict__ d
 // `limit_bit`.  One CTA per chunk; the threads try consecutive bit positions.
 __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned char* __restrict__ d, unsigned long long nbytes,
                                                                Chunk* chunks, unsigned n_chunks, unsigned long long stride,
-                                                               unsigned long long first_byte, unsigned first_chunk) {
+                                                               unsigned long long first_byte, unsigned first_chunk,
+                                                               unsigned tail_chunk) {
     const unsigned c = blockIdx.x + first_chunk;
     if (c >= n_chunks) return;
     __shared__ unsigned long long s_best;
@@ -277,7 +278,11 @@ __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned ch
     __syncthreads();
     const unsigned long long from = (first_byte + static_cast<unsigned long long>(c) * stride) * 8;
     // search one stride and a half: a start behind that belongs to the next chunk anyway
-    const unsigned long long to = min((first_byte + static_cast<unsigned long long>(c + 1) * stride + stride / 2) * 8, nbytes * 8);
+    // (the chunk behind the piece, whose start closes the piece's last chunk, may look further: the piece buffer
+    // carries three strides of overlap)
+    const bool tail = c == tail_chunk;
+    const unsigned long long reach = tail ? 3 * stride - 8192 : stride + stride / 2;
+    const unsigned long long to = min((first_byte + static_cast<unsigned long long>(c) * stride + reach) * 8, nbytes * 8);
     for (unsigned long long base = from; base < to; base += 8 * kFindThreads) {
         for (int r = 0; r < 8; ++r) {  // eight rounds between looks at the result (positions stay in order per round)
             const unsigned long long p = base + r * kFindThreads + threadIdx.x;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned ch
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        chunks[c].found = s_best != ~0ull && s_best < (first_byte + static_cast<unsigned long long>(c + 1) * stride) * 8;
+        chunks[c].found = s_best != ~0ull && (tail || s_best < (first_byte + static_cast<unsigned long long>(c + 1) * stride) * 8);
         chunks[c].start_bit = s_best;
     }
 }
