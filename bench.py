@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the scan hot path: read-names/s scanned + matched (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R] [--workload scan|demux]
 
 One step = one pass of the whole scan path over one synthetic NovaSeq-lane shaped input
 (config C2: 10+10 bp UDI, 384-sample sheet, `scan -n 1 -rc`): fused parse+pack+count kernel ->
 sorted unique list -> matcher pass 1 (forward + reverse-complement) -> per-sample orientation
-call -> matcher pass 2.  `value` is kernel-only (input resident in HBM, results left on the
-device); `e2e` feeds HOST buffers through the C-ABI (H2D of every input byte and D2H of the
-per-key results inside the timed region).  N > 1: one process per GPU (torchrun), each rank owns
-one lane (weak scaling); inside the step the per-rank unique tables are merged over NCCL so that every
-key ends on one rank (frb_shardmerge), each rank matches its share, and the per-sample orientation sums
-are all-reduced (the call of F:354-388 is over all reads of the job).
-`--impl reference` times the CPU oracle port of the reference (the reference is a Python script
-that cannot travel to the GPU box) on a bounded sample with all host cores.
+call -> matcher pass 2.
+  value   kernel-only: the lane resident in HBM, results left on the device.
+  e2e     what a user runs: one `.fastq.gz` of the lane through frb_scan_gz (the compressed bytes go host ->
+          device, are inflated there, scanned where they lie) + both matcher passes + D2H of keys, counts and
+          per-key results, wall clock.  `e2e_pcie` is the round-1 leg (decompressed text in pinned host
+          memory through frb_scan_chunk_host) beside a plain pinned-memcpy measurement of the link.
+N > 1: one process per GPU (torchrun), each rank owns one lane (weak scaling); inside the step the per-rank
+unique tables are merged over NCCL so that every key ends on one rank (frb_shardmerge), each rank matches its
+share, and the per-sample orientation sums are all-reduced (the call of F:354-388 is over all reads of the job).
+`--impl reference` times the reference itself (baseline/_ref/frender.py, copied there by
+__graft_entry__.build(); the oracle port when it is absent) with all host cores on a bounded sample of the same
+lane: the first reads of the stream the e2e leg uses.
+After the timed loop the result is CHECKED: counts sum to the reads, shares of the ranks are disjoint, and the
+first 3 M reads of the lane -- tally, both matcher passes, orientation calls -- equal the C oracle's.
 """
 import argparse
 import json
@@ -31,8 +37,10 @@ import numpy as np  # noqa: E402
 CONFIG = "C2"
 N_SUBS = 1
 GEN_CHUNK = 8_000_000          # reads per generator call
-CPU_SAMPLE_READS = 150_000     # bounded sample for the CPU arm
-E2E_MAX_BYTES = 6 << 30        # host-resident sample for the end-to-end leg
+CPU_SAMPLE_READS = 200_000     # bounded sample for the CPU arm (about 3 s of the reference per step)
+E2E_MAX_BYTES = 6 << 30        # host-resident sample for the pinned-text leg (e2e_pcie)
+E2E_GZ_READS = 4_000_000       # reads in the .fastq.gz of the end-to-end leg
+CHECK_READS = 3_000_000        # prefix of the lane compared with the C oracle after the timed loop
 
 
 def parse_args():
@@ -45,6 +53,8 @@ def parse_args():
     ap.add_argument("--table-log2", type=int, default=0, help="slots of the unique-key tables (default: by input size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--workload", default="scan", choices=["scan", "demux"])
     return ap.parse_args()
 
 
@@ -53,6 +63,7 @@ def parse_args():
 # --impl reference).  This is the one place outside tests/ that executes oracle/.
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(tmpdir, reads=CPU_SAMPLE_READS):
+    """The first `reads` reads of the lane (the stream the e2e leg compresses) as one .fastq.gz + its sheet."""
     import gzip
 
     from frender_b200 import synth
@@ -64,13 +75,44 @@ def cpu_sample(tmpdir, reads=CPU_SAMPLE_READS):
     return spec, path, len(data)
 
 
-def cpu_step(spec, path, cores):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import frender_oracle as O
+def load_reference():
+    """The reference itself (baseline/_ref/frender.py, an unmodified copy made by __graft_entry__.build()), or
+    None when it is not there."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "frender.py")):
+        return None
+    import importlib.util
+    import warnings
+    warnings.simplefilter("ignore")
+    spec = importlib.util.spec_from_file_location("frender_reference", os.path.join(ref_dir, "frender.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_step(spec, path, cores, ref=None):
+    """scan -n 1 -rc on one file, host only: tally + both matcher passes.  ref: the reference module; None: the
+    oracle port.  Returns (total s, tally s, matcher s, unique keys)."""
+    import contextlib
+    import io
+    indexes = spec.indexes()
     t0 = time.perf_counter()
-    counter = O.tally_barcodes(cores, [path])
-    t1 = time.perf_counter()
-    results, calls, _ = O.scan_analysis(cores, counter, spec.indexes(), N_SUBS, True)
+    if ref is not None:
+        with contextlib.redirect_stdout(io.StringIO()):
+            counter = ref.tally_barcodes(cores, [path], None)                       # F:183-207
+            t1 = time.perf_counter()
+            first = ref.process(cores, counter["total"], indexes, N_SUBS, True)   # F:391-426
+            calls = ref.call_rc_mode_per_id(ref.flatten_results(first), indexes["id"])      # F:354-388
+            oriented = dict(indexes)
+            oriented["idx2"] = [ref.reverse_complement(b) if calls[i]["call"] else b
+                                for b, i in zip(indexes["idx2"], indexes["id"])]     # F:618-623
+            results = ref.process(cores, counter["total"], oriented, N_SUBS, False)  # F:628-630
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import frender_oracle as O
+        counter = O.tally_barcodes(cores, [path])
+        t1 = time.perf_counter()
+        results, calls, _ = O.scan_analysis(cores, counter, indexes, N_SUBS, True)
     t2 = time.perf_counter()
     return t2 - t0, t1 - t0, t2 - t1, len(results)
 
@@ -80,25 +122,29 @@ def run_reference(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
+    ref = load_reference()
+    kind = "reference" if ref is not None else "port"
     with tempfile.TemporaryDirectory() as d:
         spec, path, nbytes = cpu_sample(d)
         times, parts = [], []
         for i in range(args.warmup + args.steps):
-            total, t_tally, t_match, uniq = cpu_step(spec, path, cores)
+            total, t_tally, t_match, uniq = cpu_step(spec, path, cores, ref)
             if i >= args.warmup:
                 times.append(total)
                 parts.append((t_tally, t_match))
     ms = 1e3 * sum(times) / len(times)
     value = CPU_SAMPLE_READS / (ms / 1e3)
-    sample = (f"{CPU_SAMPLE_READS} reads of the {CONFIG} lane ({nbytes} B decompressed) from one .fastq.gz: "
-              f"gzip inflate + tally (1 core: one file) + matcher both passes on {cores} cores; "
+    what = ("/root/reference/frender.py (unmodified copy in baseline/_ref): tally_barcodes + process(rc) + "
+            "call_rc_mode_per_id + process" if ref is not None else "oracle port of the reference")
+    sample = (f"{what}; the first {CPU_SAMPLE_READS} reads of the {CONFIG} lane ({nbytes} B decompressed) from one "
+              f".fastq.gz per step: gzip inflate + tally (1 core: one file) + matcher both passes on {cores} cores; "
               f"{uniq} unique keys")
     line = {
         "impl": "reference", "metric": "read_names_per_s_scanned_matched", "value": value, "unit": "reads/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64",
-        "data": "synthetic", "config": workload_config(CPU_SAMPLE_READS, 1),
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample,
+        "data": "synthetic", "config": workload_config(args.reads or 400_000_000, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample,
                          "tally_s": sum(p[0] for p in parts) / len(parts),
                          "match_s": sum(p[1] for p in parts) / len(parts)},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -348,7 +394,7 @@ def run_b200(args):
     scan_ms_per = scan_ms / max(scan_n, 1)
     achieved = nbytes / (scan_ms_per * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_scan_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = nbytes * tj["traffic_per_algorithmic_byte"]
@@ -356,15 +402,77 @@ def run_b200(args):
                        "from %d to %d algorithmic bytes" % (tj["source"], tj["algorithmic_bytes"], nbytes))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "scan_ws_kernel (parse+pack+count, warp-specialised)", "peak_source": peak_src,
+                "kernel": "scan_spec_kernel (parse+pack+count, warp-specialised, speculative line phase)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": scan_ms_per,
                 "step_share": {name: prof[k][0] / args.steps for name, k in
                                (("scan_ms", L.K_SCAN), ("export_sort_merge_ms", L.K_EXPORT),
                                 ("match_ms", L.K_MATCH), ("clear_ms", L.K_OTHER), ("verify_ms", L.K_VERIFY))}}
 
-    # ---- end to end: host buffers -> H2D -> kernels -> D2H of per-key results -------------------
-    e2e = None
+    # ---- end to end, as a user runs it: one .fastq.gz -> frb_scan_gz (compressed bytes host -> device, inflated
+    #      there, scanned where they lie) -> both matcher passes -> D2H of keys, counts and per-key results ----
+    e2e = e2e_pcie = None
     if not args.no_e2e:
+        import zlib
+        g_reads = min(E2E_GZ_READS, reads)
+        raw = np.empty(int(g_reads * 376), np.uint8)
+        n_raw = C.c_uint64()
+        tmpbuf = C.c_void_p()
+        ck(lib.frb_dev_alloc(h, raw.size, C.byref(tmpbuf)))
+        ck(lib.frb_synth_generate(h, g_base, g_base + g_reads, 1, tmpbuf, raw.size, C.byref(n_raw)))
+        ck(lib.frb_d2h(h, vp(raw), tmpbuf, n_raw.value))
+        ck(lib.frb_dev_free(h, tmpbuf))
+        with tempfile.TemporaryDirectory() as d:
+            gz_path = os.path.join(d, "Undetermined_S0_L001_R1_001.fastq.gz")
+            z = zlib.compressobj(1, zlib.DEFLATED, 31)       # ONE gzip member, as a sequencer's fastq.gz
+            with open(gz_path, "wb") as fh:
+                view = memoryview(raw)[:n_raw.value]
+                for off in range(0, n_raw.value, 64 << 20):
+                    fh.write(z.compress(view[off:off + (64 << 20)]))
+                fh.write(z.flush())
+            gz_size = os.path.getsize(gz_path)
+            d2h = [0]
+
+            def step_gz():
+                ctx.reset()
+                got_r, _, got_raw = ctx.scan_gz(gz_path, rank)
+                if world > 1:
+                    n_u = C.c_uint64()
+                    ck(lib.frb_shardmerge(h, C.byref(n_u)))
+                keys, counts, _ = ctx.total_arrays()
+                out = analyze(True)
+                d2h[0] = keys.nbytes + counts.nbytes + sum(v.nbytes for v in out.values())
+                assert got_raw == n_raw.value
+                return got_r
+
+            e_steps, e_warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
+            _, e_wall, e_got = timed(step_gz, e_steps, e_warm)
+            assert e_got == g_reads, (e_got, g_reads)
+            e_s = e_wall / e_steps
+            if dist:
+                box = [None] * world
+                dist.all_gather_object(box, e_s)
+                e_s = max(box)
+            e2e = {"value": g_reads * world / e_s, "unit": "reads/s", "h2d_bytes_per_step": gz_size,
+                   "d2h_bytes_per_step": d2h[0], "reads_per_step_per_gpu": g_reads, "ms_per_step": e_s * 1e3,
+                   "gz_bytes": gz_size, "raw_bytes": n_raw.value, "inflate_gbs": n_raw.value / e_s / 1e9,
+                   "sample": "one single-member .fastq.gz (zlib level 1) of the first %d reads of the lane through "
+                             "frb_scan_gz (device-side inflate) + both matcher passes + D2H of keys, counts and "
+                             "per-key results; wall clock, sync both sides" % g_reads}
+            if rank == 0 and world == 1:
+                # the same file with zlib on a host thread (round 1's path, FRB_GZ_DEVICE=0 in a child process)
+                code = ("import sys, time; sys.path.insert(0, %r)\n"
+                        "from frender_b200.engine import Context\n"
+                        "ctx = Context(%d, table_log2=22); ctx.scan_gz(%r, 0); ctx.reset()\n"
+                        "t0 = time.perf_counter(); r, u, raw = ctx.scan_gz(%r, 0); print(r / (time.perf_counter() - t0))"
+                        % (ROOT, local, gz_path, gz_path))
+                res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                                     env=dict(os.environ, FRB_GZ_DEVICE="0"))
+                if res.returncode == 0:
+                    e2e["host_zlib_reads_per_s"] = float(res.stdout.strip().splitlines()[-1])
+
+        # ---- round 1's leg: decompressed text in pinned host memory -> H2D -> kernels -> D2H, and what the
+        #      link alone does (one pinned cudaMemcpy of the same bytes) -----------------------------------
         k = max(1, sum(1 for b in bounds[1:] if b <= E2E_MAX_BYTES))
         e_bytes = bounds[k]
         e_reads = min(k * GEN_CHUNK, reads)
@@ -386,86 +494,95 @@ def run_b200(args):
             d2h[0] = keys.nbytes + counts.nbytes + sum(v.nbytes for v in out.values())
             return n_reads.value
 
-        e_steps, e_warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
-        _, e_wall, e_got = timed(step_host, e_steps, e_warm)
-        assert e_got == e_reads, (e_got, e_reads)
-        e_s = e_wall / e_steps
+        _, p_wall, p_got = timed(step_host, 2, 1)
+        assert p_got == e_reads, (p_got, e_reads)
+        p_s = p_wall / 2
+        scratch = C.c_void_p()
+        ck(lib.frb_dev_alloc(h, e_bytes, C.byref(scratch)))
+        ck(lib.frb_h2d(h, scratch, hbuf, e_bytes))
+        t0 = time.perf_counter()
+        ck(lib.frb_h2d(h, scratch, hbuf, e_bytes))
+        link_s = time.perf_counter() - t0
+        ck(lib.frb_dev_free(h, scratch))
+        ck(lib.frb_host_free(hbuf))
         if dist:
             box = [None] * world
-            dist.all_gather_object(box, e_s)
-            e_s = max(box)
-        e2e = {"value": e_reads * world / e_s, "unit": "reads/s", "h2d_bytes_per_step": e_bytes,
-               "d2h_bytes_per_step": d2h[0], "reads_per_step_per_gpu": e_reads, "ms_per_step": e_s * 1e3,
-               "h2d_gbs": e_bytes / e_s / 1e9,
-               "sample": "host-pinned decompressed FASTQ (first %d reads of the lane) through frb_scan_chunk_host; "
-                         "wall clock, sync both sides" % e_reads}
-        ck(lib.frb_host_free(hbuf))
+            dist.all_gather_object(box, (p_s, link_s))
+            p_s, link_s = max(b[0] for b in box), max(b[1] for b in box)
+        e2e_pcie = {"value": e_reads * world / p_s, "unit": "reads/s", "h2d_bytes_per_step": e_bytes,
+                    "d2h_bytes_per_step": d2h[0], "h2d_gbs": e_bytes / p_s / 1e9,
+                    "pinned_memcpy_gbs": e_bytes / link_s / 1e9, "pcie_frac": (e_bytes / p_s) / (e_bytes / link_s),
+                    "sample": "host-pinned decompressed FASTQ (first %d reads of the lane) through "
+                              "frb_scan_chunk_host; pcie_frac = its H2D rate / a plain pinned cudaMemcpy of the "
+                              "same bytes on the same GPU at the same time on every rank" % e_reads}
 
-    # ---- end to end WITH host gzip: a .fastq.gz sample through frb_scan_gz (zlib inflate thread, pinned
-    #      ring, H2D overlapped with the kernels), as the CLI does; inflate-bound by construction ----------
-    e2e_gzip = None
-    if rank == 0 and world == 1 and not args.no_e2e:
-        import zlib
-        g_reads = min(2_000_000, reads)
-        g_bytes = bounds[1] if GEN_CHUNK <= g_reads else None
-        raw = np.empty(int(g_reads * 376), np.uint8)
-        n_raw = C.c_uint64()
-        tmpbuf = C.c_void_p()
-        ck(lib.frb_dev_alloc(h, raw.size, C.byref(tmpbuf)))
-        ck(lib.frb_synth_generate(h, g_base, g_base + g_reads, 1, tmpbuf, raw.size, C.byref(n_raw)))
-        ck(lib.frb_d2h(h, vp(raw), tmpbuf, n_raw.value))
-        ck(lib.frb_dev_free(h, tmpbuf))
-        with tempfile.TemporaryDirectory() as d:
-            gz_path = os.path.join(d, "Undetermined_S0_L001_R1_001.fastq.gz")
-            z = zlib.compressobj(1, zlib.DEFLATED, 31)
-            with open(gz_path, "wb") as fh:
-                view = memoryview(raw)[:n_raw.value]
-                for off in range(0, n_raw.value, 64 << 20):
-                    fh.write(z.compress(view[off:off + (64 << 20)]))
-                fh.write(z.flush())
-            gz_size = os.path.getsize(gz_path)
-            best = None
-            for _ in range(3):
-                t0 = time.perf_counter()
-                ctx.reset()
-                got_r, got_u, got_raw = ctx.scan_gz(gz_path, 0)
-                ctx.total_arrays()
-                analyze(True)
-                dt = time.perf_counter() - t0
-                best = dt if best is None else min(best, dt)
-            assert got_r == g_reads and got_raw == n_raw.value
-            # the same through the CLI's `-c N` path: N files inflated and scanned at the same time, one
-            # context per stream on this GPU, per-file lists folded into one total on the device (F:189-203)
-            from frender_b200.cli import scan_files_concurrent
-            streams = max(2, min(8, len(os.sched_getaffinity(0))))
-            files = []
-            for k in range(streams):
-                pth = os.path.join(d, f"lane{k}_R1.fastq.gz")
-                os.link(gz_path, pth)
-                files.append(pth)
-            best_m = None
-            for _ in range(2):
-                t0 = time.perf_counter()
-                per_file, _tot = scan_files_concurrent(files, None, streams, local, 21, ctx)
-                analyze(True)
-                dt = time.perf_counter() - t0
-                best_m = dt if best_m is None else min(best_m, dt)
-            assert all(per_file[k][0] == g_reads for k in range(streams))
-        e2e_gzip = {"value": g_reads / best, "unit": "reads/s", "reads": g_reads, "gz_bytes": gz_size,
-                    "raw_bytes": n_raw.value, "inflate_gbs": n_raw.value / best / 1e9,
-                    "note": "one .fastq.gz stream; single zlib inflate thread is the bound (SURVEY 8f-1)",
-                    "multi_file": {"value": streams * g_reads / best_m, "unit": "reads/s", "files": streams,
-                                   "streams": streams, "inflate_gbs": streams * n_raw.value / best_m / 1e9,
-                                   "note": "`-c N`: N files at the same time, one context and one zlib thread each"}}
+    # ---- the result itself: conservation, disjoint shares, and the lane's first reads against the C oracle -----
+    checked = None
+    if not args.no_check:
+        step_resident()
+        keys, counts, first = ctx.total_arrays()
+        total_reads = int(counts.sum())
+        if dist:
+            box = [None] * world
+            dist.all_gather_object(box, (total_reads, keys))
+            total_reads = sum(b[0] for b in box)
+            allk = np.concatenate([b[1] for b in box])
+            assert len(np.unique(allk)) == len(allk), "shares of the ranks overlap"
+        assert total_reads == reads * world, (total_reads, reads * world)
+        assert (np.diff(first.astype(np.int64)) > 0).all(), "total list is not in first-appearance order"
+        checked = {"conservation": True, "shares_disjoint": True if dist else None}
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import c_oracle
+            from frender_b200.engine import reverse_complement, unpack_keys
+            c_reads = min(CHECK_READS, reads)
+            c_bytes = bounds[1] if GEN_CHUNK <= c_reads else None
+            sub = np.empty(int(c_reads * 376), np.uint8)
+            n_sub, tmpbuf = C.c_uint64(), C.c_void_p()
+            ck(lib.frb_dev_alloc(h, sub.size, C.byref(tmpbuf)))
+            ck(lib.frb_synth_generate(h, g_base, g_base + c_reads, 1, tmpbuf, sub.size, C.byref(n_sub)))
+            ck(lib.frb_d2h(h, vp(sub), tmpbuf, n_sub.value))
+            cctx = Context(local, table_log2=21)
+            ck2 = cctx._ck
+            ck2(lib.frb_scan_begin(cctx._h, 0, 0))
+            ck2(lib.frb_scan_chunk_dev(cctx._h, tmpbuf, n_sub.value, 0, L.RULE_SCAN, None, None))
+            r_, u_ = C.c_uint64(), C.c_uint64()
+            ck2(lib.frb_scan_end(cctx._h, C.byref(r_), C.byref(u_)))
+            want, want_reads = c_oracle.tally(sub[:n_sub.value].tobytes())
+            k2, c2, _ = cctx.total_arrays()
+            names = unpack_keys(k2)
+            assert r_.value == want_reads == c_reads and names == list(want) and c2.tolist() == list(want.values()), \
+                "tally of the lane's first reads differs from the C oracle"
+            idx = spec.indexes()
+            cctx.load_sheet(idx)
+            res = cctx.match(N_SUBS, True)
+            ref = np.array(c_oracle.classify_all_rc(names, idx, N_SUBS), np.int32)
+            for col, name in enumerate(("m1", "m2", "type", "srow", "m2rc", "type_rc", "srow_rc")):
+                assert (res[name].astype(np.int32) == ref[:, col]).all(), "first pass differs from the C oracle: " + name
+            calls = c_oracle.rc_calls(names, c2.tolist(), ref.tolist(), idx)
+            got_calls = cctx.rc_calls(res)
+            assert {k: (v["call"], v["reads_f"], v["reads_rc"]) for k, v in got_calls.items()} == calls
+            use = np.array([calls[name][0] for name in idx["id"]], np.uint8)
+            oriented = dict(idx, idx2=[reverse_complement(b) if u else b for b, u in zip(idx["idx2"], use)])
+            res2 = cctx.match(N_SUBS, False, use)
+            ref2 = np.array(c_oracle.classify_all(names, oriented, N_SUBS), np.int32)
+            for col, name in enumerate(("m1", "m2", "type", "srow")):
+                assert (res2[name].astype(np.int32) == ref2[:, col]).all(), "second pass differs from the C oracle: " + name
+            cctx.close()
+            ck(lib.frb_dev_free(h, tmpbuf))
+            checked["c_oracle"] = {"reads": c_reads, "unique_keys": len(names), "tally": True, "pass_rc": True,
+                                   "orientation_calls": True, "pass_oriented": True}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0))
+        ref = load_reference()
         with tempfile.TemporaryDirectory() as d:
             cspec, path, cbytes = cpu_sample(d)
-            total, t_tally, t_match, uniq = cpu_step(cspec, path, cores)
-        cpu = {"value": CPU_SAMPLE_READS / total, "unit": "reads/s", "cores": cores, "kind": "port",
-               "sample": f"{CPU_SAMPLE_READS} reads of the same lane shape from one .fastq.gz: inflate+tally "
+            total, t_tally, t_match, uniq = cpu_step(cspec, path, cores, ref)
+        cpu = {"value": CPU_SAMPLE_READS / total, "unit": "reads/s", "cores": cores,
+               "kind": "reference" if ref is not None else "port",
+               "sample": f"the first {CPU_SAMPLE_READS} reads of the same lane from one .fastq.gz: inflate+tally "
                          f"{t_tally:.2f}s (1 core, one file) + matcher both passes {t_match:.2f}s on {cores} cores"}
 
     if rank == 0:
@@ -474,7 +591,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic (device-generated, "
             "counter-based; byte-identical to frender_b200/synth.py)",
-            "config": workload_config(reads, world), "clocks": clk, "e2e": e2e, "e2e_gzip": e2e_gzip,
+            "config": workload_config(reads, world), "clocks": clk, "e2e": e2e, "e2e_pcie": e2e_pcie,
+            "checked": checked,
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu,
             "unique_keys": n_uniq.value, "input_bytes_per_gpu": nbytes, "gen_s": t_gen,
