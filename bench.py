@@ -81,12 +81,14 @@ def load_reference():
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.exists(os.path.join(ref_dir, "frender.py")):
         return None
-    import importlib.util
+    import importlib
     import warnings
     warnings.simplefilter("ignore")
-    spec = importlib.util.spec_from_file_location("frender_reference", os.path.join(ref_dir, "frender.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    # under its own module name: its process pools pickle their work functions by reference (frender.scan_file)
+    sys.path.insert(0, ref_dir)
+    sys.modules.pop("frender", None)
+    mod = importlib.import_module("frender")
+    assert os.path.dirname(os.path.abspath(mod.__file__)) == ref_dir, mod.__file__
     return mod
 
 
