@@ -524,13 +524,22 @@ def write_scan_csv(path, tables, res, sheet, idx2_used, ok):
 # ---------------------------------------------------------------------------------------------
 # demux (F:645-814)
 # ---------------------------------------------------------------------------------------------
+SCAN_LAYOUT = ["idx1", "idx2", "matched_idx1", "matched_idx2", "read_type", "sample_name", "reads", "demux_ok"]
+DEMUX_LAYOUT = ["idx1", "idx2", "reads", "matched_idx1", "matched_idx2", "read_type", "sample_name"]
+
+
 def parse_results_file(result_file):
-    """{key: (read_type, sample_id)} by column position 0,1,5,6; header assertion of F:649-657."""
+    """{key: (read_type, sample_id)}.  The reference reads columns 0, 1, 5, 6 after asserting the readme's column
+    order (F:649-664) -- an order its own `scan` does not write (SURVEY finding 1), so the reference's demux refuses
+    the reference's scan output.  EXTENSION: the layout `scan` actually writes is accepted as well, by column
+    name; every other header fails with the reference's assertion."""
     with open(result_file, newline="") as fh:
         rows = csv.reader(fh)
         header = next(rows)
-        assert header[0:7] == ["idx1", "idx2", "reads", "matched_idx1", "matched_idx2", "read_type",
-                               "sample_name"], f"${result_file} does not appear to be a valid frender result file!"
+        if header[0:8] == SCAN_LAYOUT:
+            kind, sid = header.index("read_type"), header.index("sample_name")
+            return {r[0] + "+" + r[1]: (r[kind], r[sid]) for r in rows}
+        assert header[0:7] == DEMUX_LAYOUT, f"${result_file} does not appear to be a valid frender result file!"
         return {r[0] + "+" + r[1]: (r[5], r[6]) for r in rows}
 
 

@@ -139,3 +139,25 @@ def test_cli_scan_grows_a_full_table(golden, golden_dir, tmp_path, monkeypatch, 
     run_cli(["scan", "-n", "1", "-rc", "-b", str(tmp_path / "SampleSheet.csv"), str(dst)], tmp_path)
     assert "tallying again with 2^12" in capsys.readouterr().out
     assert (tmp_path / f"frender-scan-results_1-mismatches_{fname}.csv").read_bytes() == unb64(case["scan_csv"])
+
+
+def test_cli_demux_accepts_the_scan_layout(golden, tmp_path):
+    """Extension (SURVEY finding 1): `demux -r` takes the CSV exactly as `scan` wrote it; same sinks, same bytes as
+    with the reordered file the reference needs.  Any other header still fails with the reference's assertion."""
+    from frender_b200 import synth
+    case = golden["demux"]["c1"]
+    scan = golden["scan"]["c1"]
+    spec = synth.make_spec(scan["config"], n_samples=scan["n_samples"])
+    p1 = tmp_path / "Undetermined_S0_L001_R1_001.fastq.gz"
+    p2 = tmp_path / "Undetermined_S0_L001_R2_001.fastq.gz"
+    p1.write_bytes(gzip.compress(synth.generate_big(spec, 0, case["reads"], 1), 1))
+    p2.write_bytes(gzip.compress(synth.generate_big(spec, 0, case["reads"], 2), 1))
+    (tmp_path / "scan.csv").write_bytes(unb64(scan["scan_csv"]))
+    run_cli(["demux", "-r", str(tmp_path / "scan.csv"), "-d", str(tmp_path / "out"), str(p1), str(p2)], tmp_path)
+    assert sorted(os.listdir(tmp_path / "out")) == sorted(case["sinks"])
+    for fname, want in case["sinks"].items():
+        raw = gzip.open(tmp_path / "out" / fname, "rb").read()
+        assert hashlib.sha256(raw).hexdigest() == want["sha256"], fname
+    (tmp_path / "bad.csv").write_text("a,b,c\r\n1,2,3\r\n")
+    with pytest.raises(AssertionError, match="does not appear to be a valid frender result file"):
+        run_cli(["demux", "-r", str(tmp_path / "bad.csv"), "-d", str(tmp_path / "out2"), str(p1), str(p2)], tmp_path)
