@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--workload", default="scan", choices=["scan", "demux"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one lane per GPU; strong: ONE lane, its record chunks dealt to the GPUs")
     return ap.parse_args()
 
 
@@ -262,13 +264,16 @@ def run_b200(args):
         import torch.distributed as dist  # host-side rendezvous only (gloo); the data path is NCCL in the .so
         dist.init_process_group("gloo", rank=rank, world_size=world)
 
-    spec = synth.make_spec(CONFIG, lane=1 + rank % 8)
+    spec = synth.make_spec(CONFIG, lane=1 if args.scaling == "strong" else 1 + rank % 8)
     lib = L.lib
     probe = Context(local, table_log2=10)
     free_b, total_b = C.c_uint64(), C.c_uint64()
     probe._ck(lib.frb_mem_info(probe._h, C.byref(free_b), C.byref(total_b)))
     probe.close()
+    strong = args.scaling == "strong" and world > 1
     reads = args.reads or 400_000_000
+    if strong:          # one lane for the whole job: rank r scans the reads [r * reads, (r + 1) * reads) of it
+        reads = -(-reads // world)
     bytes_per_read = 375.0
     table_log2 = args.table_log2 or (26 if reads > 100_000_000 else (24 if reads > 8_000_000 else 21))
     overhead = 2 * (32 << table_log2) + (8 << 30)
@@ -326,8 +331,10 @@ def run_b200(args):
 
     def step_resident():
         ck(lib.frb_reset(h))
-        ck(lib.frb_scan_begin(h, rank, 0))
-        ck(lib.frb_scan_chunk_dev(h, dbuf, nbytes, 0, L.RULE_SCAN, None, None))
+        # weak: every rank its own file (ordinal = rank).  strong: the ranks hold consecutive chunks of ONE file: same
+        # ordinal, and the chunk's global line number makes `first` the read ordinal within the whole file
+        ck(lib.frb_scan_begin(h, 0 if strong else rank, 0))
+        ck(lib.frb_scan_chunk_dev(h, dbuf, nbytes, 4 * g_base if strong else 0, L.RULE_SCAN, None, None))
         n_reads, n_uniq = C.c_uint64(), C.c_uint64()
         ck(lib.frb_scan_end(h, C.byref(n_reads), C.byref(n_uniq)))
         if world > 1:
@@ -591,7 +598,7 @@ def run_b200(args):
         line = {
             "metric": "read_names_per_s_scanned_matched", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic (device-generated, "
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic (device-generated, "
             "counter-based; byte-identical to frender_b200/synth.py)",
             "config": workload_config(reads, world), "clocks": clk, "e2e": e2e, "e2e_pcie": e2e_pcie,
             "checked": checked,

@@ -145,9 +145,11 @@ class Context:
         self._ck(lib.frb_gz_inflate(self._h, os.fsencode(str(path)), _ptr(out), cap, C.byref(n), C.byref(used)))
         return out[:n.value].tobytes() if used.value else None
 
-    def scan_bytes(self, data, ordinal=0, sample=None, rule=_lib.RULE_SCAN, name=None, chunk=None):
+    def scan_bytes(self, data, ordinal=0, sample=None, rule=_lib.RULE_SCAN, name=None, chunk=None, line_base=0):
         """Decompressed FASTQ bytes from host memory, optionally fed in `chunk`-sized pieces cut
-        at line ends.  Returns (reads, unique keys)."""
+        at line ends.  line_base: lines of the FILE in front of `data` (a rank that scans only some chunks of a
+        file passes each chunk's global line number; `first` then holds global read ordinals and the per-rank
+        lists merge exactly).  Returns (reads, unique keys)."""
         self._ck(lib.frb_scan_begin(self._h, ordinal, sample or 0))
         view = memoryview(data)
         pos, n = 0, len(view)
@@ -161,7 +163,7 @@ class Context:
                     raise FrbError(_lib.ERR_ARG, "chunk holds no line end")
                 end = pos + cut + 1
             piece = np.frombuffer(view[pos:end], dtype=np.uint8)
-            self._ck(lib.frb_scan_chunk_host(self._h, _ptr(piece), piece.size, 0 if first else _lib.CARRY, rule))
+            self._ck(lib.frb_scan_chunk_host(self._h, _ptr(piece), piece.size, line_base if first else _lib.CARRY, rule))
             first = False
             pos = end
         reads, uniq = C.c_uint64(), C.c_uint64()

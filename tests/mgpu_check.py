@@ -1,6 +1,7 @@
-"""Run under torchrun with N ranks (one per GPU): every rank scans its own shard of a synthetic
-lane, the per-rank tables are merged over NCCL (frb_allmerge) and every rank must end with the
-oracle's tally of the whole lane, in the oracle's order, and the oracle's classifications."""
+"""Run under torchrun with N ranks (one per GPU): the record chunks of ONE synthetic lane are dealt round-robin to
+the ranks, every rank scans its chunks with their global line numbers, the per-rank tables are merged over NCCL
+(frb_allmerge, then frb_shardmerge) and every rank must end with the oracle's tally of the whole lane, in the
+oracle's order, and the oracle's classifications."""
 import os
 import sys
 
@@ -23,7 +24,23 @@ def main():
     ctx = Context(int(os.environ["LOCAL_RANK"]), table_log2=18)
     spec = synth.make_spec("C2", n_samples=64)
     per = 30_000
-    shard = synth.generate(spec, rank * per, (rank + 1) * per)          # chunk sharding: rank r owns chunk r
+    # CHUNK sharding of ONE file: rank r owns the chunks r, r + world, ... of the lane (three chunks each, so that a
+    # rank's chunks are not contiguous); a chunk is scanned with its global line number, so `first` holds global
+    # read ordinals and the file ordinal is the same (0) on every rank
+    n_chunks = 3 * world
+    per //= 3
+    mine = [k for k in range(n_chunks) if k % world == rank]
+
+    def scan_my_chunks():
+        ctx._ck(L.lib.frb_scan_begin(ctx._h, 0, 0))
+        for k in mine:
+            piece = np.frombuffer(synth.generate(spec, k * per, (k + 1) * per), np.uint8)
+            ctx._ck(L.lib.frb_scan_chunk_host(ctx._h, piece.ctypes.data_as(C.c_void_p), piece.size, 4 * k * per, L.RULE_SCAN))
+        r, u = C.c_uint64(), C.c_uint64()
+        ctx._ck(L.lib.frb_scan_end(ctx._h, C.byref(r), C.byref(u)))
+        assert r.value == len(mine) * per
+        ctx.file_names.append("lane")
+
     ident = (C.c_char * 128)()
     if rank == 0:
         ctx._ck(L.lib.frb_nccl_unique_id(ident))
@@ -31,14 +48,14 @@ def main():
     dist.broadcast_object_list(box, src=0)
     ctx._ck(L.lib.frb_nccl_init(ctx._h, box[0], rank, world))
     ctx.reset()
-    ctx.scan_bytes(shard, ordinal=rank)                                  # first_pos = (chunk ordinal, read ordinal)
+    scan_my_chunks()
     n = C.c_uint64()
     ctx._ck(L.lib.frb_allmerge(ctx._h, C.byref(n)))
     keys, counts, _ = ctx.total_arrays()
-    whole = synth.generate(spec, 0, world * per)
+    whole = synth.generate(spec, 0, n_chunks * per)
     want, visited = O.tally_text(whole.decode().splitlines(keepends=True))
     got = dict(zip(unpack_keys(keys), counts.tolist()))
-    assert visited == world * per
+    assert visited == n_chunks * per
     assert list(got.items()) == list(want.items()), f"rank {rank}: merged tally differs from the oracle"
     res, calls, _ = ctx.analyze(spec.indexes(), 1, True)
     want_res, want_calls, _ = O.scan_analysis(1, {"total": want}, spec.indexes(), 1, True)
@@ -46,7 +63,7 @@ def main():
     # sharded merge of the same per-rank tallies: disjoint shares, union == the oracle's tally (counts and
     # first-appearance order), every share classified like the oracle classifies those keys
     ctx.reset()
-    ctx.scan_bytes(shard, ordinal=rank)
+    scan_my_chunks()
     ctx.shardmerge()
     skeys, scounts, sfirst = ctx.total_arrays()
     sres, _, _ = ctx.analyze(spec.indexes(), 1, True)
@@ -66,8 +83,8 @@ def main():
     assert merged_res == ref or {k: merged_res[k] for k in ref} == ref, "sharded matcher differs from the oracle"
     dist.barrier()
     if rank == 0:
-        print(f"mgpu ok: {world} ranks, {len(got)} unique keys, merged == oracle on every rank, "
-              f"shares {[len(s[0]) for s in shares]}")
+        print(f"mgpu ok: {world} ranks, {n_chunks} chunks of one file round-robin, {len(got)} unique keys, merged == oracle "
+              f"on every rank (counts, first-appearance order, both matcher passes), shares {[len(s[0]) for s in shares]}")
     ctx.close()
     dist.destroy_process_group()
 
