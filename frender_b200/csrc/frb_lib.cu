@@ -330,6 +330,32 @@ int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out, int fi
     return unsorted_to_sorted_list(c, k0, c0, f0, n, out, first_bits);
 }
 
+// The same when the number of occupied slots is not known: one pass over the table compacts and counts at once
+// (bound = an upper limit of the occupied slots, which sizes the pool allocations).
+int table_to_sorted_list_counting(frb_ctx* c, Slot* tab, uint64_t bound, KeyList* out, int first_bits,
+                                  const unsigned long long* tile_first) {
+    bound = std::max<uint64_t>(std::min<uint64_t>(bound, c->cap), 1);
+    if (bound >= (1ULL << 32)) return fail(c, FRB_ERR_ARG, "more than 2^32 unique keys");
+    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr;
+    TRY(dmalloc(c, &k0, bound * 8));
+    TRY(dmalloc(c, &c0, bound * 8));
+    TRY(dmalloc(c, &f0, bound * 8));
+    {
+        ProfScope ps(c, FRB_K_EXPORT);
+        CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
+        compact_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(
+            tab, c->cap, k0, c0, f0, &c->st->scratch, bound, tile_first);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    CU(c, cudaStreamSynchronize(c->compute));
+    TRY(device_error_check(c));
+    const uint64_t n = c->st_host->scratch;
+    if (n > bound) return fail(c, FRB_ERR_STATE, "more occupied slots (%llu) than reads scanned (%llu)", (unsigned long long)n,
+                               (unsigned long long)bound);
+    return unsorted_to_sorted_list(c, k0, c0, f0, n, out, first_bits);
+}
+
 int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t line_base, int rule,
                 unsigned long long* keys_out, unsigned long long* rec_off_out, Slot* table, uint64_t pos_base,
                 uint64_t out_cap = ~0ULL) {
@@ -747,20 +773,14 @@ int frb_scan_end(frb_ctx* c, uint64_t* n_reads, uint64_t* n_unique) {
     if (!c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_end: no file begun");
     c->in_file = false;
     CU(c, cudaStreamSynchronize(c->copy));
-    {   // unique keys of the file = occupied slots of its table
-        ProfScope ps(c, FRB_K_EXPORT);
-        CU(c, cudaMemsetAsync(&c->st->occupied, 0, 8, c->compute));
-        count_table_kernel<<<grid_for(c->cap, 256, c->sm_count, 16), 256, 0, c->compute>>>(c->file_tab, c->cap,
-                                                                                          &c->st->occupied);
-        c->launches++;
-    }
     CU(c, cudaStreamSynchronize(c->compute));
     TRY(device_error_check(c));
     KeyList fl;
     fl.reads = c->st_host->n_reads;
     fl.ordinal = c->cur_ordinal;
-    // read ordinals of one file stay below 2^40; composite positions become ordinals here
-    TRY(table_to_sorted_list(c, c->file_tab, c->st_host->occupied, &fl, 40, c->file_composite == 1 ? c->tile_first : nullptr));
+    // Unique keys of the file = occupied slots of its table (at most one per read): compacted and counted in one
+    // pass.  Read ordinals of one file stay below 2^40; composite positions become ordinals here.
+    TRY(table_to_sorted_list_counting(c, c->file_tab, fl.reads, &fl, 40, c->file_composite == 1 ? c->tile_first : nullptr));
     c->files.push_back(fl);
     c->total_ready = false;
     if (n_reads) *n_reads = fl.reads;

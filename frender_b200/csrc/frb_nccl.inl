@@ -250,42 +250,50 @@ int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
     lap("send/recv");
     // 4. fold my share: sort what arrived by key, one entry per run of equal keys (count: +, first: min),
     //    then the usual sort by first appearance.  No table involved: sequential traffic only.
-    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr, *ks = nullptr;
-    unsigned *pi = nullptr, *po = nullptr;
+    unsigned long long *k0 = nullptr, *c0 = nullptr, *f0 = nullptr;
+    unsigned *pi = nullptr, *po = nullptr, *h_in = nullptr, *h_sorted = nullptr;
     TRY(dmalloc(c, &k0, m1 * 8));
     TRY(dmalloc(c, &c0, m1 * 8));
     TRY(dmalloc(c, &f0, m1 * 8));
-    TRY(dmalloc(c, &ks, m1 * 8));
+    TRY(dmalloc(c, &h_in, m1 * 4));
+    TRY(dmalloc(c, &h_sorted, m1 * 4));
     TRY(dmalloc(c, &pi, m1 * 4));
     TRY(dmalloc(c, &po, m1 * 4));
     CU(c, cudaMemsetAsync(&c->st->scratch, 0, 8, c->compute));
+    CU(c, cudaMemsetAsync(&c->st->occupied_total, 0, 8, c->compute));  // borrowed: largest `first` received
     if (m) {
         if (m >= (1ULL << 31)) return fail(c, FRB_ERR_ARG, "frb_shardmerge: share too large");
         ProfScope ps(c, FRB_K_EXPORT);
         const unsigned grid = static_cast<unsigned>((m + 255) / 256);
         iota_kernel<<<grid, 256, 0, c->compute>>>(pi, m);
+        hash32_kernel<<<grid, 256, 0, c->compute>>>(got, got + 2 * m, m, h_in, &c->st->occupied_total);
         size_t tmp = 0;
-        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, got, ks, pi, po, static_cast<int>(m), 0, 64, c->compute));
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, h_in, h_sorted, pi, po, static_cast<int>(m), 0, 32, c->compute));
         TRY(ensure_cub_tmp(c, tmp));
-        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, got, ks, pi, po, static_cast<int>(m), 0, 64, c->compute));
-        fold_runs_kernel<<<grid, 256, 0, c->compute>>>(ks, po, got + m, got + 2 * m, m, k0, c0, f0, &c->st->scratch);
-        c->launches += 10;
+        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, h_in, h_sorted, pi, po, static_cast<int>(m), 0, 32, c->compute));
+        fold_hash_runs_kernel<<<grid, 256, 0, c->compute>>>(h_sorted, po, got, got + m, got + 2 * m, m, k0, c0, f0,
+                                                            &c->st->scratch);
+        c->launches += 7;
         CU(c, cudaGetLastError());
     }
-    unsigned long long u = 0;
+    unsigned long long u = 0, max_first = 0;
     CU(c, cudaMemcpyAsync(&u, &c->st->scratch, 8, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaMemcpyAsync(&max_first, &c->st->occupied_total, 8, cudaMemcpyDeviceToHost, c->compute));
     CU(c, cudaStreamSynchronize(c->compute));
     lap("sort by key + fold");
     TRY(dfree(c, own));
     TRY(dfree(c, own_sorted));
     TRY(dfree(c, idx));
     TRY(dfree(c, idx_sorted));
-    TRY(dfree(c, ks));
+    TRY(dfree(c, h_in));
+    TRY(dfree(c, h_sorted));
     TRY(dfree(c, pi));
     TRY(dfree(c, po));
     TRY(device_error_check(c));
     TRY(free_list(c, c->total));
-    TRY(unsorted_to_sorted_list(c, k0, c0, f0, u, &c->total));
+    int first_bits = 1;  // significant bits of (file ordinal << 40 | read ordinal) among what arrived
+    while (first_bits < 64 && (max_first >> first_bits)) ++first_bits;
+    TRY(unsorted_to_sorted_list(c, k0, c0, f0, u, &c->total, first_bits));
     c->merged_upto = c->files.size();
     c->sharded = true;
     lap("sorted share");

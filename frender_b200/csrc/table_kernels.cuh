@@ -13,21 +13,9 @@ __global__ void __launch_bounds__(256) clear_table_kernel(Slot* tab, unsigned lo
         t4[i] = make_ulonglong4(kEmpty, ~0ULL, 0ULL, 0ULL);  // key, first, count, aux
 }
 
-// Number of occupied slots (the unique keys of a file).  The scan kernel does not keep this count: knowing who
-// won a slot would mean waiting for every compare-and-swap's result.
-__global__ void __launch_bounds__(256) count_table_kernel(const Slot* __restrict__ tab, unsigned long long cap,
-                                                          unsigned long long* counter) {
-    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    unsigned n = 0;
-    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < cap;
-         i += stride)
-        n += (tab[i].key != kEmpty && tab[i].count != 0) ? 1u : 0u;  // count 0: taken back by a negate pass
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, d);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, static_cast<unsigned long long>(n));
-}
-
-// Occupied slots -> dense arrays (arbitrary order); *counter receives the number written.  One atomic per
+// Occupied slots (key present, count not taken back to 0 by a negate pass) -> dense arrays in arbitrary order;
+// *counter receives their number (the scan kernel does not keep it: knowing who won a slot would mean waiting for
+// every compare-and-swap's result).  One atomic per
 // block and pass (a per-warp atomic on the one counter was the kernel's bound: 2 M atomics for 2^26 slots).
 __global__ void __launch_bounds__(256) compact_table_kernel(const Slot* __restrict__ tab, unsigned long long cap,
                                                             unsigned long long* __restrict__ keys,
@@ -142,6 +130,59 @@ __global__ void __launch_bounds__(256) fold_runs_kernel(const unsigned long long
             f_out[idx] = mn;
         }
     }
+}
+
+// 32 bits of the key's hash for every entry (what the received parts of a sharded merge are sorted on: four radix
+// passes instead of the eight a 64-bit key takes) and the largest `first` among them (significant bits of the
+// sort by first appearance that follows).
+__global__ void __launch_bounds__(256) hash32_kernel(const unsigned long long* __restrict__ keys,
+                                                     const unsigned long long* __restrict__ first, unsigned long long n,
+                                                     unsigned* __restrict__ h32, unsigned long long* max_first) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    unsigned long long f = 0;
+    if (i < n) {
+        h32[i] = static_cast<unsigned>(hash64(keys[i]) >> 8);
+        f = first[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, f, d);
+        f = o > f ? o : f;
+    }
+    if ((threadIdx.x & 31) == 0 && f) atomicMax(max_first, f);
+}
+
+// Entries sorted by hs = 32 hash bits of their keys (perm = original positions): one output entry per distinct
+// KEY (count: +, first: min), appended in arbitrary order.  A run of equal hash bits holds one key from up to
+// n_ranks parts -- and now and then a second key with the same 32 bits, which is why the keys themselves are
+// compared inside the run.
+__global__ void __launch_bounds__(256) fold_hash_runs_kernel(const unsigned* __restrict__ hs, const unsigned* __restrict__ perm,
+                                                             const unsigned long long* __restrict__ keys,
+                                                             const unsigned long long* __restrict__ counts,
+                                                             const unsigned long long* __restrict__ first,
+                                                             unsigned long long n, unsigned long long* __restrict__ k_out,
+                                                             unsigned long long* __restrict__ c_out,
+                                                             unsigned long long* __restrict__ f_out,
+                                                             unsigned long long* counter) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const unsigned h = hs[i];
+    // this thread speaks for the key at sorted position i if no earlier position of the run holds the same key
+    const unsigned long long key = keys[perm[i]];
+    for (unsigned long long j = i; j > 0 && hs[j - 1] == h; --j)
+        if (keys[perm[j - 1]] == key) return;
+    unsigned long long sum = 0, mn = ~0ULL;
+    for (unsigned long long j = i; j < n && hs[j] == h; ++j) {
+        const unsigned p = perm[j];
+        if (keys[p] != key) continue;
+        sum += counts[p];
+        const unsigned long long f = first[p];
+        mn = f < mn ? f : mn;
+    }
+    const unsigned long long idx = atomicAdd(counter, 1ULL);
+    k_out[idx] = key;
+    c_out[idx] = sum;
+    f_out[idx] = mn;
 }
 
 // Owner rank of a key in the sharded merge: hash bits the table index does not use.
