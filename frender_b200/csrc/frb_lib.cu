@@ -41,6 +41,8 @@ struct KeyList {  // device arrays of one (key,count,first) list
     unsigned long long *keys = nullptr, *counts = nullptr, *first = nullptr;
     uint64_t n = 0, reads = 0;
     uint32_t ordinal = 0;
+    bool sorted = true;   // in first-appearance order (a file's list is sorted when somebody first needs the order)
+    int first_bits = 64;  // significant bits of `first` (passes of that sort)
 };
 
 struct ProfPair {
@@ -309,6 +311,21 @@ int unsorted_to_sorted_list(frb_ctx* c, unsigned long long* k0, unsigned long lo
     return FRB_OK;
 }
 
+// A list that came out of a table in slot order -> first-appearance order, in place.
+int ensure_sorted(frb_ctx* c, KeyList& l) {
+    if (l.sorted || l.n == 0) {
+        l.sorted = true;
+        return FRB_OK;
+    }
+    KeyList tmp = l;
+    KeyList out = l;
+    out.keys = out.counts = out.first = nullptr;
+    TRY(unsorted_to_sorted_list(c, tmp.keys, tmp.counts, tmp.first, tmp.n, &out, l.first_bits));  // frees tmp's arrays
+    out.sorted = true;
+    l = out;
+    return FRB_OK;
+}
+
 // Table -> list sorted by `first`.
 int table_to_sorted_list(frb_ctx* c, Slot* tab, uint64_t n, KeyList* out, int first_bits = 64,
                          const unsigned long long* tile_first = nullptr) {
@@ -353,7 +370,12 @@ int table_to_sorted_list_counting(frb_ctx* c, Slot* tab, uint64_t bound, KeyList
     const uint64_t n = c->st_host->scratch;
     if (n > bound) return fail(c, FRB_ERR_STATE, "more occupied slots (%llu) than reads scanned (%llu)", (unsigned long long)n,
                                (unsigned long long)bound);
-    return unsorted_to_sorted_list(c, k0, c0, f0, n, out, first_bits);
+    // left in slot order: sorted by first appearance when somebody needs the order (ensure_sorted); a sharded
+    // merge does not
+    out->keys = k0, out->counts = c0, out->first = f0, out->n = n;
+    out->sorted = false;
+    out->first_bits = first_bits;
+    return FRB_OK;
 }
 
 int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t line_base, int rule,
@@ -798,7 +820,8 @@ int frb_file_size(frb_ctx* c, uint32_t i, uint64_t* n_unique, uint64_t* n_reads)
     if (n_reads) *n_reads = c->files[i].reads;
     return FRB_OK;
 }
-static int export_list(frb_ctx* c, const KeyList& l, uint64_t* keys, uint64_t* counts, uint64_t* first, uint64_t cap) {
+static int export_list(frb_ctx* c, KeyList& l, uint64_t* keys, uint64_t* counts, uint64_t* first, uint64_t cap) {
+    TRY(ensure_sorted(c, l));
     if (cap < l.n) return fail(c, FRB_ERR_ARG, "export buffer too small (%llu < %llu)", (unsigned long long)cap,
                                (unsigned long long)l.n);
     if (!l.n) return FRB_OK;
@@ -829,15 +852,17 @@ static int merge_pending_files(frb_ctx* c) {  // fold file lists into total_tab 
     return FRB_OK;
 }
 
-int frb_total_finish(frb_ctx* c, uint64_t* n_unique) {
-    CU(c, cudaSetDevice(c->device));
-    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_total_finish: a file is still open");
+// need_order = false: the caller (a sharded merge) regroups the entries anyway
+static int total_build(frb_ctx* c, bool need_order) {
     if (!c->total_ready) {
         TRY(free_list(c, c->total));
         if (c->files.size() == 1 && c->merged_upto == 0 && !c->ext_merged) {
             // one file: "total" is that file's list (F:199-203 degenerates to a copy); only `first`
             // gets the file ordinal in its high bits
-            const KeyList& fl = c->files[0];
+            KeyList& fl = c->files[0];
+            if (need_order) TRY(ensure_sorted(c, fl));
+            c->total.sorted = fl.sorted;
+            c->total.first_bits = 64;
             c->total.n = fl.n;
             if (fl.n) {
                 TRY(dmalloc(c, &c->total.keys, fl.n * 8));
@@ -860,6 +885,14 @@ int frb_total_finish(frb_ctx* c, uint64_t* n_unique) {
         c->total_ready = true;
         c->total_gen++;
     }
+    if (need_order) TRY(ensure_sorted(c, c->total));
+    return FRB_OK;
+}
+
+int frb_total_finish(frb_ctx* c, uint64_t* n_unique) {
+    CU(c, cudaSetDevice(c->device));
+    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_total_finish: a file is still open");
+    TRY(total_build(c, true));
     if (n_unique) *n_unique = c->total.n;
     return FRB_OK;
 }

@@ -179,7 +179,8 @@ int frb_shardmerge(frb_ctx* c, uint64_t* n_unique) {
         fprintf(stderr, "[shardmerge rank %d] %-22s %.3f ms\n", c->rank, what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
-    TRY(frb_total_finish(c, nullptr));
+    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_shardmerge: a file is still open");
+    TRY(total_build(c, false));  // the entries are regrouped by owner: their order does not matter here
     lap("local total");
     if (c->n_ranks <= 1 || !c->nccl_comm) {
         if (n_unique) *n_unique = c->total.n;
