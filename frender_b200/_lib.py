@@ -60,6 +60,9 @@ SIGNATURES = {
     "frb_match": (C.c_int, [vp, u32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "frb_route_load": (C.c_int, [vp, vp, vp, u64, u32]),
     "frb_route_pair": (C.c_int, [vp, vp, u64, vp, u64, C.c_int, vp, vp, vp, vp, P(u64), P(u64), P(u64), P(u64)]),
+    "frb_route_reset": (C.c_int, [vp]),
+    "frb_route_push": (C.c_int, [vp, vp, u64, vp, u64, C.c_int]),
+    "frb_route_pop": (C.c_int, [vp, P(vp), P(vp), vp, vp, P(u64), P(u64), P(u64), P(u64)]),
     "frb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "frb_nccl_init": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int]),
     "frb_allmerge": (C.c_int, [vp, P(u64)]),

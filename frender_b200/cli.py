@@ -560,36 +560,27 @@ class GzSink:
 
 
 class TextChunks:
-    """Decompressed bytes of a fastq.gz with the newline translation of text mode (F:776)."""
+    """Decompressed bytes of a fastq.gz with the newline translation of text mode (F:776), piece by piece."""
 
-    def __init__(self, path, size):
+    def __init__(self, path):
         self.fh = gzip.open(path, "rb")
-        self.size = size
-        self.buf = b""
         self.eof = False
+        self.held = b""            # a trailing "\r": the next byte decides whether it is half of "\r\n"
 
-    def fill(self):
-        while not self.eof and len(self.buf) < self.size:
-            piece = self.fh.read(self.size - len(self.buf))
-            if not piece:
-                self.eof = True
-                break
-            if b"\r" in piece or self.buf.endswith(b"\r"):
-                joined = (self.buf + piece)
-                tail = b"\r" if joined.endswith(b"\r") and not self.eof else b""
-                body = joined[:len(joined) - len(tail)]
-                self.buf = body.replace(b"\r\n", b"\n").replace(b"\r", b"\n") + tail
-            else:
-                self.buf += piece
-        if self.eof and self.buf.endswith(b"\r"):
-            self.buf = self.buf[:-1] + b"\n"
-
-    def take(self):
-        """Bytes up to the last complete line (everything at EOF)."""
-        if self.eof:
-            return len(self.buf)
-        cut = self.buf.rfind(b"\n")
-        return cut + 1
+    def read(self, size):
+        """About `size` bytes (all that is left at the end of the file, where self.eof turns True)."""
+        piece = self.fh.read(max(size - len(self.held), 1))
+        if not piece:
+            self.eof = True
+            out, self.held = self.held.replace(b"\r", b"\n"), b""
+            return out
+        if self.held or b"\r" in piece:
+            piece = self.held + piece
+            self.held = b""
+            if piece.endswith(b"\r"):
+                piece, self.held = piece[:-1], b"\r"
+            piece = piece.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+        return piece
 
 
 def frender_demux(args, ctx=None):
@@ -665,34 +656,43 @@ def frender_demux(args, ctx=None):
             f.result()
         writes.clear()
 
+    def write_out(popped):
+        o1, o2, off1, off2 = popped[:4]
+        if off1[reject + 1] > off1[reject]:
+            raise SystemExit("Unrecognized read type found in supplied frender result file!")
+        drain()                                     # a sink's compress() calls stay in order
+        for s in range(n_sinks):
+            if off1[s + 1] > off1[s]:
+                writes.append(pool.submit(sinks[s]["R1"].write, o1[off1[s]:off1[s + 1]]))
+            if off2[s + 1] > off2[s]:
+                writes.append(pool.submit(sinks[s]["R2"].write, o2[off2[s]:off2[s + 1]]))
+
     try:
         ctx.route_load(keys, routes, n_sinks + 1)
         for r1_path, r2_path in pairs:
             print(f"Demultiplexing {r1_path.name}...")
-            a, b = TextChunks(r1_path, chunk), TextChunks(r2_path, chunk)
-            while True:
-                fills = [pool.submit(a.fill), pool.submit(b.fill)]
-                for f in fills:
-                    f.result()
-                fa, fb = a.eof, b.eof                       # eof: the buffer holds all that is left
-                na, nb = a.take(), b.take()
-                o1, o2, off1, off2, done, used1, used2 = ctx.route_pair(
-                    a.buf[:na], b.buf[:nb], (1 if fa else 0) | (2 if fb else 0))
-                if off1[reject + 1] > off1[reject]:
-                    raise SystemExit("Unrecognized read type found in supplied frender result file!")
-                drain()                                     # a sink's compress() calls stay in order
-                v1, v2 = memoryview(o1), memoryview(o2)
-                for s in range(n_sinks):
-                    if off1[s + 1] > off1[s]:
-                        writes.append(pool.submit(sinks[s]["R1"].write, v1[off1[s]:off1[s + 1]]))
-                    if off2[s + 1] > off2[s]:
-                        writes.append(pool.submit(sinks[s]["R2"].write, v2[off2[s]:off2[s + 1]]))
-                a.buf, b.buf = a.buf[used1:], b.buf[used2:]
-                if (fa and not a.buf) or (fb and not b.buf) or (fa and fb):
-                    break                                   # zip() ends with the shorter mate (F:777)
-                if done == 0:                               # a record longer than the window: widen it
-                    a.size += chunk
-                    b.size += chunk
+            # The pair as a STREAM of chunks, two in flight: while chunk k is routed on the device and chunk k-1
+            # comes back and is deflated, chunk k+1 is inflated.  Chunks are cut anywhere; records that are not
+            # complete yet (and the lead of one mate over the other) are carried on the device.
+            a, b = TextChunks(r1_path), TextChunks(r2_path)
+            ctx.route_reset()
+            flags, carry, over = [], (0, 0), False
+            while not over:
+                want = [max(chunk - c, MIN_CHUNK // 4) for c in carry]   # carry + new bytes stay within the window
+                fills = [pool.submit(a.read, 0 if a.eof else want[0]), pool.submit(b.read, 0 if b.eof else want[1])]
+                da, db = (f.result() for f in fills)
+                flags.append((1 if a.eof else 0) | (2 if b.eof else 0))
+                ctx.route_push(da, db, flags[-1])
+                over = a.eof and b.eof
+                if len(flags) == 2:
+                    popped, was = ctx.route_pop(), flags.pop(0)
+                    write_out(popped)
+                    carry = popped[5:7]
+                    # zip() ends with the shorter mate (F:777): that file is over and nothing of it is left on
+                    # the device (which ignores the chunk that is already queued behind this one)
+                    over = over or bool(was & 1 and carry[0] == 0) or bool(was & 2 and carry[1] == 0)
+            for _ in flags:
+                write_out(ctx.route_pop())
     except FrbError as exc:
         if exc.code == _lib.ERR_KEY_NOT_FOUND:
             raise SystemExit(exc.message)

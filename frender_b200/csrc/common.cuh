@@ -70,6 +70,10 @@ __host__ __device__ __forceinline__ unsigned long long hash64(unsigned long long
     return k;
 }
 
+// Demux parser: kBadKeyBase + (-FRB_ERR_*) in place of a key whose header line did not parse.  Only the router
+// knows whether that record is routed at all (the last record of a chunk may be cut anywhere) and reports it then.
+constexpr unsigned long long kBadKeyBase = ~0ULL - 256ULL;
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void raise_error(DevState* st, int code, unsigned long long pos) {
     if (atomicCAS(&st->err_code, 0, code) == 0) st->err_pos = pos;

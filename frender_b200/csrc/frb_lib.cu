@@ -113,7 +113,7 @@ struct frb_ctx {
     Slot* route_tab = nullptr;
     uint64_t route_cap = 0;
     uint32_t n_sinks = 0;
-    RouteBufs rb;
+    struct RouteStreamHolder* route = nullptr;  // the demux stream (frb_route.inl)
     // device inflate (frb_gz.inl)
     struct GzBuffersHolder* gzbuf = nullptr;
     // synth
@@ -380,7 +380,7 @@ int table_to_sorted_list_counting(frb_ctx* c, Slot* tab, uint64_t bound, KeyList
 
 int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t line_base, int rule,
                 unsigned long long* keys_out, unsigned long long* rec_off_out, Slot* table, uint64_t pos_base,
-                uint64_t out_cap = ~0ULL) {
+                uint64_t out_cap = ~0ULL, const unsigned long long* skip_ptr = nullptr) {
     if (nbytes == 0) return FRB_OK;
     if (reinterpret_cast<uintptr_t>(dev) & 15) return fail(c, FRB_ERR_ARG, "chunk pointer must be 16-byte aligned");
     // FRB_SCAN_SPEC=0: the general (look-back) kernel everywhere -- A/B switch
@@ -413,6 +413,7 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     a.keys_out = keys_out;
     a.rec_off_out = rec_off_out;
     a.out_cap = out_cap;
+    a.skip_ptr = skip_ptr;
     a.n_tiles = static_cast<unsigned>(n_tiles);
     a.rule = rule;
     static const bool no_guess = getenv("FRB_SCAN_NO_GUESS") != nullptr;
@@ -553,10 +554,12 @@ struct GzBuffersHolder {
     GzBuffers b;
 };
 
+static void route_stream_destroy(frb_ctx* c);  // frb_route.inl
+
 // ============================================================================================
 extern "C" {
 
-int frb_version(void) { return 100; }
+int frb_version(void) { return 200; }
 
 int frb_device_count(int* n) {
     cudaError_t e = cudaGetDeviceCount(n);
@@ -630,7 +633,7 @@ void frb_destroy(frb_ctx* c) {
     cudaFree(c->f_sum), cudaFree(c->rc_sum);
     cudaFree(c->m1), cudaFree(c->m2), cudaFree(c->srow), cudaFree(c->m2rc), cudaFree(c->srowrc);
     cudaFree(c->type), cudaFree(c->typerc), cudaFree(c->work), cudaFree(c->work_n), cudaFree(c->cub_tmp), cudaFree(c->route_tab);
-    route_free(c->rb);
+    route_stream_destroy(c);
     if (c->gzbuf) {
         gz_free(c->gzbuf->b);
         delete c->gzbuf;

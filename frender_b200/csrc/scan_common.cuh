@@ -34,6 +34,9 @@ struct ScanArgs {
     unsigned long long* timing;  // optional: per-role clock64 sums (instrumented instantiation only)
     unsigned long long* tile_first;  // speculative path: first read ordinal of every tile of the file
     unsigned long long tile_base;  // speculative path: tiles of this file before the chunk (composite positions)
+    const unsigned long long* skip_ptr;  // device value: bytes at the start of `data` that are not text (the
+                                         // demux stream keeps `data` aligned and puts a carried tail in front)
+    unsigned long long skip;     // ... its value inside the kernels (filled in by them)
     int negate;                  // speculative path: take the chunk's guessed keys out of the table again
     int composite;               // scan_redo_kernel: record composite positions, leave n_reads / line_carry alone
     unsigned int* redo;          // tiles left to scan_redo_kernel, capacity n_tiles
@@ -267,7 +270,7 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
             *start_out = tile_off + sb - kHalo;
         } else {
             unsigned long long s_g = tile_off + eb - kHalo;
-            while (s_g > 0 && a.data[s_g - 1] != '\n') --s_g;
+            while (s_g > a.skip && a.data[s_g - 1] != '\n') --s_g;
             *start_out = s_g;
         }
         *key_out = 0;
@@ -315,7 +318,7 @@ __device__ __forceinline__ int parse_header(const unsigned char* buf, const unsi
         s_g = tile_off + sb - kHalo;
     } else {
         s_g = e_g;
-        while (s_g > 0 && a.data[s_g - 1] != '\n') --s_g;
+        while (s_g > a.skip && a.data[s_g - 1] != '\n') --s_g;
     }
     *start_out = s_g;
     return parse_serial(a.data + s_g, e_g - s_g, rule, key_out);
@@ -411,7 +414,7 @@ __device__ __forceinline__ int header_key(const HeaderRegs& r, const uint4* scra
         s_g = tile_off + r.sb - kHalo;
     } else {
         s_g = e_g;
-        while (s_g > 0 && a.data[s_g - 1] != '\n') --s_g;
+        while (s_g > a.skip && a.data[s_g - 1] != '\n') --s_g;
     }
     return parse_serial(a.data + s_g, e_g - s_g, FRB_RULE_SCAN, key_out);
 }

@@ -102,6 +102,18 @@ __device__ __forceinline__ TileMeta count_tile(const ScanArgs& a, unsigned char*
         if (2 * q + 1 < G::seg) w[q] = eq_mask32_rev(t4[2 * q], t4[2 * q + 1], a.pat_nl);
         else w[q] = eq_mask16_rev_hi(t4[2 * q], a.pat_nl);
     }
+    // bytes in front of a.skip (a carried tail was put in front of an aligned buffer) are not text
+    const long long sk = static_cast<long long>(a.skip) - static_cast<long long>(tile_off);
+    if (sk > 0) {
+        const long long ns = sk - static_cast<long long>(ct) * kWsPerThread;  // bytes of this thread to ignore
+        if (ns > 0) {
+#pragma unroll
+            for (int q = 0; q < kWords; ++q) {
+                const long long n = ns - 32 * q;  // leading bytes of word q to ignore = its top n bits
+                w[q] = n <= 0 ? w[q] : (n >= 32 ? 0u : (w[q] & (0xFFFFFFFFu >> n)));
+            }
+        }
+    }
     {
         const int nv = static_cast<int>(valid) - ct * kWsPerThread;
         if (nv < kWsPerThread) {
@@ -133,7 +145,7 @@ __device__ __forceinline__ TileMeta count_tile(const ScanArgs& a, unsigned char*
     // Thread 32: not the thread that arrives on the mbarrier afterwards
     if (kPublish && ct == 32) status[t] = (t == 0 ? kFlagInc : kFlagAgg) | total;
     // a last line without '\n' still is a line (F:161 iterates it; F:169 rstrip)
-    const unsigned vnl = (t == a.n_tiles - 1 && valid > 0 && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
+    const unsigned vnl = (t == a.n_tiles - 1 && valid > 0 && sk < static_cast<long long>(valid) && buf[kHalo + valid - 1] != '\n') ? 1u : 0u;
     {   // ordered list of newline positions; which of them end header lines is decided later
         unsigned idx = wbase + incl - cnt;
         unsigned pos0 = kHalo + ct * kWsPerThread;
@@ -171,13 +183,20 @@ __device__ __forceinline__ TileMeta count_tile(const ScanArgs& a, unsigned char*
         }
         if (ct == 0 && vnl && total < static_cast<unsigned>(kWsNlCap)) nl[total] = static_cast<uint16_t>(kHalo + valid);
     }
-    unsigned halo_start = kHalo;
-    if (warp == 0 && t != 0) {  // start of the line that straddles the tile start (last newline of the halo)
-        const unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane], a.pat_nl);
+    // start of the line that straddles the tile start: behind the last newline of the halo -- or at a.skip, where
+    // the text begins (in this tile: sk >= 0; inside the halo: -kHalo < sk < 0)
+    unsigned halo_start = kHalo + static_cast<unsigned>(sk > 0 ? sk : 0);
+    if (warp == 0 && t != 0 && sk < 0) {
+        unsigned m = newline_mask16(reinterpret_cast<const uint4*>(buf)[lane], a.pat_nl);
+        const long long text0 = kHalo + sk;  // buffer position of a.skip (<= 0: the whole halo is text)
+        if (text0 > 0) {
+            const long long cut = text0 - lane * 16;  // leading bytes of this lane's segment in front of the text
+            m = cut >= 16 ? 0u : (cut > 0 ? (m & (0xFFFFu << cut)) : m);
+        }
         const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
         const int top = 31 - __clz(any);  // -1: no newline in the halo
         const unsigned mine = lane * 16 + (31 - __clz(m)) + 1;
-        halo_start = any ? __shfl_sync(0xFFFFFFFFu, mine, top & 31) : kUnknown;
+        halo_start = any ? __shfl_sync(0xFFFFFFFFu, mine, top & 31) : (text0 > 0 ? static_cast<unsigned>(text0) : kUnknown);
     }
     group_sync<kWsGroup>(1);  // list complete (also protects s_cwarp)
     unsigned g = kNoGuess;

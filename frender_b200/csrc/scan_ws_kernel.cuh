@@ -23,7 +23,9 @@
 namespace frb {
 
 template <class G>
-__global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_kernel(const ScanArgs a_in) {
+    ScanArgs a = a_in;
+    a.skip = a.skip_ptr ? *a.skip_ptr : 0ULL;
     constexpr int kRule = kRuleRuntime;
     constexpr int kStages = G::stages;
     constexpr int kWsTile = G::tile, kWsBuf = G::buf, kWsNlCap = G::nl_cap, kWsPerThread = G::per_thread;
@@ -239,8 +241,14 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
                             const unsigned j = j0 + 4 * h;
                             const unsigned sb = j ? nl[j - 1] + 1u : halo_start;
                             rc = parse_header<kRule, true>(buf, s_lut, sb, nl[j], a, tile_off, &key, &start_g);
-                            if (rc) key = kEmpty;
-                            else if (!guessed) emit(of + h, key, start_g);
+                            if (rc && a.rule == FRB_RULE_DEMUX && a.keys_out && !a.table) {  // the router decides whether it matters
+                                emit(of + h, kBadKeyBase + static_cast<unsigned long long>(-rc), start_g);
+                                key = kEmpty, rc = 0;
+                            } else if (rc) {
+                                key = kEmpty;
+                            } else if (!guessed) {
+                                emit(of + h, key, start_g);
+                            }
                         }
                         tick(1);
                         const unsigned n = n_owned - h0 < static_cast<unsigned>(kExt) ? n_owned - h0 : kExt;
@@ -399,7 +407,9 @@ __global__ void __launch_bounds__(G::threads) __maxnreg__(G::maxreg) scan_ws_ker
 // not well-formed FASTQ), or more newlines than a tile's position list holds -- tallied strictly by line
 // count, one thread per tile, from the bytes in global memory.  status[] holds every tile's inclusive
 // newline prefix by now.  Slow and exact; the list is empty for ordinary input.
-__global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a_in) {
+    ScanArgs a = a_in;
+    a.skip = a.skip_ptr ? *a.skip_ptr : 0ULL;
     // speculative path: a wrong guess somewhere in the chunk -> every tile is redone (the negate pass took the
     // guessed keys out again); a parse error of a guessed tile stands once all guesses are confirmed
     const bool all = a.composite && a.st->spec_bad;
@@ -416,11 +426,11 @@ __global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
         const unsigned long long off = static_cast<unsigned long long>(t) * a.tile_bytes;
         const unsigned long long end = off + a.tile_bytes < a.nbytes ? off + a.tile_bytes : a.nbytes;
         unsigned long long k = L0 + (t ? (a.status[t] & kValMask) : 0ULL);  // a.status[1 + (t - 1)]
-        unsigned long long prev = off;
-        while (prev > 0 && a.data[prev - 1] != '\n') --prev;
-        const bool vnl = t == a.n_tiles - 1 && end > off && a.data[end - 1] != '\n';
+        unsigned long long prev = off > a.skip ? off : a.skip;
+        while (prev > a.skip && a.data[prev - 1] != '\n') --prev;
+        const bool vnl = t == a.n_tiles - 1 && end > off && end > a.skip && a.data[end - 1] != '\n';
         unsigned long long reads = 0;
-        for (unsigned long long p = off; p <= end; ++p) {
+        for (unsigned long long p = off > a.skip ? off : a.skip; p <= end; ++p) {
             const bool is_end = p < end ? a.data[p] == '\n' : vnl;
             if (!is_end) continue;
             if ((k & 3) == 0 && (k >> 2) < a.read_limit) {
@@ -429,7 +439,13 @@ __global__ void __launch_bounds__(64) scan_redo_kernel(const ScanArgs a) {
                 const unsigned long long pos =
                     a.composite ? (((a.tile_base + t) << kCompositeShift) | reads) : a.pos_base + (k >> 2);
                 ++reads;
-                if (rc) {
+                if (rc && a.rule == FRB_RULE_DEMUX && a.keys_out && !a.table) {
+                    const unsigned long long slot = (k >> 2) - chunk_first_read;
+                    if (slot < a.out_cap) {
+                        if (a.keys_out) a.keys_out[slot] = kBadKeyBase + static_cast<unsigned long long>(-rc);
+                        if (a.rec_off_out) a.rec_off_out[slot] = prev;
+                    }
+                } else if (rc) {
                     raise_error(a.st, rc, k >> 2);
                 } else {
                     if (a.table) table_add(a.table, a.table_mask, key, 1, pos, &a.st->occupied, a.st);

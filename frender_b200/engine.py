@@ -353,6 +353,31 @@ class Context:
         return (o1[:u1.value].tobytes(), o2[:u2.value].tobytes(), off1.astype(np.int64), off2.astype(np.int64),
                 pairs.value, u1.value, u2.value)
 
+    def route_reset(self):
+        """A new stream of chunk pairs begins (frb_route_reset)."""
+        self._ck(lib.frb_route_reset(self._h))
+
+    def route_push(self, r1, r2, final=0):
+        """Queue one chunk pair of the demux stream (frb_route_push): bytes cut anywhere; what is not complete
+        yet is carried on the device.  Returns at once; at most two chunks may be in flight."""
+        a = np.frombuffer(r1, np.uint8)
+        b = np.frombuffer(r2, np.uint8)
+        self._ck(lib.frb_route_push(self._h, _ptr(a), a.size, _ptr(b), b.size, int(final)))
+
+    def route_pop(self):
+        """The oldest chunk in flight (frb_route_pop): (out_r1, out_r2, off_r1, off_r2, pairs, carry_r1, carry_r2).
+        out_m are views of the library's pinned memory, valid until the chunk after next is pushed; sink s of
+        mate m is out_m[off_m[s]:off_m[s+1]]."""
+        o1, o2 = C.c_void_p(), C.c_void_p()
+        off1, off2 = np.zeros(self._n_sinks + 1, np.uint64), np.zeros(self._n_sinks + 1, np.uint64)
+        pairs, c1, c2, bad = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(lib.frb_route_pop(self._h, C.byref(o1), C.byref(o2), _ptr(off1), _ptr(off2), C.byref(pairs),
+                                   C.byref(c1), C.byref(c2), C.byref(bad)))
+        n1, n2 = int(off1[-1]), int(off2[-1])
+        v1 = np.ctypeslib.as_array((C.c_uint8 * max(n1, 1)).from_address(o1.value))[:n1]
+        v2 = np.ctypeslib.as_array((C.c_uint8 * max(n2, 1)).from_address(o2.value))[:n2]
+        return v1, v2, off1.astype(np.int64), off2.astype(np.int64), pairs.value, c1.value, c2.value
+
     # ---- measurement ------------------------------------------------------------------------
     def launches(self):
         return lib.frb_launch_count(self._h)

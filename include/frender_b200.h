@@ -173,6 +173,18 @@ int frb_route_load(frb_ctx* ctx, const uint64_t* keys, const uint32_t* sink_ids,
 int frb_route_pair(frb_ctx* ctx, const void* r1, uint64_t r1_bytes, const void* r2, uint64_t r2_bytes,
                    int final_chunk, void* out_r1, void* out_r2, uint64_t* off_r1, uint64_t* off_r2,
                    uint64_t* n_pairs, uint64_t* consumed_r1, uint64_t* consumed_r2, uint64_t* bad_key);
+/* The same as a STREAM, two chunk pairs in flight: push queues a chunk pair and returns (H2D, kernels and the D2H
+ * of the chunk before run at the same time); the inputs may be cut anywhere -- records that are not complete yet,
+ * and the lead of one mate over the other, are carried on the device into the next chunk.  A stream's chunks may
+ * not be larger than its first one.  final_chunk bit 0 / 1: the R1 / R2 file ends with this chunk.
+ *   frb_route_pop   the oldest chunk in flight: *out_r1 / *out_r2 point into pinned memory of the library (valid
+ *                   until the chunk after next is pushed), sink s of mate m is out_m[off_m[s], off_m[s + 1]);
+ *                   carry_r1 / carry_r2 = bytes pushed so far that are not routed yet.
+ *   frb_route_reset a new stream begins (nothing carried).                                                      */
+int frb_route_reset(frb_ctx* ctx);
+int frb_route_push(frb_ctx* ctx, const void* r1, uint64_t r1_bytes, const void* r2, uint64_t r2_bytes, int final_chunk);
+int frb_route_pop(frb_ctx* ctx, void** out_r1, void** out_r2, uint64_t* off_r1, uint64_t* off_r2, uint64_t* n_pairs,
+                  uint64_t* carry_r1, uint64_t* carry_r2, uint64_t* bad_key);
 
 /* ---- multi-GPU: merge of the per-rank totals over NCCL (NVLink) ------------------------------
  * One process (or thread) per GPU.  Rank 0 makes the id, the host hands it to every rank.
