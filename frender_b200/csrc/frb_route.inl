@@ -13,7 +13,6 @@ struct RouteSlot {
     unsigned char *hout1 = nullptr, *hout2 = nullptr;  // pinned twins of out1 / out2
     unsigned char *hin1 = nullptr, *hin2 = nullptr;    // pinned staging for pageable input
     unsigned long long* sink_off = nullptr;            // device: [2][n_sinks + 1]
-    RouteState* snap = nullptr;                        // device copy of the state when the chunk was done
     unsigned char* hstate = nullptr;                   // pinned: RouteState + sink offsets
     cudaEvent_t copied = nullptr, kernels = nullptr, state_done = nullptr, d2h_done = nullptr;
     uint64_t end1 = 0, end2 = 0;                       // bytes in the chunk buffers (carry area included)
@@ -33,7 +32,7 @@ struct RouteStream {
 
 void route_stream_free(RouteStream& r) {
     for (auto& s : r.slot) {
-        cudaFree(s.in1), cudaFree(s.in2), cudaFree(s.out1), cudaFree(s.out2), cudaFree(s.sink_off), cudaFree(s.snap);
+        cudaFree(s.in1), cudaFree(s.in2), cudaFree(s.out1), cudaFree(s.out2), cudaFree(s.sink_off);
         cudaFreeHost(s.hout1), cudaFreeHost(s.hout2), cudaFreeHost(s.hin1), cudaFreeHost(s.hin2), cudaFreeHost(s.hstate);
         if (s.copied) cudaEventDestroy(s.copied), cudaEventDestroy(s.kernels), cudaEventDestroy(s.state_done), cudaEventDestroy(s.d2h_done);
     }
@@ -64,7 +63,6 @@ int route_stream_ensure(frb_ctx* c, RouteStream& r, size_t bytes, unsigned n_sin
         CU(c, cudaMallocHost(&s.hin1, cap));
         CU(c, cudaMallocHost(&s.hin2, cap));
         CU(c, cudaMalloc(&s.sink_off, 2 * (n_sinks + 1) * 8));
-        CU(c, cudaMalloc(&s.snap, sizeof(RouteState)));
         CU(c, cudaMallocHost(&s.hstate, sizeof(RouteState) + 2 * (n_sinks + 1) * 8));
         CU(c, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&s.kernels, cudaEventDisableTiming));
@@ -78,7 +76,7 @@ int route_stream_ensure(frb_ctx* c, RouteStream& r, size_t bytes, unsigned n_sin
     CU(c, cudaMalloc(&r.sink, r.rec_cap * 4));
     CU(c, cudaMalloc(&r.local1, r.rec_cap * 4));
     CU(c, cudaMalloc(&r.local2, r.rec_cap * 4));
-    CU(c, cudaMalloc(&r.cell, 2ull * n_sinks * r.n_blocks * 8));
+    CU(c, cudaMalloc(&r.cell, (2ull * n_sinks * r.n_blocks + 2ull * n_sinks) * 8));  // + per-sink totals
     RouteState init{};
     init.skip1 = init.skip2 = r.cap;  // nothing carried: the text begins where the host puts the new bytes
     CU(c, cudaMemcpy(r.rs, &init, sizeof init, cudaMemcpyHostToDevice));
@@ -202,11 +200,12 @@ int frb_route_push(frb_ctx* c, const void* r1, uint64_t n1, const void* r2, uint
     }
     {
         ProfScope ps(c, FRB_K_ROUTE);
+        unsigned long long* const tot = r.cell + 2ull * S * r.n_blocks;
         route_plan_kernel<<<1, 32, 0, c->compute>>>(r.rs, c->st, r.off1, r.off2, s.in1, s.in2, s.end1, s.end2, final_chunk,
-                                               r.rec_cap, r.cap);
+                                               r.rec_cap, r.cap, tot, 2 * S);
         route_hist_kernel<<<r.n_blocks, kRouteBlock, 2 * S * sizeof(unsigned), c->compute>>>(
-            c->route_tab, c->route_cap - 1, r.key2, r.off1, r.off2, r.rs, S, r.n_blocks, r.sink, r.local1, r.local2, r.cell);
-        route_scan_kernel<<<2, 1024, 0, c->compute>>>(r.cell, S, r.n_blocks, r.rs, s.sink_off);
+            c->route_tab, c->route_cap - 1, r.key2, r.off1, r.off2, r.rs, S, r.n_blocks, r.sink, r.local1, r.local2, r.cell, tot);
+        route_scan_kernel<<<dim3(S, 2), kRouteBlock, 0, c->compute>>>(r.cell, S, r.n_blocks, r.rs, tot, s.sink_off);
         const int grid = c->sm_count * 8;
         route_copy_kernel<<<grid, 256, 0, c->compute>>>(r.rs, r.sink, r.local1, r.cell, r.n_blocks, r.off1, s.in1, s.out1);
         route_copy_kernel<<<grid, 256, 0, c->compute>>>(r.rs, r.sink, r.local2,
@@ -216,13 +215,12 @@ int frb_route_push(frb_ctx* c, const void* r1, uint64_t n1, const void* r2, uint
         c->launches += 8;
         CU(c, cudaGetLastError());
     }
-    CU(c, cudaMemcpyAsync(s.snap, r.rs, sizeof(RouteState), cudaMemcpyDeviceToDevice, c->compute));
+    // ---- the chunk's state to the host, in stream order behind its kernels (a few hundred bytes; on the D2H stream
+    // it would queue the routed bytes of the chunk before, which frb_route_pop sends there, behind these kernels)
+    CU(c, cudaMemcpyAsync(s.hstate, r.rs, sizeof(RouteState), cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaMemcpyAsync(s.hstate + sizeof(RouteState), s.sink_off, 2 * (S + 1) * 8, cudaMemcpyDeviceToHost, c->compute));
     CU(c, cudaEventRecord(s.kernels, c->compute));
-    // ---- the chunk's state to the host (third stream); the routed bytes follow in frb_route_pop --------------------
-    CU(c, cudaStreamWaitEvent(r.d2h, s.kernels, 0));
-    CU(c, cudaMemcpyAsync(s.hstate, s.snap, sizeof(RouteState), cudaMemcpyDeviceToHost, r.d2h));
-    CU(c, cudaMemcpyAsync(s.hstate + sizeof(RouteState), s.sink_off, 2 * (S + 1) * 8, cudaMemcpyDeviceToHost, r.d2h));
-    CU(c, cudaEventRecord(s.state_done, r.d2h));
+    CU(c, cudaEventRecord(s.state_done, c->compute));
     s.busy = true;
     r.pushed++;
     return FRB_OK;

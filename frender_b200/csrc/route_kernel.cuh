@@ -75,7 +75,9 @@ __global__ void route_grab_kernel(DevState* st, RouteState* rs, int which) {
 __global__ void route_plan_kernel(RouteState* rs, DevState* st, unsigned long long* off1, unsigned long long* off2,
                                   const unsigned char* __restrict__ in1, const unsigned char* __restrict__ in2,
                                   unsigned long long end1, unsigned long long end2, int final_chunk,
-                                  unsigned long long rec_cap, unsigned long long carry_cap) {
+                                  unsigned long long rec_cap, unsigned long long carry_cap, unsigned long long* tot,
+                                  unsigned n_tot) {
+    for (unsigned k = threadIdx.x; k < n_tot; k += blockDim.x) tot[k] = 0;  // per-sink bytes, summed by the histogram
     if (threadIdx.x || blockIdx.x) return;
     rs->error = 0;
     if (rs->done) {  // chunks the host had already queued when the shorter mate ran out
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(kRouteBlock) route_hist_kernel(const Slot* __r
                                                                  RouteState* rs, unsigned n_sinks, unsigned n_blocks,
                                                                  unsigned* __restrict__ sink, unsigned* __restrict__ local1,
                                                                  unsigned* __restrict__ local2,
-                                                                 unsigned long long* __restrict__ cell) {
+                                                                 unsigned long long* __restrict__ cell,
+                                                                 unsigned long long* __restrict__ tot) {
     extern __shared__ unsigned s_acc[];  // [2][n_sinks]
     const unsigned long long n = rs->pairs;
     const unsigned b = blockIdx.x;
@@ -180,56 +183,63 @@ __global__ void __launch_bounds__(kRouteBlock) route_hist_kernel(const Slot* __r
     for (unsigned k = threadIdx.x; k < n_sinks; k += kRouteBlock) {
         cell[static_cast<unsigned long long>(k) * n_blocks + b] = s_acc[k];
         cell[static_cast<unsigned long long>(n_sinks + k) * n_blocks + b] = s_acc[n_sinks + k];
+        if (s_acc[k]) atomicAdd(&tot[k], static_cast<unsigned long long>(s_acc[k]));
+        if (s_acc[n_sinks + k]) atomicAdd(&tot[n_sinks + k], static_cast<unsigned long long>(s_acc[n_sinks + k]));
     }
 }
 
-// Exclusive sum of cell[0, n) per mate (n = n_sinks * n_blocks, sink-major), in place; sink_off[m][s] = start of
-// sink s (n_sinks + 1 entries per mate).  One block per mate: the matrix is small (a few hundred thousand cells).
-__global__ void __launch_bounds__(1024) route_scan_kernel(unsigned long long* cell, unsigned n_sinks, unsigned n_blocks,
-                                                          RouteState* rs, unsigned long long* sink_off) {
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
-    const unsigned mate = blockIdx.x;
-    const unsigned long long used_blocks = (rs->pairs + kRouteBlock - 1) / kRouteBlock;
-    unsigned long long* const c = cell + static_cast<unsigned long long>(mate) * n_sinks * n_blocks;
-    unsigned long long* const so = sink_off + static_cast<unsigned long long>(mate) * (n_sinks + 1);
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
+// Exclusive sum over the (sink, block) matrix of one mate in sink-major order, in place: where every cell starts in
+// the output.  Block (s, mate) takes row s: its base is the sum of the totals of the sinks in front (tot[], summed
+// by the histogram), then the row's used cells are summed 256 at a time.  sink_off[m][s] = start of sink s
+// (n_sinks + 1 entries per mate).
+__global__ void __launch_bounds__(kRouteBlock) route_scan_kernel(unsigned long long* cell, unsigned n_sinks, unsigned n_blocks,
+                                                                 RouteState* rs, const unsigned long long* __restrict__ tot,
+                                                                 unsigned long long* sink_off) {
+    __shared__ unsigned long long s_warp[kRouteBlock / 32];
+    const unsigned s = blockIdx.x, mate = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned s = 0; s < n_sinks; ++s) {
-        if (threadIdx.x == 0) so[s] = s_carry;
-        for (unsigned long long b0 = 0; b0 < used_blocks; b0 += 1024) {
-            const unsigned long long b = b0 + threadIdx.x;
-            const unsigned long long v = b < used_blocks ? c[static_cast<unsigned long long>(s) * n_blocks + b] : 0ull;
-            unsigned long long incl = v;
+    const unsigned long long used_blocks = (rs->pairs + kRouteBlock - 1) / kRouteBlock;
+    unsigned long long* const row = cell + (static_cast<unsigned long long>(mate) * n_sinks + s) * n_blocks;
+    const unsigned long long* const t = tot + static_cast<unsigned long long>(mate) * n_sinks;
+    auto block_scan = [&](unsigned long long v, unsigned long long* total) {  // inclusive sum over the block
+        unsigned long long incl = v;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            if (lane == 31) s_warp[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                unsigned long long wv = s_warp[lane];
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        __syncthreads();  // s_warp of the round before has been read
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long before = 0, all = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, wv, d);
-                    if (lane >= d) wv += o;
-                }
-                s_warp[lane] = wv;
-            }
-            __syncthreads();
-            const unsigned long long base = s_carry + (warp ? s_warp[warp - 1] : 0ull);
-            if (b < used_blocks) c[static_cast<unsigned long long>(s) * n_blocks + b] = base + incl - v;
-            __syncthreads();
-            if (threadIdx.x == 0) s_carry += s_warp[31];
-            __syncthreads();
+        for (int w = 0; w < kRouteBlock / 32; ++w) {
+            const unsigned long long x = s_warp[w];
+            before += w < warp ? x : 0ull;
+            all += x;
+        }
+        *total = all;
+        return incl + before;
+    };
+    unsigned long long mine = 0, base;
+    for (unsigned k = threadIdx.x; k < s; k += kRouteBlock) mine += t[k];
+    block_scan(mine, &base);
+    if (threadIdx.x == 0) {
+        sink_off[static_cast<unsigned long long>(mate) * (n_sinks + 1) + s] = base;
+        if (s == n_sinks - 1) {
+            const unsigned long long end = base + t[s];
+            sink_off[static_cast<unsigned long long>(mate) * (n_sinks + 1) + n_sinks] = end;
+            if (mate == 0) rs->out1 = end;
+            else rs->out2 = end;
         }
     }
-    if (threadIdx.x == 0) {
-        so[n_sinks] = s_carry;
-        if (mate == 0) rs->out1 = s_carry;
-        else rs->out2 = s_carry;
+    for (unsigned long long b0 = 0; b0 < used_blocks; b0 += kRouteBlock) {
+        const unsigned long long b = b0 + threadIdx.x;
+        const unsigned long long v = b < used_blocks ? row[b] : 0ull;
+        unsigned long long total;
+        const unsigned long long incl = block_scan(v, &total);
+        if (b < used_blocks) row[b] = base + incl - v;
+        base += total;
     }
 }
 
