@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-demux", action="store_true")
     ap.add_argument("--workload", default="scan", choices=["scan", "demux"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one lane per GPU; strong: ONE lane, its record chunks dealt to the GPUs")
@@ -155,6 +156,194 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# Demux workload (configs[3]): the record router as a stream, and the reference's demux beside it
+# ------------------------------------------------------------------------------------------------
+DEMUX_PAIRS = 4_000_000         # pairs per GPU and pass (1.5 GB per mate; chunks of 64 MB, two in flight)
+DEMUX_CPU_PAIRS = 50_000        # bounded sample for the reference's demux (gz in -> 387 gz sinks out)
+
+
+def demux_cpu_sample(tmpdir, pairs=DEMUX_CPU_PAIRS):
+    """R1/R2 .fastq.gz of the first `pairs` pairs of the C4 lane and the scan-results CSV of R1 (made by this repo's
+    scan; the reference's parse_results_file wants the columns in the order its demux asserts, F:645-664)."""
+    import contextlib
+    import csv
+    import gzip
+    import io
+
+    from frender_b200 import cli, synth
+    spec = synth.make_spec("C4")
+    paths = []
+    for mate in (1, 2):
+        path = os.path.join(tmpdir, f"Undetermined_S0_L001_R{mate}_001.fastq.gz")
+        with gzip.open(path, "wb", compresslevel=1) as fh:
+            fh.write(synth.generate_big(spec, 0, pairs, mate))
+        paths.append(path)
+    sheet = os.path.join(tmpdir, "SampleSheet.csv")
+    idx = spec.indexes()
+    with open(sheet, "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["Sample_ID", "index", "index2"])
+        w.writerows(zip(idx["id"], idx["idx1"], idx["idx2"]))
+    cwd = os.getcwd()
+    os.chdir(tmpdir)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            cli.main(["scan", "-n", str(N_SUBS), "-rc", "-b", sheet, "-o", "bench", paths[0]])
+        made = [f for f in os.listdir(tmpdir) if f.startswith("frender-scan-results_")][0]
+    finally:
+        os.chdir(cwd)
+    rows = list(csv.reader(open(os.path.join(tmpdir, made), newline="")))
+    head = rows[0]
+    order = [head.index(c) for c in ["idx1", "idx2", "reads", "matched_idx1", "matched_idx2", "read_type", "sample_name",
+                                     "demux_ok"]]
+    res = os.path.join(tmpdir, "results.csv")
+    with open(res, "w", newline="") as fh:
+        csv.writer(fh).writerows([[r[i] for i in order] for r in rows])
+    return paths, res
+
+
+def demux_cpu_step(paths, res, outdir, ref):
+    """The reference's frender_demux (F:733-814) on the sample files, or -- without baseline/_ref -- this repo's
+    oracle port of it with the same gzip sinks.  Returns seconds."""
+    import argparse
+    import contextlib
+    import gzip
+    import io
+    t0 = time.perf_counter()
+    if ref is not None:
+        ns = argparse.Namespace(no_index_hop=False, no_ambiguous=False, no_undeter=False, no_samples=False, o=None,
+                                d=outdir, r=res, files=list(paths))
+        ref.args = ns                                                    # open_files reads a global (F:672)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref.frender_demux(ns)
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import frender_oracle as O
+        table = O.parse_results_file(res)
+        os.makedirs(outdir, exist_ok=True)
+        for name, (a, b) in O.demux_files(paths[0], paths[1], table, O.sink_names(table)).items():
+            for mate, data in (("R1", a), ("R2", b)):
+                with gzip.open(os.path.join(outdir, f"{name}_{mate}.fastq.gz"), "wb") as fh:
+                    fh.write(data)
+    return time.perf_counter() - t0
+
+
+def demux_cli_step(paths, res, outdir):
+    """This repo's `demux` on the same files: host inflate -> device router -> host deflate.  Returns seconds."""
+    import contextlib
+    import io
+
+    from frender_b200 import cli
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        cli.main(["demux", "-r", res, "-d", outdir] + list(paths))
+    return time.perf_counter() - t0
+
+
+def demux_files_equal(dir_a, dir_b):
+    import gzip
+    import hashlib
+    names = sorted(os.listdir(dir_a))
+    if names != sorted(os.listdir(dir_b)):
+        return False
+    digest = lambda p: hashlib.sha256(gzip.open(p, "rb").read()).hexdigest()
+    return all(digest(os.path.join(dir_a, n)) == digest(os.path.join(dir_b, n)) for n in names)
+
+
+def demux_cpu_baseline(with_cli=True):
+    cores = len(os.sched_getaffinity(0))
+    ref = load_reference()
+    with tempfile.TemporaryDirectory() as d:
+        paths, res = demux_cpu_sample(d)
+        t_ref = demux_cpu_step(paths, res, os.path.join(d, "out_ref"), ref)
+        out = {"value": DEMUX_CPU_PAIRS / t_ref, "unit": "pairs/s", "cores": 1,
+               "kind": "reference" if ref is not None else "port",
+               "sample": f"frender_demux on the first {DEMUX_CPU_PAIRS} pairs of the C4 lane: R1/R2 .fastq.gz in, 387 "
+                         f".fastq.gz sinks out (gzip level 9, as the reference opens them), one process as the "
+                         f"reference runs it ({cores} cores on the box)"}
+        if with_cli:
+            t_cli = demux_cli_step(paths, res, os.path.join(d, "out_b200"))
+            out["same_files_through_this_repo"] = {
+                "pairs_per_s": DEMUX_CPU_PAIRS / t_cli, "threads": cores,
+                "what": "frender_b200 demux on the same files (host inflate, device router, host deflate at level 9)",
+                "sinks_identical_after_gunzip": demux_files_equal(os.path.join(d, "out_ref"), os.path.join(d, "out_b200"))}
+    return out
+
+
+def run_demux(args):
+    """--workload demux: configs[3] through the record router.  value = pairs/s by the device's own time (parser of
+    both mates + router), e2e = the same stream from pinned host buffers to pinned host buffers."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cpu = demux_cpu_baseline(with_cli=False)
+            print(json.dumps({"impl": "reference", "metric": "record_pairs_per_s_demuxed", "value": cpu["value"],
+                              "unit": "pairs/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                              "ms_per_step": 1e3 * DEMUX_CPU_PAIRS / cpu["value"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic",
+                              "config": demux_config(args.reads or DEMUX_PAIRS, args.gpus), "cpu_baseline": cpu,
+                              "e2e": {"value": cpu["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bench_demux import measure
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    pairs = args.reads or DEMUX_PAIRS
+    sampler = Clocks(local) if rank == 0 else None
+    if dist:
+        dist.barrier()
+    m = measure(local, pairs, 64, args.steps, args.warmup)
+    clk = sampler.stop() if sampler else None
+    parts = [m]
+    if dist:
+        parts = [None] * world
+        dist.all_gather_object(parts, m)
+    if rank == 0:
+        kernel_ms = max(p["kernel_ms"] for p in parts)
+        pass_ms = max(p["ms_per_pass_host_to_host"] for p in parts)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peaks = {"sustained": json.load(open(peaks_path))["hbm_gbs"], "source": "MEASURED_PEAKS.json hbm_gbs (measured copy)"}
+        else:
+            peaks = {"sustained": 6650.0, "source": "fallback of B200_PROFILING.md"}
+        moved = sum(p["algorithmic_bytes"] for p in parts)
+        ach = m["algorithmic_bytes"] / (m["kernel_ms"] * 1e-3) / 1e9
+        line = {"metric": "record_pairs_per_s_demuxed", "value": world * pairs / (kernel_ms * 1e-3), "unit": "pairs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64",
+                "data": "synthetic (device-generated R1/R2 of the C4 lane, pulled to pinned host memory)",
+                "config": demux_config(pairs, world), "clocks": clk,
+                "e2e": {"value": world * pairs / (pass_ms * 1e-3), "unit": "pairs/s",
+                        "h2d_bytes_per_step": moved // 2, "d2h_bytes_per_step": moved // 2,
+                        "what": "frb_route_push / frb_route_pop from pinned host buffers to pinned host buffers, "
+                                "64 MB chunks cut at fixed byte counts, two in flight; no gzip on either side",
+                        "gbs_in_plus_out_per_gpu": m["host_to_host_gbs_in_plus_out"]},
+                "gpu_launches": m["gpu_launches_per_pass"],
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["sustained"], "unit": "GB/s",
+                             "frac": ach / peaks["sustained"], "traffic": None,
+                             "what": "parser (both mates) + router kernels together: algorithmic bytes 2 x (R1 + R2) "
+                                     "per pass over their summed event time (rank 0); launched per 64 MB chunk, so "
+                                     "launch tails count", "peak_source": peaks["source"]},
+                "checked": m["checked"], "parser_ms": m["parser_ms"], "router_ms": m["router_ms"],
+                "cpu_baseline": None if args.no_cpu or world > 1 else demux_cpu_baseline()}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def demux_config(pairs_per_gpu, n_gpus):
+    return {"workload": "demux -r of a paired R1/R2 synthetic NovaSeq lane (10+10 bp UDI, 384-sample sheet) into 384 "
+                        "sample sinks + Index-hop + Ambiguous + Undetermined (BASELINE.json configs[3], bounded to what a "
+                        "few seconds of PCIe traffic hold)", "pairs_per_gpu": pairs_per_gpu,
+            "pairs_total": pairs_per_gpu * n_gpus, "sharding": "one lane per GPU, outputs rank-local",
+            "l2": "inputs far larger than L2 (1.5 GB per mate)"}
 
 
 def workload_config(reads_per_gpu, n_gpus):
@@ -607,9 +796,16 @@ def run_b200(args):
             "unique_keys": n_uniq.value, "input_bytes_per_gpu": nbytes, "gen_s": t_gen,
             "kernel_only_reads_per_s_per_gpu": reads / (scan_ms_per * 1e-3),
         }
-        print(json.dumps(line))
     ck(lib.frb_dev_free(h, dbuf))
     ctx.close()
+    if rank == 0:
+        if world == 1 and not args.no_demux:
+            # configs[3] beside the headline: the record router as a stream (python bench.py --workload demux is
+            # the full line for it, with the reference's demux timed beside)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from bench_demux import measure
+            line["demux"] = measure(local, DEMUX_PAIRS, 64, 2, 1)
+        print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
 
@@ -621,7 +817,9 @@ def main():
         del os.environ["NCCL_DEBUG"]
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload == "demux":
+        run_demux(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
