@@ -18,3 +18,5 @@ except Exception as e:
 PY
 tail -3 gpurun_out/bench_${N}gpu_$sc.err
 done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus $N --steps 3 --warmup 3 --workload demux > gpurun_out/bench_${N}gpu_demux.json 2> gpurun_out/bench_${N}gpu_demux.err; echo "bench demux rc $?"
+cut -c1-400 gpurun_out/bench_${N}gpu_demux.json; tail -3 gpurun_out/bench_${N}gpu_demux.err
