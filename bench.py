@@ -268,7 +268,7 @@ def demux_cpu_baseline(with_cli=True):
             t_cli = demux_cli_step(paths, res, os.path.join(d, "out_b200"))
             out["same_files_through_this_repo"] = {
                 "pairs_per_s": DEMUX_CPU_PAIRS / t_cli, "threads": cores,
-                "what": "frender_b200 demux on the same files (host inflate, device router, host deflate at level 9)",
+                "what": "frender_b200 demux on the same files (host inflate threads, device router stream, host deflate threads at the CLI's default level 6; includes creating the CUDA context)",
                 "sinks_identical_after_gunzip": demux_files_equal(os.path.join(d, "out_ref"), os.path.join(d, "out_b200"))}
     return out
 

@@ -160,7 +160,9 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         plan.emplace_back(off, take);
         off += take;
     }
-    TRY(gz_ensure(c, b, g, plan.size() > 1 ? piece + piece / 2 : piece));
+    uint64_t largest = 0;
+    for (const auto& p : plan) largest = std::max(largest, p.second);
+    TRY(gz_ensure(c, b, g, static_cast<size_t>((largest + 3) & ~3ull)));
     unsigned char head[1024];
     const size_t got_head = fread(head, 1, sizeof head, fh);
     const size_t hdr = gz_host_header(head, got_head);

@@ -475,8 +475,6 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
         CU(c, cudaMemsetAsync(&c->st->spec_err_pos, 0, 16, c->compute));  // spec_err_pos, spec_err_code, spec_bad
         {
             ProfScope ps(c, FRB_K_SCAN);
-            static const bool ring = getenv("FRB_SCAN_KERNEL") && strcmp(getenv("FRB_SCAN_KERNEL"), "ring") == 0;
-            static const bool regs_b = getenv("FRB_WS_REGS") && atoi(getenv("FRB_WS_REGS")) == 48;
             if (probe) scan_spec_kernel<WsTile, true><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
             else scan_spec_kernel<WsTile><<<grid, WsTile::threads, WsTile::smem, c->compute>>>(a);
         }

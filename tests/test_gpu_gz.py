@@ -53,6 +53,24 @@ def test_inflate_across_pieces(ctx, tmp_path, monkeypatch):
     assert ctx.gz_inflate(p, len(data) + 1024) == data
 
 
+def test_inflate_file_between_one_and_one_and_a_half_pieces(ctx, tmp_path, monkeypatch):
+    """Such a file is ONE piece, larger than the nominal piece size (the buffers must follow the plan)."""
+    monkeypatch.setenv("FRB_GZ_PIECE_MB", "1")
+    n = 20_000
+    while True:
+        data = fastq(n, seed=9)
+        blob = gzip.compress(data, 6, mtime=0)
+        if len(blob) <= (1 << 20) + 65536:
+            n = n * 5 // 4
+        elif len(blob) >= (3 << 19) - 65536:
+            n = n * 9 // 10
+        else:
+            break
+    p = tmp_path / "c.fastq.gz"
+    p.write_bytes(blob)
+    assert ctx.gz_inflate(p, len(data) + 1024) == data
+
+
 def test_inflate_members_and_odd_streams(ctx, tmp_path):
     rnd = random.Random(7)
     text = fastq(4000, seed=9)
