@@ -583,6 +583,82 @@ class TextChunks:
         return piece
 
 
+def _demux_worker(rank, device, jobs, opts, out_dir, threads, conn):
+    """One process per GPU: the file pairs `jobs` = [(ordinal, r1, r2)], each into its own part directory."""
+    try:
+        os.environ["FRENDER_DEVICE"] = str(device)
+        os.environ["FRENDER_GPUS"] = "1"
+        os.environ["FRENDER_DEMUX_THREADS"] = str(threads)
+        ctx = Context(device, table_log2=12)
+        try:
+            for ordinal, r1, r2 in jobs:
+                ns = argparse.Namespace(**opts, files=[str(r1), str(r2)], d=f"{out_dir}.part{ordinal}")
+                frender_demux(ns, ctx=ctx)
+        finally:
+            ctx.close()
+        conn.send(("ok", None))
+    except SystemExit as exc:
+        conn.send(("error", str(exc)))
+    except BaseException as exc:
+        conn.send(("error", repr(exc)))
+    finally:
+        conn.close()
+
+
+def demux_pairs_multi_gpu(args, pairs, n_gpus, out_dir, worker=_demux_worker):
+    """FRENDER_GPUS=N with several R1/R2 pairs (lanes): pair i is routed on GPU i % N into rank-local part files
+    (the demux outputs stay rank-local); the parts of every sink are then appended in pair order --
+    gzip members one after the other, so every sink decompresses to exactly what the sequential loop over the
+    pairs (F:774) writes."""
+    import multiprocessing as mp
+    import shutil
+    from multiprocessing.connection import wait
+
+    from .shard import assign
+    mpc = mp.get_context("spawn")
+    opts = {k: getattr(args, k) for k in ("no_index_hop", "no_ambiguous", "no_undeter", "no_samples", "o", "r")}
+    jobs = [(i, r1, r2) for i, (r1, r2) in enumerate(pairs)]
+    threads = max(2, len(os.sched_getaffinity(0)) // n_gpus)
+    procs, pipes = [], []
+    for rank in range(n_gpus):
+        parent, child = mpc.Pipe(duplex=False)
+        p = mpc.Process(target=worker, args=(rank, rank, assign(jobs, rank, n_gpus), opts, out_dir, threads, child))
+        p.start()
+        child.close()
+        procs.append(p)
+        pipes.append(parent)
+    failure = None
+    pending = set(range(n_gpus))
+    while pending and failure is None:
+        ready = wait([pipes[r] for r in pending] + [procs[r].sentinel for r in pending])
+        for r in list(pending):
+            if pipes[r] in ready or (procs[r].sentinel in ready and pipes[r].poll()):
+                try:
+                    status, payload = pipes[r].recv()
+                except EOFError:
+                    status, payload = "error", "exited without a result"
+                if status != "ok":
+                    failure = f"GPU worker {r} failed: {payload}"
+                pending.discard(r)
+            elif procs[r].sentinel in ready:
+                failure = f"GPU worker {r} exited without a result"
+                pending.discard(r)
+    for p in procs:
+        if failure is not None and p.is_alive():
+            p.terminate()
+        p.join()
+    if failure is not None:
+        raise SystemExit(failure)
+    parts = [f"{out_dir}.part{i}" for i in range(len(pairs))]
+    for name in sorted(os.listdir(parts[0])):
+        with open(out_dir + name, "wb") as out:
+            for part in parts:
+                with open(os.path.join(part, name), "rb") as src:
+                    shutil.copyfileobj(src, out, 1 << 22)
+    for part in parts:
+        shutil.rmtree(part)
+
+
 def frender_demux(args, ctx=None):
     index_hop, ambiguous = not args.no_index_hop, not args.no_ambiguous
     undeter, samples = not args.no_undeter, not args.no_samples
@@ -595,8 +671,23 @@ def frender_demux(args, ctx=None):
     if (not ids) and samples:
         print("Warning: no demuxable sample ids found in the supplied frender result file!")
 
+    if len(args.files) == 1:
+        target = Path(args.files[0])
+        if target.is_dir():
+            files = {"dir": target}
+        elif target.is_file():
+            files = {"file": target}
+        else:
+            raise SystemExit("Specified directory or file path doesn't seem to exist!")
+    else:
+        files = {"file": [Path(f) for f in args.files]}
+    pairs = get_paired_files(parse_files(files, just_r1=False))
+
     out_dir = args.d if args.d.endswith("/") else args.d + "/"
     os.mkdir(args.d)                                                            # FileExistsError as in F:755
+    n_gpus = int(os.environ.get("FRENDER_GPUS", "1"))
+    if ctx is None and n_gpus > 1 and len(pairs) > 1:
+        return demux_pairs_multi_gpu(args, pairs, min(n_gpus, len(pairs)), out_dir)
     level = int(os.environ.get("FRENDER_GZIP_LEVEL", "6"))
     infix = args.o + "_" if args.o else ""
     sink_names = []                                                             # sink id -> name
@@ -627,18 +718,6 @@ def frender_demux(args, ctx=None):
 
     keys = pack_keys(list(table.keys()))
     routes = np.array([route_of(*v) for v in table.values()], np.uint32)
-
-    if len(args.files) == 1:
-        target = Path(args.files[0])
-        if target.is_dir():
-            files = {"dir": target}
-        elif target.is_file():
-            files = {"file": target}
-        else:
-            raise SystemExit("Specified directory or file path doesn't seem to exist!")
-    else:
-        files = {"file": [Path(f) for f in args.files]}
-    pairs = get_paired_files(parse_files(files, just_r1=False))
 
     own_ctx = ctx is None
     ctx = ctx or Context(int(os.environ.get("FRENDER_DEVICE", "0")), table_log2=12)

@@ -172,3 +172,82 @@ def test_multi_gpu_worker_failure_ends_the_job(monkeypatch):
     monkeypatch.setattr(cli.Context, "nccl_unique_id", staticmethod(lambda: b"\0" * 128))
     with pytest.raises(SystemExit, match="GPU worker 1 failed: .*bad header"):
         cli.scan_files_multi_gpu(["a", "b", "c"], None, 2, 12, worker=_failing_worker)
+
+
+def _stub_demux_worker(rank, device, jobs, opts, out_dir, threads, conn):
+    """Stands in for cli._demux_worker without a GPU: writes one gzip member per sink and pair."""
+    import gzip
+    try:
+        for ordinal, r1, r2 in jobs:
+            if "bad" in str(r1):
+                raise SystemExit("Couldn't find barcode GGGG+TTTT in supplied frender result file!")
+            os.mkdir(f"{out_dir}.part{ordinal}")
+            for sink in ("S1_frender-demux_R1.fq.gz", "Undetermined_frender-demux_R1.fq.gz"):
+                with open(os.path.join(f"{out_dir}.part{ordinal}", sink), "wb") as fh:
+                    fh.write(gzip.compress(f"{sink}:{ordinal}:{os.path.basename(str(r1))}\n".encode() if "S1" in sink or ordinal == 1
+                                           else b""))
+        conn.send(("ok", None))
+    except SystemExit as exc:
+        conn.send(("error", str(exc)))
+    finally:
+        conn.close()
+
+
+def test_multi_gpu_demux_appends_the_parts_in_pair_order(tmp_path):
+    """Pair i goes to rank i % N; every sink is the parts of all pairs in pair order (gzip members), the part
+    directories are gone afterwards; a failing rank ends the job with its message."""
+    import argparse
+    import gzip
+    import frender_b200.cli as cli
+    out = str(tmp_path / "out") + "/"
+    os.mkdir(out)
+    ns = argparse.Namespace(no_index_hop=False, no_ambiguous=False, no_undeter=False, no_samples=False, o=None, r="r.csv")
+    pairs = [(f"L00{i}_R1_001.fastq.gz", f"L00{i}_R2_001.fastq.gz") for i in range(1, 6)]
+    cli.demux_pairs_multi_gpu(ns, pairs, 2, out, worker=_stub_demux_worker)
+    assert sorted(os.listdir(out)) == ["S1_frender-demux_R1.fq.gz", "Undetermined_frender-demux_R1.fq.gz"]
+    got = gzip.open(out + "S1_frender-demux_R1.fq.gz", "rb").read().decode().splitlines()
+    assert got == [f"S1_frender-demux_R1.fq.gz:{i}:L00{i + 1}_R1_001.fastq.gz" for i in range(5)]
+    assert gzip.open(out + "Undetermined_frender-demux_R1.fq.gz", "rb").read() == \
+        b"Undetermined_frender-demux_R1.fq.gz:1:L002_R1_001.fastq.gz\n"
+    out2 = str(tmp_path / "out2") + "/"
+    os.mkdir(out2)
+    with pytest.raises(SystemExit, match="GPU worker 1 failed: Couldn't find barcode GGGG\\+TTTT"):
+        cli.demux_pairs_multi_gpu(ns, [("a_R1", "a_R2"), ("bad_R1", "bad_R2")], 2, out2, worker=_stub_demux_worker)
+
+
+@pytest.mark.gpu
+def test_cli_demux_pairs_on_two_gpus(tmp_path, monkeypatch):
+    """FRENDER_GPUS=2 with three lane pairs: every sink decompresses to what the one-GPU run writes."""
+    import ctypes
+    import gzip
+    import json
+    from conftest import GOLDEN_DIR, unb64
+    from frender_b200 import synth
+    from frender_b200._lib import lib
+    from frender_b200.cli import main
+    n = ctypes.c_int()
+    lib.frb_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs >= 2 GPUs")
+    gold = json.load(open(os.path.join(GOLDEN_DIR, "golden.json")))
+    case = gold["demux"]["c1"]
+    scan = gold["scan"][case["scan_case"]]
+    spec = synth.make_spec(scan["config"], n_samples=scan["n_samples"])
+    files = []
+    for lane, (g0, g1) in enumerate([(0, 1200), (1200, 2100), (2100, 3000)], start=1):
+        for mate in (1, 2):
+            p = tmp_path / f"Undetermined_S0_L00{lane}_R{mate}_001.fastq.gz"
+            p.write_bytes(gzip.compress(synth.generate_big(spec, g0, g1, mate), 1))
+            files.append(str(p))
+    (tmp_path / "results.csv").write_bytes(unb64(case["results_csv"]))
+    main(["demux", "-r", str(tmp_path / "results.csv"), "-d", str(tmp_path / "one")] + files)
+    monkeypatch.setenv("FRENDER_GPUS", "2")
+    main(["demux", "-r", str(tmp_path / "results.csv"), "-d", str(tmp_path / "two")] + files)
+    names = sorted(os.listdir(tmp_path / "one"))
+    assert names == sorted(os.listdir(tmp_path / "two")) == sorted(case["sinks"])
+    for name in names:
+        assert gzip.open(tmp_path / "one" / name, "rb").read() == gzip.open(tmp_path / "two" / name, "rb").read(), name
+    # the three lanes are the golden case's reads in order: the sinks are the golden sinks
+    import hashlib
+    for name, want in case["sinks"].items():
+        assert hashlib.sha256(gzip.open(tmp_path / "two" / name, "rb").read()).hexdigest() == want["sha256"], name
