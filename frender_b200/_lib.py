@@ -58,6 +58,7 @@ SIGNATURES = {
     "frb_resize_tables": (C.c_int, [vp, u32]),
     "frb_sheet_load": (C.c_int, [vp, vp, vp, vp, u32, u32, u32]),
     "frb_match": (C.c_int, [vp, u32, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "frb_demux_ok": (C.c_int, [vp, vp, u32, vp, vp, vp, vp, vp, P(i32)]),
     "frb_route_load": (C.c_int, [vp, vp, vp, u64, u32]),
     "frb_route_pair": (C.c_int, [vp, vp, u64, vp, u64, C.c_int, vp, vp, vp, vp, P(u64), P(u64), P(u64), P(u64)]),
     "frb_route_reset": (C.c_int, [vp]),

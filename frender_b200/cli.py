@@ -312,36 +312,39 @@ def scan_files_multi_gpu(files, sample, n_gpus, table_log2, worker=_scan_worker)
     return per_file, total
 
 
-def demux_ok_flags(tables, read_type, sample_row, sheet_ids, prefix):
-    """demux_ok per unique key and the set of files holding a key they should not (F:504-564).
-    The class x file match matrix uses the reference's own regexes (sample name as a pattern)."""
-    files = tables.file_names
-    n = len(tables.keys)
-    fixed = [re.compile("undetermined", re.I), re.compile("undetermined|index-hop", re.I), None,
-             re.compile("undetermined|ambiguous", re.I)]
-    ok = np.ones(n, bool)
-    bad_files = set()
-    order = np.argsort(tables.keys, kind="stable")
-    sorted_keys = tables.keys[order]
-    name_match = {}
+def class_file_matrix(files, sheet_ids, prefix):
+    """uint8 [(4 + sheet rows), files]: does the NAME of file f fit keys of class c (read type 0/1/3, or 4 + sample
+    row for demuxable keys)?  The reference's own regexes (sample name as a pattern, F:521-550), evaluated once per
+    class and file; 2 = the sample name is not a valid pattern."""
+    fixed = {0: re.compile("undetermined", re.I), 1: re.compile("undetermined|index-hop", re.I),
+             3: re.compile("undetermined|ambiguous", re.I)}
+    match = np.zeros((4 + len(sheet_ids), len(files)), np.uint8)
+    patterns = {}
     for f, fname in enumerate(files):
-        fkeys, fcounts = tables.files[f]
-        fkeys = fkeys[fcounts > 0]
-        idx = order[np.searchsorted(sorted_keys, fkeys)]
-        cls = read_type[idx]
-        match = np.zeros(len(idx), bool)
-        for t in (0, 1, 3):
-            match[cls == t] = bool(fixed[t].search(fname))
-        dem = np.flatnonzero(cls == 2)
-        for row in np.unique(sample_row[idx[dem]]):
-            name = sheet_ids[row]
-            if (name, fname) not in name_match:
-                name_match[(name, fname)] = bool(re.search(re.compile(name.removeprefix(prefix), re.I), fname))
-            match[dem[sample_row[idx[dem]] == row]] = name_match[(name, fname)]
-        ok[idx[~match]] = False
-        if (~match).any():
-            bad_files.add(fname)
-    return ok, bad_files
+        for t, pat in fixed.items():
+            match[t, f] = bool(pat.search(fname))
+        for row, name in enumerate(sheet_ids):
+            if name not in patterns:
+                try:
+                    patterns[name] = re.compile(name.removeprefix(prefix), re.I)
+                except re.error:
+                    patterns[name] = None                  # only an error if such a key really sits in a file
+            pat = patterns[name]
+            match[4 + row, f] = 2 if pat is None else bool(pat.search(fname))
+    return match
+
+
+def demux_ok_flags(ctx, tables, sheet_ids, prefix):
+    """demux_ok per unique key and the set of files holding a key they should not (F:504-564): the class x file
+    matrix from the host, the reduction over the unique keys of every file on the device (frb_demux_ok) against
+    the last classification."""
+    files = tables.file_names
+    if not files:
+        return np.ones(len(tables.keys), bool), set()
+    ok, bad, err_row = ctx.demux_ok(class_file_matrix(files, sheet_ids, prefix), tables.files)
+    if err_row is not None:
+        re.compile(sheet_ids[err_row].removeprefix(prefix), re.I)   # raises what the reference's re.search raises
+    return ok, {files[f] for f in np.flatnonzero(bad)}
 
 
 def report_rc_call_info(rc_calls, indexes, out_csv_name):
@@ -483,7 +486,7 @@ def frender_scan(args, ctx=None):
         res = ctx.match(num_subs, False, use)
 
         # ---- demux_ok + CSV (F:632-642) --------------------------------------------------------
-        ok, bad_files = demux_ok_flags(tables, res["type"], res["srow"], sheet.ids, prefix)
+        ok, bad_files = demux_ok_flags(ctx, tables, sheet.ids, prefix)
         if bad_files:
             print("Incorrectly demultiplexed barcodes found! Affected files:")
             for f in sorted(bad_files):

@@ -1327,6 +1327,90 @@ int frb_match(frb_ctx* c, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_ro
     return device_error_check(c);
 }
 
+// demux_ok per unique key of the total list + which files hold a key they should not (F:504-564), on the device.
+// match: (4 + sheet rows) x n_files bytes made by the host with the reference's regexes; file_keys == NULL: the
+// per-file lists of this context (n_files == files scanned); else host arrays (file lists that live elsewhere:
+// other ranks, other streams).  Needs the classification of the LAST frb_match over the current total list.
+int frb_demux_ok(frb_ctx* c, const uint8_t* match, uint32_t n_files, const uint64_t* const* file_keys,
+                 const uint64_t* const* file_counts, const uint64_t* file_n, uint8_t* ok_out, uint8_t* bad_files_out,
+                 int32_t* err_row_out) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->total_ready) return fail(c, FRB_ERR_STATE, "frb_demux_ok: no total list");
+    const uint64_t n = c->total.n;
+    if (n > c->match_cap || c->m1_total_gen != c->total_gen)
+        return fail(c, FRB_ERR_STATE, "frb_demux_ok: frb_match over the current total list first");
+    if (!file_keys && n_files != c->files.size()) return fail(c, FRB_ERR_ARG, "frb_demux_ok: %u files, context holds %zu", n_files, c->files.size());
+    if (err_row_out) *err_row_out = 0x7FFFFFFF;
+    if (n_files) memset(bad_files_out, 0, n_files);
+    if (!n || !n_files) return FRB_OK;
+    const size_t classes = 4 + static_cast<size_t>(c->rows);
+    unsigned long long* sorted_keys = nullptr;
+    unsigned *i0 = nullptr, *i1 = nullptr;
+    unsigned char *d_match = nullptr, *d_ok = nullptr, *d_bad = nullptr;
+    int* d_err = nullptr;
+    TRY(dmalloc(c, &sorted_keys, n * 8));
+    TRY(dmalloc(c, &i0, n * 4));
+    TRY(dmalloc(c, &i1, n * 4));
+    TRY(dmalloc(c, &d_match, classes * n_files));
+    TRY(dmalloc(c, &d_ok, n));
+    TRY(dmalloc(c, &d_bad, n_files));
+    TRY(dmalloc(c, &d_err, 4));
+    CU(c, cudaMemcpyAsync(d_match, match, classes * n_files, cudaMemcpyHostToDevice, c->compute));
+    CU(c, cudaMemsetAsync(d_ok, 1, n, c->compute));
+    CU(c, cudaMemsetAsync(d_bad, 0, n_files, c->compute));
+    CU(c, cudaMemsetAsync(d_err, 0x7F, 4, c->compute));
+    {
+        ProfScope ps(c, FRB_K_EXPORT);
+        iota_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->compute>>>(i0, n);
+        size_t tmp = 0;
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->total.keys, sorted_keys, i0, i1, static_cast<int>(n), 0, 63,
+                                              c->compute));
+        TRY(ensure_cub_tmp(c, tmp));
+        CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->total.keys, sorted_keys, i0, i1, static_cast<int>(n), 0, 63,
+                                              c->compute));
+        for (uint32_t f = 0; f < n_files; ++f) {
+            const unsigned long long *fk = nullptr, *fc = nullptr;
+            unsigned long long *up_k = nullptr, *up_c = nullptr;
+            uint64_t nf = 0;
+            if (file_keys) {
+                nf = file_n[f];
+                if (!nf) continue;
+                TRY(dmalloc(c, &up_k, nf * 8));
+                CU(c, cudaMemcpyAsync(up_k, file_keys[f], nf * 8, cudaMemcpyHostToDevice, c->compute));
+                if (file_counts && file_counts[f]) {
+                    TRY(dmalloc(c, &up_c, nf * 8));
+                    CU(c, cudaMemcpyAsync(up_c, file_counts[f], nf * 8, cudaMemcpyHostToDevice, c->compute));
+                }
+                fk = up_k, fc = up_c;
+            } else {
+                nf = c->files[f].n;
+                if (!nf) continue;
+                fk = c->files[f].keys, fc = c->files[f].counts;
+            }
+            demux_ok_kernel<<<static_cast<unsigned>((nf + 255) / 256), 256, 0, c->compute>>>(
+                fk, fc, nf, sorted_keys, i1, n, c->type, c->srow, d_match, n_files, f, d_ok, d_bad, d_err);
+            c->launches++;
+            if (up_k) TRY(dfree(c, up_k));
+            if (up_c) TRY(dfree(c, up_c));
+        }
+        CU(c, cudaGetLastError());
+    }
+    int err_row = 0x7FFFFFFF;
+    CU(c, cudaMemcpyAsync(ok_out, d_ok, n, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaMemcpyAsync(bad_files_out, d_bad, n_files, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaMemcpyAsync(&err_row, d_err, 4, cudaMemcpyDeviceToHost, c->compute));
+    CU(c, cudaStreamSynchronize(c->compute));
+    if (err_row_out) *err_row_out = err_row == 0x7F7F7F7F ? 0x7FFFFFFF : err_row;
+    TRY(dfree(c, sorted_keys));
+    TRY(dfree(c, i0));
+    TRY(dfree(c, i1));
+    TRY(dfree(c, d_match));
+    TRY(dfree(c, d_ok));
+    TRY(dfree(c, d_bad));
+    TRY(dfree(c, d_err));
+    return device_error_check(c);
+}
+
 // ---- synthetic input ------------------------------------------------------------------------
 int frb_synth_load(frb_ctx* c, uint64_t seed, uint32_t l1, uint32_t l2, uint32_t n_samples, const uint32_t* emit_i7,
                    const uint32_t* emit_i5, const uint64_t* cdf, uint32_t lane, uint32_t read_len, uint32_t sub_t,

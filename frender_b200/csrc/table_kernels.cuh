@@ -223,4 +223,38 @@ __global__ void __launch_bounds__(256) gather3_kernel(const unsigned* __restrict
     }
 }
 
+// demux_ok (F:504-564): a unique key is "ok" unless some file holds it whose NAME does not fit the key's class.
+// One thread per entry of one file's list: find the key in the total list (binary search in the key-sorted view),
+// take its class -- read type 0/1/3, or 4 + sample row for a demuxable key -- and look up class x file in the
+// match matrix the host made with the reference's regexes (0 no, 1 yes, 2 the regex does not compile).
+__global__ void __launch_bounds__(256) demux_ok_kernel(const unsigned long long* __restrict__ fkeys,
+                                                       const unsigned long long* __restrict__ fcounts, unsigned long long nf,
+                                                       const unsigned long long* __restrict__ sorted_keys,
+                                                       const unsigned* __restrict__ sorted_idx, unsigned long long n,
+                                                       const unsigned char* __restrict__ type, const int* __restrict__ srow,
+                                                       const unsigned char* __restrict__ match, unsigned n_files, unsigned f,
+                                                       unsigned char* __restrict__ ok, unsigned char* __restrict__ bad_file,
+                                                       int* err_row) {
+    const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i >= nf || (fcounts && fcounts[i] == 0)) return;
+    const unsigned long long key = fkeys[i];
+    unsigned long long lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo >= n || sorted_keys[lo] != key) return;  // not part of the total: nothing to flag
+    const unsigned idx = sorted_idx[lo];
+    const unsigned t = type[idx];
+    const unsigned cls = t == 2 ? 4u + static_cast<unsigned>(srow[idx]) : t;
+    const unsigned m = match[static_cast<unsigned long long>(cls) * n_files + f];
+    if (m == 2) {
+        atomicMin(err_row, static_cast<int>(cls) - 4);
+    } else if (m == 0) {
+        ok[idx] = 0;
+        bad_file[f] = 1;
+    }
+}
+
 }  // namespace frb

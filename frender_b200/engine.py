@@ -332,6 +332,27 @@ class Context:
         return results, calls, oriented
 
     # ---- hot path C -------------------------------------------------------------------------
+    def demux_ok(self, match, file_lists=None):
+        """demux_ok per unique key of the total list (in export order) and a flag per file that holds a key it
+        should not (frb_demux_ok; F:504-564).  match: uint8 [(4 + sheet rows), n_files] class x file matrix (0 no,
+        1 yes, 2 invalid pattern).  file_lists: None = the per-file lists of this context, else [(keys, counts)]
+        host arrays.  Returns (ok bool array, bad-file bool array, offending sample row or None)."""
+        match = np.ascontiguousarray(match, np.uint8)
+        n_files = match.shape[1]
+        n = C.c_uint64()
+        self._ck(lib.frb_total_finish(self._h, C.byref(n)))
+        ok, bad = np.ones(max(n.value, 1), np.uint8), np.zeros(max(n_files, 1), np.uint8)
+        err = C.c_int32()
+        if file_lists is None:
+            kp = cp = np_ = None
+        else:
+            keep = [(np.ascontiguousarray(k, np.uint64), np.ascontiguousarray(c, np.uint64)) for k, c in file_lists]
+            kp = (C.c_void_p * n_files)(*[k.ctypes.data for k, _ in keep])
+            cp = (C.c_void_p * n_files)(*[c.ctypes.data for _, c in keep])
+            np_ = (C.c_uint64 * n_files)(*[k.size for k, _ in keep])
+        self._ck(lib.frb_demux_ok(self._h, _ptr(match), n_files, kp, cp, np_, _ptr(ok), _ptr(bad), C.byref(err)))
+        return ok[:n.value].astype(bool), bad[:n_files].astype(bool), (None if err.value == 0x7FFFFFFF else err.value)
+
     def route_load(self, keys, sink_ids, n_sinks):
         """Results table for the demux router: packed key -> sink id (unique keys)."""
         keys = np.ascontiguousarray(keys, np.uint64)

@@ -155,6 +155,17 @@ int frb_match(frb_ctx* ctx, uint32_t n_subs, int rc_mode, const uint8_t* use_rc_
               int32_t* m2rc_row, uint8_t* type_rc, int32_t* sample_rc_row,
               uint64_t* f_sum, uint64_t* rc_sum);
 
+/* demux_ok of every unique key of the total list and the files that hold a key they should not: the reduction of
+ * call_barcodes_correctly_distributed F:504-564 (the regex of F:521-550 is evaluated by the host once per class and
+ * file, not per key).  match: (4 + sheet rows) x n_files bytes, row = read type 0/1/3 or 4 + sample row, 0 = the
+ * file name does not fit, 1 = fits, 2 = the sample name is not a valid pattern (reported through err_row: the
+ * smallest such sample row that really occurs, else INT32_MAX).  file_keys NULL: the per-file lists of this context;
+ * else n_files host arrays (file_counts optional: entries with count 0 are skipped).  ok: one byte per unique key in
+ * the order of frb_total_export; bad_files: one byte per file.  Uses the classification of the last frb_match. */
+int frb_demux_ok(frb_ctx* ctx, const uint8_t* match, uint32_t n_files, const uint64_t* const* file_keys,
+                 const uint64_t* const* file_counts, const uint64_t* file_n, uint8_t* ok, uint8_t* bad_files,
+                 int32_t* err_row);
+
 /* ---- hot path C: demux record router -------------------------------------------------------
  * Replaces the loop F:774-810 + write_reads F:726-730 (grouping F:719-723).
  *   frb_route_load   results table: packed key -> sink id (from parse_results_file F:645-664

@@ -316,3 +316,35 @@ def test_empty_sheet_is_all_undetermined(ctx):
         got = process(1, {"ACGTACGT+TTTTAAAA": 3, "NNNNNNNN+ACGTACGT": 1}, idx, n, False, ctx=ctx)
         assert [v["read_type"] for v in got.values()] == ["undetermined", "undetermined"]
         assert all(v["matched_idx1"] == "" and v["sample_name"] == "" for v in got.values())
+
+
+def test_demux_ok_on_the_device(ctx, golden, golden_dir):
+    """frb_demux_ok (F:504-564) from the context's own per-file lists and from host lists: the reference's flags."""
+    import numpy as np
+    import frender_b200.cli as cli
+    case = golden["scan"]["multi"]
+    names = list(case["files"])
+    ctx.reset()
+    for i, f in enumerate(names):
+        ctx.scan_gz(os.path.join(golden_dir, f"multi__{f}"), i)
+    ctx.file_names[:] = names
+    tables = cli.ScanTables.from_ctx(ctx, names)
+    results, _, _ = ctx.analyze(case["indexes"], case["n"], case["rc"])
+    assert list(results) == [k for k, _ in case["final"]]
+    m = cli.class_file_matrix(names, case["indexes"]["id"], case["prefix"] or "")
+    ok_dev, bad_dev, err = ctx.demux_ok(m, None)
+    ok_host, bad_host, _ = ctx.demux_ok(m, tables.files)
+    want = [rec["demux_ok"] for _, rec in case["final"]]
+    assert err is None and ok_dev.tolist() == want and ok_host.tolist() == want
+    assert bad_dev.tolist() == bad_host.tolist()
+    assert sorted(names[f] for f in np.flatnonzero(bad_dev)) == sorted(case["mismatching_files"])
+    # a sample name that is not a valid pattern only matters when a key of that sample sits in a file
+    rows = sorted({case["indexes"]["id"].index(rec["sample_name"]) for _, rec in case["final"] if rec["sample_name"]})
+    m2 = m.copy()
+    m2[4:, :] = 2
+    assert ctx.demux_ok(m2, None)[2] == rows[0]
+    unused = [r for r in range(len(case["indexes"]["id"])) if r not in rows]
+    if unused:
+        m3 = m.copy()
+        m3[4 + unused[0], :] = 2
+        assert ctx.demux_ok(m3, None)[2] is None
