@@ -27,7 +27,16 @@ struct GzBuffers {
     unsigned char* win[2] = {nullptr, nullptr};  // 32 KiB in front of / behind the piece
     unsigned char* out[2] = {nullptr, nullptr};  // inflated text, two pieces in flight (carry area in front)
     size_t out_cap = 0;
-    unsigned long long* scalars = nullptr;       // device: total symbols, last newline end; [2] as unsigned: bad, cr, fail
+    gz::Trailer* trailers = nullptr;      // member trailers the decoder passed in this piece
+    size_t trailer_cap = 0;
+    unsigned long long* tr_end[2] = {nullptr, nullptr};  // their ends in the text, unsorted / sorted
+    unsigned* tr_idx[2] = {nullptr, nullptr};
+    unsigned* tr_crc = nullptr;           // crc32 of the text up to every trailer end
+    unsigned* crc_blk = nullptr;          // crc32 of every 4 KiB block of the piece's text, and their prefix
+    unsigned* crc_pre = nullptr;
+    // device: [0] total symbols, [1] last newline end; [2..3] as unsigned: bad, cr, fail; [4] as unsigned: trailers;
+    // [5..6] as unsigned: members whose CRC32 / ISIZE disagree, crc and length (lo, hi) of the open member
+    unsigned long long* scalars = nullptr;
     unsigned long long* scalars_host = nullptr;  // pinned
 };
 
@@ -54,6 +63,8 @@ void gz_free(GzBuffers& b) {
     cudaFree(b.stage), cudaFree(b.chunks), cudaFreeHost(b.chunks_host);
     cudaFree(b.maps), cudaFree(b.group_win), cudaFree(b.prev_found);
     cudaFree(b.windows), cudaFree(b.win[0]), cudaFree(b.win[1]), cudaFree(b.out[0]), cudaFree(b.out[1]);
+    cudaFree(b.trailers), cudaFree(b.tr_end[0]), cudaFree(b.tr_end[1]), cudaFree(b.tr_idx[0]), cudaFree(b.tr_idx[1]);
+    cudaFree(b.tr_crc), cudaFree(b.crc_blk), cudaFree(b.crc_pre);
     cudaFree(b.scalars), cudaFreeHost(b.scalars_host);
     b = GzBuffers{};
 }
@@ -82,6 +93,16 @@ int gz_ensure(frb_ctx* c, GzBuffers& b, const GzConfig& g, size_t piece_bytes) {
         CU(c, cudaMalloc(&b.win[i], gz::kWindow));
         CU(c, cudaMalloc(&b.out[i], out_cap));
     }
+    const size_t trailer_cap = 4 * n_chunks + 4096;  // BGZF: about two members per 32 KiB of compressed bytes
+    CU(c, cudaMalloc(&b.trailers, trailer_cap * sizeof(gz::Trailer)));
+    for (int i = 0; i < 2; ++i) {
+        CU(c, cudaMalloc(&b.tr_end[i], trailer_cap * 8));
+        CU(c, cudaMalloc(&b.tr_idx[i], trailer_cap * 4));
+    }
+    CU(c, cudaMalloc(&b.tr_crc, trailer_cap * 4));
+    CU(c, cudaMalloc(&b.crc_blk, (out_cap / gz::kCrcBlock + 2) * 4));
+    CU(c, cudaMalloc(&b.crc_pre, (out_cap / gz::kCrcBlock + 2) * 4));
+    b.trailer_cap = trailer_cap;
     CU(c, cudaMalloc(&b.scalars, 64));
     CU(c, cudaMallocHost(&b.scalars_host, 64));
     b.comp_cap = comp_cap, b.chunk_cap = n_chunks, b.stage_syms = stage_syms, b.out_cap = out_cap;
@@ -115,6 +136,22 @@ struct GzTimer {
                         "resolve %.2f ms\n", piece, n_in, (unsigned long long)n_sym, n_chunks, t[0], t[1], t[2], t[3], t[4], t[6]);
     }
 };
+
+// x^(2^k) mod P, k < 32, for the CRC-32 kernels (reflected polynomial, bit 31 = x^0)
+gz::CrcPowers gz_crc_powers() {
+    auto mul = [](unsigned a, unsigned b) {
+        unsigned p = 0;
+        for (int k = 0; k < 32; ++k) {
+            if ((a >> (31 - k)) & 1u) p ^= b;
+            b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+        }
+        return p;
+    };
+    gz::CrcPowers pw;
+    pw.x2n[0] = 0x40000000u;  // x^1
+    for (int k = 1; k < 32; ++k) pw.x2n[k] = mul(pw.x2n[k - 1], pw.x2n[k - 1]);
+    return pw;
+}
 
 // gzip member header in host memory (RFC 1952): bytes of the header, 0 = not gzip / incomplete
 size_t gz_host_header(const unsigned char* d, size_t n) {
@@ -222,6 +259,9 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
     size_t carry_len = 0;                  // bytes of an unfinished line in front of the next piece's text
     int ob = 0;                            // output buffer in use
     uint64_t total_out = 0;
+    unsigned member_crc = 0;               // crc32 / bytes of the member that is open at the start of the next piece
+    uint64_t member_len = 0;
+    static const gz::CrcPowers crc_pw = gz_crc_powers();
     CU(c, cudaMemsetAsync(b.win[0], 0, gz::kWindow, c->compute));
     for (int piece_no = 0;; ++piece_no) {
         // ---- compressed bytes of the piece (+ overlap) -----------------------------------------------------
@@ -262,7 +302,8 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
                                                          last_piece ? 0 : 1, flags + 2);
             tm.mark(2);
             gz::gz_decode_kernel<<<(n_chunks + gz::kDecodeWarps - 1) / gz::kDecodeWarps, gz::kDecodeWarps * 32, 0, c->compute>>>(
-                comp, n_in, b.chunks, n_chunks, b.stage);
+                comp, n_in, b.chunks, n_chunks, b.stage, b.trailers, static_cast<unsigned>(b.trailer_cap),
+                reinterpret_cast<unsigned*>(b.scalars + 4), flags + 2);
             tm.mark(3);
             gz::gz_offsets_kernel<<<1, 1024, 0, c->compute>>>(b.chunks, n_chunks, b.scalars, flags);
             tm.mark(4);
@@ -284,6 +325,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         cv.notify_all();
         const unsigned* hflags = reinterpret_cast<const unsigned*>(b.scalars_host + 2);
         const uint64_t n_sym = b.scalars_host[0];
+        if (hflags[2]) return FRB_GZ_RETRY_HOST;  // no block start found behind the piece (nothing was decoded)
         if (hflags[0] != 0xFFFFFFFFu) {  // a chunk failed: which way?
             gz::Chunk bad;
             CU(c, cudaMemcpy(&bad, b.chunks + hflags[0], sizeof bad, cudaMemcpyDeviceToHost));
@@ -296,7 +338,8 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
             if (bad.status == gz::GZ_ERR_TRUNC && last_piece) return fail(c, FRB_ERR_IO, "%s: unexpected end of file", path);
             return bad.status == gz::GZ_ERR_SPACE ? FRB_GZ_RETRY_SPACE : FRB_GZ_RETRY_HOST;
         }
-        if (hflags[2]) return FRB_GZ_RETRY_HOST;  // no block start found behind the piece
+        const unsigned n_tr = *reinterpret_cast<const unsigned*>(b.scalars_host + 4);
+        if (n_tr > b.trailer_cap) return FRB_GZ_RETRY_HOST;  // thousands of tiny members: zlib's job
         if (carry_len + n_sym + 64 > b.out_cap) return FRB_GZ_RETRY_HOST;
         // ---- symbols -> text behind the carried line ---------------------------------------------------------
         unsigned char* const text = b.out[ob] + carry_len;
@@ -307,12 +350,38 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
             gz::gz_resolve_kernel<<<dim3(per_chunk_blocks, n_chunks), 256, 0, c->compute>>>(b.chunks, b.stage, b.windows, text,
                                                                                          n_sym);
             tm.mark(7);
+            // CRC32 + ISIZE of every member that ends in this piece (RFC 1952), on the text where it lies
+            unsigned* const crc_res = reinterpret_cast<unsigned*>(b.scalars + 5);
+            gz::gz_crc_blocks_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(text, n_sym, b.crc_blk, crc_pw);
+            gz::gz_crc_scan_kernel<<<1, 1024, 0, c->compute>>>(b.crc_blk, n_sym, b.crc_pre, crc_pw);
+            if (n_tr) {
+                gz::gz_trailer_ends_kernel<<<(n_tr + 255) / 256, 256, 0, c->compute>>>(b.trailers, n_tr, b.chunks, b.tr_end[0],
+                                                                                   b.tr_idx[0]);
+                size_t tmp = 0;
+                CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, b.tr_end[0], b.tr_end[1], b.tr_idx[0], b.tr_idx[1],
+                                                      static_cast<int>(n_tr), 0, 40, c->compute));
+                TRY(ensure_cub_tmp(c, tmp));
+                CU(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, b.tr_end[0], b.tr_end[1], b.tr_idx[0], b.tr_idx[1],
+                                                      static_cast<int>(n_tr), 0, 40, c->compute));
+                gz::gz_crc_ends_kernel<<<(n_tr + 127) / 128, 128, 0, c->compute>>>(text, b.tr_end[1], n_tr, b.crc_pre, b.tr_crc,
+                                                                               crc_pw);
+            }
+            gz::gz_crc_check_kernel<<<std::max(1u, (n_tr + 127) / 128), 128, 0, c->compute>>>(
+                b.trailers, b.tr_idx[1], b.tr_end[1], b.tr_crc, n_tr, b.crc_pre, n_sym, member_crc, member_len, crc_res, crc_pw);
+            c->launches += 5;
             gz::gz_text_kernel<<<c->sm_count * 2, 1024, 0, c->compute>>>(text, n_sym, b.scalars + 1, flags + 1);
             c->launches += 2;
         }
         CU(c, cudaMemcpyAsync(b.scalars_host, b.scalars, 64, cudaMemcpyDeviceToHost, c->compute));
         CU(c, cudaStreamSynchronize(c->compute));
         tm.report(piece_no, n_in, n_sym, n_chunks);
+        {
+            const unsigned* const crc_res = reinterpret_cast<const unsigned*>(b.scalars_host + 5);
+            if (crc_res[0]) return fail(c, FRB_ERR_IO, "%s: CRC check failed (gzip member trailer)", path);
+            member_crc = crc_res[1];
+            member_len = static_cast<uint64_t>(crc_res[2]) | (static_cast<uint64_t>(crc_res[3]) << 32);
+            if (last_piece && member_len) return fail(c, FRB_ERR_IO, "%s: unexpected end of file", path);
+        }
         if (hflags[1]) return FRB_GZ_RETRY_HOST;  // '\r' in the text: universal newlines are the host path's job
         total_out += n_sym;
         const uint64_t have = carry_len + n_sym;

@@ -56,6 +56,16 @@ struct Chunk {
     unsigned int member_start;     // a gzip member begins with this chunk's first block: nothing in front to refer to
 };
 
+// A member trailer the decoder passed: the member ends `local_end` symbols into chunk `chunk`.
+struct Trailer {
+    unsigned int chunk, local_end, crc, isize;
+};
+
+// x^(2^k) mod P for k < 32 (P = the CRC-32 polynomial, reflected; made by the host), kernel parameter
+struct CrcPowers {
+    unsigned int x2n[32];
+};
+
 // ---- bit access ---------------------------------------------------------------------------------------------
 // 64 bits starting at absolute bit `pos` (LSB first, as deflate packs them).  The buffer is word aligned and
 // padded with 64 zero bytes behind its `nbytes`, so the three aligned 32-bit loads never leave it.
@@ -207,13 +217,17 @@ __device__ __forceinline__ int decode_slow(unsigned bits, const unsigned short* 
     return -1;
 }
 
+__device__ inline unsigned long long member_header(const unsigned char* __restrict__ d, unsigned long long nbytes,
+                                                   unsigned long long pos);
+
 // Is a dynamic block likely to start at bit `pos`?  Header valid, and the first symbols decode (no unused code, no
 // distance beyond the window).  One thread, local scratch only.
 __device__ inline bool plausible_block_start(const unsigned char* __restrict__ d, unsigned long long nbytes,
-                                             unsigned long long pos) {
+                                             unsigned long long pos, bool any_final = false) {
     {   // the cheap part first: block type, code counts, complete code-length code (Kraft sum over 7-bit codes)
         const unsigned long long v = bits64(d, pos);
-        if ((v & 7) != 4u) return false;  // BFINAL = 0, BTYPE = 10
+        // BTYPE = 10; BFINAL = 0 -- a last block is only looked for behind a member header (any_final)
+        if ((v & (any_final ? 6u : 7u)) != 4u) return false;
         if (((v >> 3) & 31) > 29u || ((v >> 8) & 31) > 29u) return false;
         const int hclen = static_cast<int>((v >> 13) & 15) + 4;
         const unsigned long long cl = bits64(d, pos + 17);
@@ -286,15 +300,27 @@ __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned ch
     for (unsigned long long base = from; base < to; base += 8 * kFindThreads) {
         for (int r = 0; r < 8; ++r) {  // eight rounds between looks at the result (positions stay in order per round)
             const unsigned long long p = base + r * kFindThreads + threadIdx.x;
-            if (p < to && plausible_block_start(d, nbytes, p)) atomicMin(&s_best, p);
+            if (p >= to) continue;
+            if (plausible_block_start(d, nbytes, p)) atomicMin(&s_best, (p << 1) | 1ull);
+            // a gzip member header (files of many small members, BGZF): the first block of a member may be its
+            // last, and nothing in front of it is referred to
+            if ((p & 7) == 0) {
+                const unsigned long long b = p >> 3;
+                if (b + 18 < nbytes && d[b] == 0x1f && d[b + 1] == 0x8b && d[b + 2] == 8) {
+                    const unsigned long long hb = member_header(d, nbytes, b);
+                    if (hb && plausible_block_start(d, nbytes, hb * 8, true)) atomicMin(&s_best, (hb * 8) << 1);
+                }
+            }
         }
         __syncthreads();
         if (s_best != ~0ull) break;
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        chunks[c].found = s_best != ~0ull && (tail || s_best < (first_byte + static_cast<unsigned long long>(c + 1) * stride) * 8);
-        chunks[c].start_bit = s_best;
+    if (threadIdx.x == 0) {  // s_best = (bit << 1) | 1, or bit << 1 for the first block of a member
+        const unsigned long long best = s_best >> 1;
+        chunks[c].found = s_best != ~0ull && (tail || best < (first_byte + static_cast<unsigned long long>(c + 1) * stride) * 8);
+        chunks[c].start_bit = best;
+        chunks[c].member_start = s_best != ~0ull && (s_best & 1) == 0;
     }
 }
 
@@ -363,8 +389,11 @@ __device__ inline unsigned long long member_header(const unsigned char* __restri
 // One warp per chunk.  Lane 0 reads bits and walks the codes; the warp copies matches, builds tables.
 __global__ void __launch_bounds__(kDecodeWarps * 32) gz_decode_kernel(const unsigned char* __restrict__ d,
                                                                       unsigned long long nbytes, Chunk* chunks,
-                                                                      unsigned n_chunks, unsigned short* stage) {
+                                                                      unsigned n_chunks, unsigned short* stage,
+                                                                      Trailer* trailers, unsigned trailer_cap,
+                                                                      unsigned* trailer_n, const unsigned* link_failed) {
     __shared__ WarpTables s_tab[kDecodeWarps];
+    if (*link_failed) return;  // no block start behind the piece: the host inflates this file
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned c = blockIdx.x * kDecodeWarps + w;
     if (c >= n_chunks || !chunks[c].found) return;
@@ -489,6 +518,8 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) gz_decode_kernel(const unsi
                     // a run of literals without involving the other lanes
                     for (;;) {
                         if (cnt <= 32) {
+                            // more than two words of padding taken in: the block runs past the end of the data
+                            if (wpos > nwords + 2) { op = GZ_ERR_TRUNC; break; }
                             buf |= static_cast<unsigned long long>(wpos < nwords ? d32[wpos] : 0u) << cnt;
                             cnt += 32;
                             ++wpos;
@@ -567,6 +598,13 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) gz_decode_kernel(const unsi
             const unsigned isize = d[b + 4] | (d[b + 5] << 8) | (d[b + 6] << 16) | (static_cast<unsigned>(d[b + 7]) << 24);
             // bytes of the member produced by THIS chunk can be checked only when the member began here
             if (known_from != ~0u && static_cast<unsigned>(n - member_out0) != isize) isize_ok = 0;
+            if (lane == 0) {  // CRC32 and ISIZE of the whole member are checked once the text is there (gz_crc_*)
+                const unsigned t = atomicAdd(trailer_n, 1u);
+                if (t < trailer_cap) {
+                    const unsigned crc = d[b] | (d[b + 1] << 8) | (d[b + 2] << 16) | (static_cast<unsigned>(d[b + 3]) << 24);
+                    trailers[t] = Trailer{c, n, crc, isize};
+                }
+            }
             unsigned long long nb = b + 8;
             while (nb < nbytes && d[nb] == 0) ++nb;  // zero padding between / behind members (gzip tolerates it)
             if (nb >= nbytes) {
@@ -757,6 +795,161 @@ __global__ void __launch_bounds__(1024) gz_text_kernel(const unsigned char* __re
     }
     if (best) atomicMax(last_nl_end, best);
     if (cr) atomicOr(has_cr, 1u);
+}
+
+// ---- CRC-32 of the inflated text (RFC 1952 trailer check) -------------------------------------------------------
+// Standard CRC-32 values combine like zlib's crc32_combine: crc(A || B) = x^(8 |B|) * crc(A) + crc(B) in
+// GF(2)[x] / P (reflected bit order, bit 31 = x^0).  So the text is summed in 4 KiB blocks by warps (gz_crc_blocks),
+// the block sums are prefix-combined (gz_crc_scan: F[b] = crc of text[0, 4096 b)), and every member end e gets
+// F(e) from F[e / 4096] and the bytes behind it (gz_crc_ends); a member [a, e) then has
+// crc = F(e) + x^(8 (e - a)) * F(a), which gz_crc_check compares with the trailer, as it does ISIZE.
+constexpr unsigned kCrcPoly = 0xEDB88320u;
+constexpr unsigned kCrcBlock = 4096;
+
+__device__ __forceinline__ unsigned crc_mul(unsigned a, unsigned b) {  // a * b mod P
+    unsigned p = 0;
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        p ^= b & (0u - ((a >> (31 - k)) & 1u));
+        b = (b >> 1) ^ (kCrcPoly & (0u - (b & 1u)));
+    }
+    return p;
+}
+__device__ inline unsigned crc_xpow8(const CrcPowers& pw, unsigned long long nbytes) {  // x^(8 nbytes) mod P
+    unsigned p = 0x80000000u;
+    for (int k = 3; nbytes; nbytes >>= 1, ++k)
+        if (nbytes & 1) p = crc_mul(pw.x2n[k & 31], p);
+    return p;
+}
+__device__ __forceinline__ unsigned crc_join(const CrcPowers& pw, unsigned crc_a, unsigned crc_b, unsigned long long len_b) {
+    return len_b ? (crc_mul(crc_xpow8(pw, len_b), crc_a) ^ crc_b) : crc_a;
+}
+__device__ inline unsigned crc_bytes(const unsigned char* __restrict__ p, unsigned n) {  // crc32 of n bytes, bit by bit
+    unsigned crc = 0xFFFFFFFFu;
+    for (unsigned i = 0; i < n; ++i) {
+        crc ^= p[i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) crc = (crc >> 1) ^ (kCrcPoly & (0u - (crc & 1u)));
+    }
+    return ~crc;
+}
+
+// blk[b] = crc32 of text[4096 b, min(4096 (b + 1), n)): one warp per block, 128 bytes per lane
+__global__ void __launch_bounds__(256) gz_crc_blocks_kernel(const unsigned char* __restrict__ text, unsigned long long n,
+                                                            unsigned* __restrict__ blk, CrcPowers pw) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_blocks = (n + kCrcBlock - 1) / kCrcBlock;
+    for (unsigned long long b = blockIdx.x * 8ull + (threadIdx.x >> 5); b < n_blocks; b += gridDim.x * 8ull) {
+        const unsigned long long base = b * kCrcBlock + lane * 128ull;
+        unsigned len = base < n ? static_cast<unsigned>(n - base < 128 ? n - base : 128) : 0u;
+        unsigned crc = len ? crc_bytes(text + base, len) : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {  // (crc, len) of lane L joins in front of lane L + d's
+            const unsigned ocrc = __shfl_down_sync(0xFFFFFFFFu, crc, d);
+            const unsigned olen = __shfl_down_sync(0xFFFFFFFFu, len, d);
+            if ((lane & (2 * d - 1)) == 0) {
+                crc = crc_join(pw, crc, ocrc, olen);
+                len += olen;
+            }
+        }
+        if (lane == 0) blk[b] = crc;
+    }
+}
+
+// F[b] = crc32 of text[0, 4096 b) for b <= n_blocks (exclusive prefix; F[n_blocks] = the whole text).  One block.
+__global__ void __launch_bounds__(1024) gz_crc_scan_kernel(const unsigned* __restrict__ blk, unsigned long long n,
+                                                           unsigned* __restrict__ F, CrcPowers pw) {
+    __shared__ unsigned s_crc[1024];
+    __shared__ unsigned long long s_len[1024];
+    const unsigned t = threadIdx.x;
+    const unsigned long long n_blocks = (n + kCrcBlock - 1) / kCrcBlock;
+    const unsigned long long per = (n_blocks + 1023) / 1024;
+    const unsigned long long b0 = t * per, b1 = b0 + per < n_blocks ? b0 + per : n_blocks;
+    const unsigned x4k = crc_xpow8(pw, kCrcBlock);
+    auto block_len = [&](unsigned long long b) { return b + 1 < n_blocks ? kCrcBlock : n - b * kCrcBlock; };
+    unsigned crc = 0;
+    unsigned long long len = 0;
+    for (unsigned long long b = b0; b < b1; ++b) {
+        const unsigned long long l = block_len(b);
+        crc = (l == kCrcBlock ? crc_mul(x4k, crc) : crc_mul(crc_xpow8(pw, l), crc)) ^ blk[b];
+        len += l;
+    }
+    s_crc[t] = crc, s_len[t] = len;
+    __syncthreads();
+    for (unsigned d = 1; d < 1024; d <<= 1) {  // inclusive scan of (crc, len) under the join
+        unsigned c2 = 0;
+        unsigned long long l2 = 0;
+        if (t >= d) c2 = s_crc[t - d], l2 = s_len[t - d];
+        __syncthreads();
+        if (t >= d) {
+            s_crc[t] = crc_join(pw, c2, s_crc[t], s_len[t]);
+            s_len[t] += l2;
+        }
+        __syncthreads();
+    }
+    unsigned run = t ? s_crc[t - 1] : 0u;  // everything in front of this thread's blocks
+    for (unsigned long long b = b0; b < b1; ++b) {
+        F[b] = run;
+        const unsigned long long l = block_len(b);
+        run = (l == kCrcBlock ? crc_mul(x4k, run) : crc_mul(crc_xpow8(pw, l), run)) ^ blk[b];
+    }
+    if (b0 < n_blocks && b1 == n_blocks) F[n_blocks] = run;
+    if (n_blocks == 0 && t == 0) F[0] = 0u;
+}
+
+// end[i] = absolute end of trailer i in the piece's text (chunk offset + local end)
+__global__ void gz_trailer_ends_kernel(const Trailer* __restrict__ tr, unsigned n_tr, const Chunk* __restrict__ chunks,
+                                       unsigned long long* __restrict__ end, unsigned* __restrict__ idx) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tr) return;
+    end[i] = chunks[tr[i].chunk].out_off + tr[i].local_end;
+    idx[i] = i;
+}
+
+// Fe[i] = crc32 of text[0, end[i]) for the trailers in text order
+__global__ void __launch_bounds__(128) gz_crc_ends_kernel(const unsigned char* __restrict__ text,
+                                                          const unsigned long long* __restrict__ end, unsigned n_tr,
+                                                          const unsigned* __restrict__ F, unsigned* __restrict__ Fe, CrcPowers pw) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tr) return;
+    const unsigned long long e = end[i], b = e / kCrcBlock;
+    const unsigned rest = static_cast<unsigned>(e - b * kCrcBlock);
+    Fe[i] = rest ? crc_join(pw, F[b], crc_bytes(text + b * kCrcBlock, rest), rest) : F[b];
+}
+
+// Every member that ends in this piece against its trailer.  carry_crc / carry_len: the part of the first member
+// that earlier pieces produced.  result[0] = members that disagree, result[1] / result[2..3] = crc / length of the
+// open member behind the last trailer (the next piece's carry).
+__global__ void __launch_bounds__(128) gz_crc_check_kernel(const Trailer* __restrict__ tr, const unsigned* __restrict__ idx,
+                                                           const unsigned long long* __restrict__ end,
+                                                           const unsigned* __restrict__ Fe, unsigned n_tr,
+                                                           const unsigned* __restrict__ F, unsigned long long n,
+                                                           unsigned carry_crc, unsigned long long carry_len,
+                                                           unsigned* __restrict__ result, CrcPowers pw) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n_blocks = (n + kCrcBlock - 1) / kCrcBlock;
+    if (i < n_tr) {
+        const Trailer t = tr[idx[i]];
+        const unsigned long long a = i ? end[i - 1] : 0ull, e = end[i];
+        unsigned crc = Fe[i] ^ (i ? crc_mul(crc_xpow8(pw, e - a), Fe[i - 1]) : 0u);  // crc32 of text[a, e)
+        unsigned long long len = e - a;
+        if (i == 0) {
+            crc = crc_join(pw, carry_crc, crc, len);
+            len += carry_len;
+        }
+        if (crc != t.crc || static_cast<unsigned>(len) != t.isize) atomicAdd(&result[0], 1u);
+    }
+    if (i == 0) {  // what is open behind the last trailer
+        const unsigned long long a = n_tr ? end[n_tr - 1] : 0ull;
+        unsigned crc = F[n_blocks] ^ (n_tr ? crc_mul(crc_xpow8(pw, n - a), Fe[n_tr - 1]) : 0u);
+        unsigned long long len = n - a;
+        if (!n_tr) {
+            crc = crc_join(pw, carry_crc, crc, len);
+            len += carry_len;
+        }
+        result[1] = crc;
+        result[2] = static_cast<unsigned>(len), result[3] = static_cast<unsigned>(len >> 32);
+    }
 }
 
 }  // namespace gz

@@ -135,6 +135,39 @@ def test_truncated_and_foreign_files_fail(ctx, tmp_path):
     ctx.reset()
 
 
+@pytest.mark.parametrize("piece_mb", ["128", "1"])
+def test_member_trailers_are_checked(ctx, tmp_path, monkeypatch, piece_mb):
+    """CRC32 and ISIZE of every gzip member (RFC 1952) are verified on the device: a wrong trailer is what
+    gzip.open reports as BadGzipFile in the reference (F:159) -- FRB_ERR_IO here; members that span pieces and
+    chunks, several members per file and BGZF-sized members pass."""
+    from frender_b200 import _lib
+    from frender_b200.engine import FrbError
+    monkeypatch.setenv("FRB_GZ_PIECE_MB", piece_mb)
+    data = fastq(40_000, seed=21)
+    one = gzip.compress(data, 6, mtime=0)
+    three = gz_members(data, 3, 6)
+    tiny = gz_members(data, 300, 6)                       # ~ 50 KB of text per member, like BGZF
+    first_len = len(gzip.compress(data[:(len(data) + 2) // 3], 6, mtime=0))
+    good = {"one": one, "three": three, "tiny": tiny}
+    for name, blob in good.items():
+        p = tmp_path / f"{name}.fastq.gz"
+        p.write_bytes(blob)
+        assert ctx.gz_inflate(p, len(data) + 1024) == data, name
+    flip = lambda blob, at, bit=1: blob[:at] + bytes([blob[at] ^ bit]) + blob[at + 1:]
+    n = len(one)
+    bad = {"crc_last": flip(one, n - 8), "isize_last": flip(one, n - 2, 0x10),
+           "crc_first_member": flip(three, first_len - 7), "isize_first_member": flip(three, first_len - 4),
+           "crc_tiny_member": flip(tiny, len(tiny) - 6)}
+    for name, blob in bad.items():
+        p = tmp_path / f"{name}.fastq.gz"
+        p.write_bytes(blob)
+        with pytest.raises(FrbError) as info:
+            ctx.gz_inflate(p, len(data) + 1024)
+        assert info.value.code == _lib.ERR_IO, name
+        with pytest.raises((gzip.BadGzipFile, EOFError, zlib.error)):
+            gzip.open(p, "rb").read()
+
+
 def test_crlf_file_larger_than_the_staging_buffer(ctx, tmp_path, monkeypatch):
     """Universal newlines on the host path (the device path hands '\\r' files over): "\\r\\n", lone "\\r" and a
     "\\r\\n" split across reads, with staging buffers far smaller than the file."""
