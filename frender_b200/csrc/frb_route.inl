@@ -42,14 +42,7 @@ void route_stream_free(RouteStream& r) {
     r = RouteStream{};
 }
 
-int route_stream_ensure(frb_ctx* c, RouteStream& r, size_t bytes, unsigned n_sinks) {
-    if (bytes <= r.cap && n_sinks == r.n_sinks) return FRB_OK;
-    if (r.pushed != r.popped) return fail(c, FRB_ERR_STATE, "demux stream: chunks in flight while its buffers would grow");
-    CU(c, cudaStreamSynchronize(c->compute));
-    const size_t cap = std::max<size_t>(std::max(bytes, r.cap), 1 << 20);
-    route_stream_free(r);
-    r.cap = cap;
-    r.n_sinks = n_sinks;
+int route_stream_alloc(frb_ctx* c, RouteStream& r, size_t cap, unsigned n_sinks) {
     r.rec_cap = 2 * cap / 16 + 16;  // a record shorter than 16 bytes is reported as an error
     r.n_blocks = static_cast<unsigned>((r.rec_cap + kRouteBlock - 1) / kRouteBlock);
     CU(c, cudaStreamCreateWithFlags(&r.d2h, cudaStreamNonBlocking));
@@ -78,8 +71,27 @@ int route_stream_ensure(frb_ctx* c, RouteStream& r, size_t bytes, unsigned n_sin
     CU(c, cudaMalloc(&r.local2, r.rec_cap * 4));
     CU(c, cudaMalloc(&r.cell, (2ull * n_sinks * r.n_blocks + 2ull * n_sinks) * 8));  // + per-sink totals
     RouteState init{};
-    init.skip1 = init.skip2 = r.cap;  // nothing carried: the text begins where the host puts the new bytes
+    init.skip1 = init.skip2 = cap;  // nothing carried: the text begins where the host puts the new bytes
     CU(c, cudaMemcpy(r.rs, &init, sizeof init, cudaMemcpyHostToDevice));
+    // the histogram keeps two counters per sink in shared memory
+    CU(c, cudaFuncSetAttribute(route_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(std::max<size_t>(2 * n_sinks * sizeof(unsigned), 48 << 10))));
+    return FRB_OK;
+}
+
+int route_stream_ensure(frb_ctx* c, RouteStream& r, size_t bytes, unsigned n_sinks) {
+    if (bytes <= r.cap && n_sinks == r.n_sinks) return FRB_OK;
+    if (r.pushed != r.popped) return fail(c, FRB_ERR_STATE, "demux stream: chunks in flight while its buffers would grow");
+    CU(c, cudaStreamSynchronize(c->compute));
+    const size_t cap = std::max<size_t>(std::max(bytes, r.cap), 1 << 20);
+    route_stream_free(r);
+    const int rc = route_stream_alloc(c, r, cap, n_sinks);
+    if (rc != FRB_OK) {  // out of memory half way: nothing of the stream stays behind
+        route_stream_free(r);
+        return rc;
+    }
+    r.cap = cap;
+    r.n_sinks = n_sinks;
     return FRB_OK;
 }
 

@@ -32,6 +32,7 @@ constexpr int kDistBits = 9;
 constexpr unsigned kWindow = 32768;
 constexpr unsigned kMarker = 0x8000;         // symbol >= kMarker: byte at offset (symbol - kMarker) of the window
 constexpr int kFindThreads = 128;
+constexpr int kFindWindow = 8192;            // bit positions per round of the finder
 constexpr int kDecodeWarps = 4;              // warps (= chunks) per decode CTA
 
 enum : int {
@@ -146,6 +147,9 @@ __device__ inline unsigned long long dynamic_header(const unsigned char* __restr
     const int total = hlit + hdist;
     int idx = 0;
     unsigned char prev = 0;
+    // code space left (in units of 2^-15) while the lengths come in: an over-subscribed code is given up at once --
+    // what bits that are not a block header turn into after a few dozen lengths
+    int room[2] = {1 << 15, 1 << 15};
     while (idx < total) {
         unsigned bits = peek(d, nbytes, pos, 7 + 7);
         int code = 0, first = 0, index = 0, s = -1, used = 0;
@@ -166,6 +170,7 @@ __device__ inline unsigned long long dynamic_header(const unsigned char* __restr
         if (s < 0) return 0;
         if (s < 16) {
             lens[idx < hlit ? idx : 288 + (idx - hlit)] = prev = static_cast<unsigned char>(s);
+            if (s && (room[idx >= hlit] -= (1 << 15) >> s) < 0) return 0;
             ++idx;
             pos += used;
         } else {
@@ -184,7 +189,10 @@ __device__ inline unsigned long long dynamic_header(const unsigned char* __restr
                 pos += used + 7;
             }
             if (idx + rep > total) return 0;
-            for (; rep; --rep, ++idx) lens[idx < hlit ? idx : 288 + (idx - hlit)] = val;
+            for (; rep; --rep, ++idx) {
+                lens[idx < hlit ? idx : 288 + (idx - hlit)] = val;
+                if (val && (room[idx >= hlit] -= (1 << 15) >> val) < 0) return 0;
+            }
             prev = val;
         }
     }
@@ -222,22 +230,33 @@ __device__ inline unsigned long long member_header(const unsigned char* __restri
 
 // Is a dynamic block likely to start at bit `pos`?  Header valid, and the first symbols decode (no unused code, no
 // distance beyond the window).  One thread, local scratch only.
+// The test in three steps of rising cost, so that the finder can run each step on a dense list of survivors:
+//   block_head_ok   block type and code counts (the first 13 bits)
+//   block_kraft_ok  the code-length code is complete (Kraft sum of its up to 19 three-bit lengths)
+//   block_body_ok   the code lengths decode to valid codes and the first symbols decode
+__device__ __forceinline__ bool block_head_ok(unsigned v, bool any_final) {
+    // BTYPE = 10; BFINAL = 0 -- a last block is only looked for behind a member header (any_final)
+    return (v & (any_final ? 6u : 7u)) == 4u && ((v >> 3) & 31u) <= 29u && ((v >> 8) & 31u) <= 29u;
+}
+__device__ __forceinline__ bool block_kraft_ok(const unsigned char* __restrict__ d, unsigned long long pos) {
+    const int hclen = static_cast<int>((bits64(d, pos) >> 13) & 15) + 4;
+    const unsigned long long cl = bits64(d, pos + 17);
+    unsigned kraft = 0;
+    for (int i = 0; i < hclen; ++i) {
+        const unsigned l = static_cast<unsigned>(cl >> (3 * i)) & 7u;
+        kraft += l ? (128u >> l) : 0u;
+    }
+    return kraft == 128u;
+}
+__device__ inline bool block_body_ok(const unsigned char* __restrict__ d, unsigned long long nbytes, unsigned long long pos);
+
 __device__ inline bool plausible_block_start(const unsigned char* __restrict__ d, unsigned long long nbytes,
                                              unsigned long long pos, bool any_final = false) {
-    {   // the cheap part first: block type, code counts, complete code-length code (Kraft sum over 7-bit codes)
-        const unsigned long long v = bits64(d, pos);
-        // BTYPE = 10; BFINAL = 0 -- a last block is only looked for behind a member header (any_final)
-        if ((v & (any_final ? 6u : 7u)) != 4u) return false;
-        if (((v >> 3) & 31) > 29u || ((v >> 8) & 31) > 29u) return false;
-        const int hclen = static_cast<int>((v >> 13) & 15) + 4;
-        const unsigned long long cl = bits64(d, pos + 17);
-        unsigned kraft = 0;
-        for (int i = 0; i < hclen; ++i) {
-            const unsigned l = static_cast<unsigned>(cl >> (3 * i)) & 7u;
-            kraft += l ? (128u >> l) : 0u;
-        }
-        if (kraft != 128u) return false;
-    }
+    return block_head_ok(static_cast<unsigned>(bits64(d, pos)), any_final) && block_kraft_ok(d, pos) &&
+           block_body_ok(d, nbytes, pos);
+}
+
+__device__ inline bool block_body_ok(const unsigned char* __restrict__ d, unsigned long long nbytes, unsigned long long pos) {
     unsigned char lens[320];
     int n_lit, n_dist;
     unsigned long long p = dynamic_header(d, nbytes, pos + 3, lens, &n_lit, &n_dist);
@@ -297,11 +316,21 @@ __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned ch
     const bool tail = c == tail_chunk;
     const unsigned long long reach = tail ? 3 * stride - 8192 : stride + stride / 2;
     const unsigned long long to = min((first_byte + static_cast<unsigned long long>(c) * stride + reach) * 8, nbytes * 8);
-    for (unsigned long long base = from; base < to; base += 8 * kFindThreads) {
-        for (int r = 0; r < 8; ++r) {  // eight rounds between looks at the result (positions stay in order per round)
-            const unsigned long long p = base + r * kFindThreads + threadIdx.x;
-            if (p >= to) continue;
-            if (plausible_block_start(d, nbytes, p)) atomicMin(&s_best, (p << 1) | 1ull);
+    // kFindWindow bit positions per round, in three passes: every position gets the 13-bit test; the survivors
+    // (one in nine) are collected and shared out over ALL threads for the Kraft sum; what is left of them (a few
+    // dozen) is collected again for the expensive part.  Done in place, a single survivor in a warp keeps the other
+    // 31 lanes waiting through its code lengths and trial decode: 3.5e9 warp instructions per piece at ten active
+    // lanes, most of them that wait.
+    __shared__ unsigned short s_a[kFindWindow], s_b[kFindWindow];
+    __shared__ unsigned s_na, s_nb;
+    for (unsigned long long base = from; base < to; base += kFindWindow) {
+        if (threadIdx.x == 0) s_na = 0, s_nb = 0;
+        __syncthreads();
+        for (int r = 0; r < kFindWindow / kFindThreads; ++r) {
+            const unsigned rel = r * kFindThreads + threadIdx.x;
+            const unsigned long long p = base + rel;
+            if (p >= to) break;
+            if (block_head_ok(static_cast<unsigned>(bits64(d, p)), false)) s_a[atomicAdd(&s_na, 1u)] = static_cast<unsigned short>(rel);
             // a gzip member header (files of many small members, BGZF): the first block of a member may be its
             // last, and nothing in front of it is referred to
             if ((p & 7) == 0) {
@@ -313,8 +342,17 @@ __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned ch
             }
         }
         __syncthreads();
-        if (s_best != ~0ull) break;
+        const unsigned na = s_na;
+        for (unsigned i = threadIdx.x; i < na; i += kFindThreads)
+            if (block_kraft_ok(d, base + s_a[i])) s_b[atomicAdd(&s_nb, 1u)] = s_a[i];
         __syncthreads();
+        const unsigned nb = s_nb;
+        for (unsigned i = threadIdx.x; i < nb; i += kFindThreads) {
+            const unsigned long long p = base + s_b[i];
+            if (block_body_ok(d, nbytes, p)) atomicMin(&s_best, (p << 1) | 1ull);
+        }
+        __syncthreads();
+        if (s_best != ~0ull) break;
     }
     if (threadIdx.x == 0) {  // s_best = (bit << 1) | 1, or bit << 1 for the first block of a member
         const unsigned long long best = s_best >> 1;
