@@ -62,6 +62,7 @@ SIGNATURES = {
     "frb_route_load": (C.c_int, [vp, vp, vp, u64, u32]),
     "frb_route_pair": (C.c_int, [vp, vp, u64, vp, u64, C.c_int, vp, vp, vp, vp, P(u64), P(u64), P(u64), P(u64)]),
     "frb_route_reset": (C.c_int, [vp]),
+    "frb_route_reserve": (C.c_int, [vp, u64]),
     "frb_route_push": (C.c_int, [vp, vp, u64, vp, u64, C.c_int]),
     "frb_route_pop": (C.c_int, [vp, P(vp), P(vp), vp, vp, P(u64), P(u64), P(u64), P(u64)]),
     "frb_nccl_unique_id": (C.c_int, [C.c_char_p]),

@@ -757,7 +757,7 @@ def frender_demux(args, ctx=None):
             # comes back and is deflated, chunk k+1 is inflated.  Chunks are cut anywhere; records that are not
             # complete yet (and the lead of one mate over the other) are carried on the device.
             a, b = TextChunks(r1_path), TextChunks(r2_path)
-            ctx.route_reset()
+            ctx.route_reset(chunk)
             flags, carry, over = [], (0, 0), False
             while not over:
                 want = [max(chunk - c, MIN_CHUNK // 4) for c in carry]   # carry + new bytes stay within the window

@@ -159,6 +159,18 @@ int frb_route_reset(frb_ctx* c) {
     return FRB_OK;
 }
 
+// Buffers for chunks of up to `chunk_bytes` per mate (otherwise the first chunk pushed sets the size, and later
+// chunks of the stream may not be larger).  Between streams only.
+int frb_route_reserve(frb_ctx* c, uint64_t chunk_bytes) {
+    CU(c, cudaSetDevice(c->device));
+    if (!c->route_tab) return fail(c, FRB_ERR_STATE, "frb_route_reserve: frb_route_load first");
+    if (!c->route) c->route = new RouteStreamHolder();
+    RouteStream& r = c->route->r;
+    if (r.pushed != r.popped) return fail(c, FRB_ERR_STATE, "frb_route_reserve: chunks in flight");
+    TRY(route_stream_ensure(c, r, chunk_bytes, c->n_sinks));
+    return frb_route_reset(c);
+}
+
 int frb_route_push(frb_ctx* c, const void* r1, uint64_t n1, const void* r2, uint64_t n2, int final_chunk) {
     CU(c, cudaSetDevice(c->device));
     if (!c->route_tab) return fail(c, FRB_ERR_STATE, "frb_route_push: frb_route_load first");

@@ -374,9 +374,13 @@ class Context:
         return (o1[:u1.value].tobytes(), o2[:u2.value].tobytes(), off1.astype(np.int64), off2.astype(np.int64),
                 pairs.value, u1.value, u2.value)
 
-    def route_reset(self):
-        """A new stream of chunk pairs begins (frb_route_reset)."""
-        self._ck(lib.frb_route_reset(self._h))
+    def route_reset(self, chunk_bytes=None):
+        """A new stream of chunk pairs begins (frb_route_reset); chunk_bytes: the largest chunk per mate that will
+        be pushed (frb_route_reserve) -- without it the first chunk sets the size."""
+        if chunk_bytes:
+            self._ck(lib.frb_route_reserve(self._h, int(chunk_bytes)))
+        else:
+            self._ck(lib.frb_route_reset(self._h))
 
     def route_push(self, r1, r2, final=0):
         """Queue one chunk pair of the demux stream (frb_route_push): bytes cut anywhere; what is not complete

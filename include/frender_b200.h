@@ -191,8 +191,11 @@ int frb_route_pair(frb_ctx* ctx, const void* r1, uint64_t r1_bytes, const void* 
  *   frb_route_pop   the oldest chunk in flight: *out_r1 / *out_r2 point into pinned memory of the library (valid
  *                   until the chunk after next is pushed), sink s of mate m is out_m[off_m[s], off_m[s + 1]);
  *                   carry_r1 / carry_r2 = bytes pushed so far that are not routed yet.
- *   frb_route_reset a new stream begins (nothing carried).                                                      */
+ *   frb_route_reset a new stream begins (nothing carried).
+ *   frb_route_reserve  buffers for chunks of up to chunk_bytes per mate (and a new stream); without it the first
+ *                   chunk pushed sets the size.                                                                 */
 int frb_route_reset(frb_ctx* ctx);
+int frb_route_reserve(frb_ctx* ctx, uint64_t chunk_bytes);
 int frb_route_push(frb_ctx* ctx, const void* r1, uint64_t r1_bytes, const void* r2, uint64_t r2_bytes, int final_chunk);
 int frb_route_pop(frb_ctx* ctx, void** out_r1, void** out_r2, uint64_t* off_r1, uint64_t* off_r2, uint64_t* n_pairs,
                   uint64_t* carry_r1, uint64_t* carry_r2, uint64_t* bad_key);
