@@ -223,8 +223,10 @@ def scan_files_concurrent(files, sample, streams, device, table_log2, main_ctx):
         except BaseException as exc:
             errors.append(exc)
 
-    # each stream is bound by its zlib thread (≈ 0.5 GB/s), so small staging buffers are enough and make the
-    # per-context set-up (pinned ring, device stages) cheap
+    # a stream that falls back to its zlib thread is bound by it (≈ 0.5 GB/s), so small staging buffers are enough
+    # there and make the per-context set-up (pinned ring, device stages) cheap; streams that inflate on the device
+    # size their buffers from the file (a few GB each for files of 128 MB and more -- hence at most 4 streams by
+    # default: one device-inflated stream already does what twenty zlib threads do)
     had = os.environ.get("FRB_STAGE_MB")
     if had is None:
         os.environ["FRB_STAGE_MB"] = "16"
@@ -395,7 +397,7 @@ def tally_files(ctx, files, names, sample, cores, n_gpus):
         tables = ScanTables(names, total, [per_file[i][2:] for i in range(len(names))])
         ctx.load_total_arrays(*total)
     elif cores > 1 and len(files) > 1:
-        streams = min(cores, len(files), int(os.environ.get("FRENDER_MAX_STREAMS", "16")))
+        streams = min(cores, len(files), int(os.environ.get("FRENDER_MAX_STREAMS", "4")))
         per_file, total = scan_files_concurrent(files, sample, streams, ctx.device, ctx.table_log2, ctx)
         for ordinal, name in enumerate(names):
             reads, uniq = per_file[ordinal][:2]
