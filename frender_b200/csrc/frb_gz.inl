@@ -10,6 +10,12 @@ namespace {
 constexpr int FRB_GZ_RETRY_HOST = 1000;   // internal status: use the host (zlib) path for this file
 constexpr int FRB_GZ_RETRY_SPACE = 1001;  // internal status: a chunk's staging area was too small
 
+// FRB_GZ_VERBOSE: why the device path handed a file back
+int gz_decline(const char* why) {
+    if (getenv("FRB_GZ_VERBOSE")) fprintf(stderr, "gz: device inflate declined: %s\n", why);
+    return FRB_GZ_RETRY_HOST;
+}
+
 struct GzBuffers {
     unsigned char* comp[2] = {nullptr, nullptr};  // pieces of the compressed file (+ overlap, padded to words)
     unsigned char* host[2] = {nullptr, nullptr};  // pinned twins: a reader thread fills one while the other is in use
@@ -45,12 +51,13 @@ struct GzConfig {
     size_t stride = 32u << 10;   // compressed bytes per chunk (one warp)
     size_t expand = 12;          // staging symbols per compressed byte
     size_t carry = 4u << 20;     // room for an unfinished line in front of a piece's text
+    bool stride_fixed = false;   // FRB_GZ_STRIDE_KB given: no per-file choice
 };
 
 GzConfig gz_config() {
     GzConfig g;
     if (const char* e = getenv("FRB_GZ_PIECE_MB")) g.piece = static_cast<size_t>(atoi(e)) << 20;
-    if (const char* e = getenv("FRB_GZ_STRIDE_KB")) g.stride = static_cast<size_t>(atoi(e)) << 10;
+    if (const char* e = getenv("FRB_GZ_STRIDE_KB")) g.stride = static_cast<size_t>(atoi(e)) << 10, g.stride_fixed = true;
     if (const char* e = getenv("FRB_GZ_EXPAND")) g.expand = static_cast<size_t>(atoi(e));
     return g;
 }
@@ -70,7 +77,10 @@ void gz_free(GzBuffers& b) {
 }
 
 int gz_ensure(frb_ctx* c, GzBuffers& b, const GzConfig& g, size_t piece_bytes) {
-    const size_t comp_cap = piece_bytes + 3 * g.stride + 64;
+    // sizes in steps of 16 MiB, so that a run of files of similar size keeps one set of buffers (allocating and
+    // freeing pinned and device memory synchronises the device and costs more than a small file's inflate)
+    piece_bytes = (piece_bytes + (16u << 20) - 1) & ~static_cast<size_t>((16u << 20) - 1);
+    const size_t comp_cap = piece_bytes + 3 * std::max<size_t>(g.stride, 32u << 10) + 64;
     const size_t n_chunks = (piece_bytes + g.stride - 1) / g.stride + 1;
     const size_t stage_syms = std::max<size_t>((n_chunks - 1) * g.stride * g.expand, 32u << 20);  // >= 64 MB of symbols
     const size_t out_cap = g.carry + stage_syms + 64;
@@ -176,7 +186,7 @@ size_t gz_host_header(const unsigned char* d, size_t n) {
 // valid until the sink of the piece after next is called.  FRB_GZ_RETRY_HOST: nothing usable happened (the
 // sink may already have been called -- the caller starts the file over).
 template <typename Sink>
-int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const char* path, uint64_t* raw_bytes, Sink&& sink) {
+int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const char* path, uint64_t* raw_bytes, Sink&& sink) {
     FILE* fh = fopen(path, "rb");
     if (!fh) return fail(c, FRB_ERR_IO, "cannot open %s", path);
     struct Closer {
@@ -186,7 +196,13 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
     fseek(fh, 0, SEEK_END);
     const uint64_t file_bytes = static_cast<uint64_t>(ftell(fh));
     fseek(fh, 0, SEEK_SET);
-    if (file_bytes < 18) return FRB_GZ_RETRY_HOST;  // smaller than an empty member: let zlib say what it is
+    if (file_bytes < 18) return gz_decline("smaller than an empty member");  // smaller than an empty member: let zlib say what it is
+    // One warp decodes one chunk from end to end, so the decode of a piece takes as long as ONE chunk does: a small
+    // file is cut into smaller chunks (down to 8 KiB) until there are a few thousand of them.
+    GzConfig g = g_in;
+    const uint64_t overlap = 3 * std::max<uint64_t>(g_in.stride, 32u << 10);  // compressed bytes read behind a piece
+    if (!g.stride_fixed)
+        while (g.stride > (8u << 10) && file_bytes / g.stride < 2048) g.stride >>= 1;
     // Pieces begin at fixed file offsets k * piece (so that they can be read ahead); the last one takes up to a
     // piece and a half rather than leaving a small rest for a launch of its own.
     const size_t piece = std::min<uint64_t>(g.piece, (file_bytes + 3) & ~3ull);
@@ -203,7 +219,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
     unsigned char head[1024];
     const size_t got_head = fread(head, 1, sizeof head, fh);
     const size_t hdr = gz_host_header(head, got_head);
-    if (!hdr) return FRB_GZ_RETRY_HOST;
+    if (!hdr) return gz_decline("no gzip header");
 
     // ---- reader thread: piece k of the file into pinned buffer k & 1, then to the device on the copy stream ---
     std::mutex mu;
@@ -221,7 +237,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
                 if (quit) return;
             }
             const uint64_t off = plan[k].first;
-            const uint64_t end = std::min<uint64_t>(off + plan[k].second + 3 * g.stride, file_bytes);
+            const uint64_t end = std::min<uint64_t>(off + plan[k].second + overlap, file_bytes);
             const size_t n = static_cast<size_t>(end - off);
             unsigned char* const hb = b.host[k & 1];
             bool ok = fseek(fh, static_cast<long>(off), SEEK_SET) == 0 && fread(hb, 1, n, fh) == n;
@@ -267,7 +283,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         // ---- compressed bytes of the piece (+ overlap) -----------------------------------------------------
         const uint64_t file_pos = plan[piece_no].first;
         const bool last_piece = static_cast<size_t>(piece_no) + 1 == plan.size();
-        const size_t n_in = static_cast<size_t>(std::min<uint64_t>(file_pos + plan[piece_no].second + 3 * g.stride, file_bytes) - file_pos);
+        const size_t n_in = static_cast<size_t>(std::min<uint64_t>(file_pos + plan[piece_no].second + overlap, file_bytes) - file_pos);
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return filled > piece_no || !io_err.empty(); });
@@ -279,7 +295,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         const unsigned n_chunks = static_cast<unsigned>((body + g.stride - 1) / g.stride);
         const uint64_t rel_start = start_bit_abs - file_pos * 8;
         const unsigned first_chunk = static_cast<unsigned>((rel_start >> 3) / g.stride);  // chunk holding the start
-        if (first_chunk >= n_chunks) return FRB_GZ_RETRY_HOST;
+        if (first_chunk >= n_chunks) return gz_decline("first block start behind the piece");
         // ---- chunk table --------------------------------------------------------------------------------
         CU(c, cudaMemsetAsync(b.chunks, 0, (n_chunks + 1) * sizeof(gz::Chunk), c->compute));
         gz::Chunk first{};
@@ -295,7 +311,8 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
             tm.mark(0);
             if (search_to > search_from)
                 gz::gz_find_kernel<<<search_to - search_from, gz::kFindThreads, 0, c->compute>>>(
-                    comp, n_in, b.chunks, search_to, g.stride, 0, search_from, last_piece ? 0xFFFFFFFFu : n_chunks);
+                    comp, n_in, b.chunks, search_to, g.stride, 0, search_from, last_piece ? 0xFFFFFFFFu : n_chunks,
+                    overlap - 8192);
             tm.mark(1);
             // every chunk of this piece an equal share of the staging area
             gz::gz_link_kernel<<<1, 32, 0, c->compute>>>(b.chunks, n_chunks, b.stage_syms / n_chunks / 16 * 16,
@@ -325,7 +342,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         cv.notify_all();
         const unsigned* hflags = reinterpret_cast<const unsigned*>(b.scalars_host + 2);
         const uint64_t n_sym = b.scalars_host[0];
-        if (hflags[2]) return FRB_GZ_RETRY_HOST;  // no block start found behind the piece (nothing was decoded)
+        if (hflags[2]) return gz_decline("no block start found behind the piece");  // (nothing was decoded)
         if (hflags[0] != 0xFFFFFFFFu) {  // a chunk failed: which way?
             gz::Chunk bad;
             CU(c, cudaMemcpy(&bad, b.chunks + hflags[0], sizeof bad, cudaMemcpyDeviceToHost));
@@ -336,11 +353,11 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
             // corrupt or truncated data in the piece the stream really ends in is an error of the file, not of the
             // chunking (every earlier chunk met its successor exactly)
             if (bad.status == gz::GZ_ERR_TRUNC && last_piece) return fail(c, FRB_ERR_IO, "%s: unexpected end of file", path);
-            return bad.status == gz::GZ_ERR_SPACE ? FRB_GZ_RETRY_SPACE : FRB_GZ_RETRY_HOST;
+            return bad.status == gz::GZ_ERR_SPACE ? FRB_GZ_RETRY_SPACE : gz_decline("a chunk did not decode to its successor's start");
         }
         const unsigned n_tr = *reinterpret_cast<const unsigned*>(b.scalars_host + 4);
-        if (n_tr > b.trailer_cap) return FRB_GZ_RETRY_HOST;  // thousands of tiny members: zlib's job
-        if (carry_len + n_sym + 64 > b.out_cap) return FRB_GZ_RETRY_HOST;
+        if (n_tr > b.trailer_cap) return gz_decline("too many members in one piece");
+        if (carry_len + n_sym + 64 > b.out_cap) return gz_decline("text larger than the output buffer");
         // ---- symbols -> text behind the carried line ---------------------------------------------------------
         unsigned char* const text = b.out[ob] + carry_len;
         {
@@ -382,14 +399,14 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
             member_len = static_cast<uint64_t>(crc_res[2]) | (static_cast<uint64_t>(crc_res[3]) << 32);
             if (last_piece && member_len) return fail(c, FRB_ERR_IO, "%s: unexpected end of file", path);
         }
-        if (hflags[1]) return FRB_GZ_RETRY_HOST;  // '\r' in the text: universal newlines are the host path's job
+        if (hflags[1]) return gz_decline("'\\r' in the text (universal newlines are the host path's job)");
         total_out += n_sym;
         const uint64_t have = carry_len + n_sym;
         uint64_t usable = have;
         if (!last_piece) {
             const uint64_t nl = b.scalars_host[1];  // end of the last complete line inside the new text
             if (nl == 0) {
-                if (have > g.carry) return FRB_GZ_RETRY_HOST;  // a line longer than the carry area
+                if (have > g.carry) return gz_decline("a line longer than the carry area");
                 usable = 0;
             } else {
                 usable = carry_len + nl;
@@ -399,7 +416,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g, const ch
         if (last_piece) break;
         // ---- next piece ---------------------------------------------------------------------------------
         const size_t tail = static_cast<size_t>(have - usable);
-        if (tail > g.carry) return FRB_GZ_RETRY_HOST;
+        if (tail > g.carry) return gz_decline("unfinished line longer than the carry area");
         if (tail) CU(c, cudaMemcpyAsync(b.out[ob ^ 1], b.out[ob] + usable, tail, cudaMemcpyDeviceToDevice, c->compute));
         carry_len = tail;
         ob ^= 1;

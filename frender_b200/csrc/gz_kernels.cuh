@@ -303,7 +303,7 @@ __device__ inline bool block_body_ok(const unsigned char* __restrict__ d, unsign
 __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned char* __restrict__ d, unsigned long long nbytes,
                                                                Chunk* chunks, unsigned n_chunks, unsigned long long stride,
                                                                unsigned long long first_byte, unsigned first_chunk,
-                                                               unsigned tail_chunk) {
+                                                               unsigned tail_chunk, unsigned long long tail_reach) {
     const unsigned c = blockIdx.x + first_chunk;
     if (c >= n_chunks) return;
     __shared__ unsigned long long s_best;
@@ -311,10 +311,10 @@ __global__ void __launch_bounds__(kFindThreads) gz_find_kernel(const unsigned ch
     __syncthreads();
     const unsigned long long from = (first_byte + static_cast<unsigned long long>(c) * stride) * 8;
     // search one stride and a half: a start behind that belongs to the next chunk anyway
-    // (the chunk behind the piece, whose start closes the piece's last chunk, may look further: the piece buffer
-    // carries three strides of overlap)
+    // (the chunk behind the piece, whose start closes the piece's last chunk, looks through the overlap the piece
+    // buffer carries: tail_reach bytes)
     const bool tail = c == tail_chunk;
-    const unsigned long long reach = tail ? 3 * stride - 8192 : stride + stride / 2;
+    const unsigned long long reach = tail ? tail_reach : stride + stride / 2;
     const unsigned long long to = min((first_byte + static_cast<unsigned long long>(c) * stride + reach) * 8, nbytes * 8);
     // kFindWindow bit positions per round, in three passes: every position gets the 13-bit test; the survivors
     // (one in nine) are collected and shared out over ALL threads for the Kraft sum; what is left of them (a few

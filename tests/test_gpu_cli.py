@@ -62,9 +62,14 @@ def test_cli_scan_csv_bytes(golden, golden_dir, tmp_path, name):
         assert (tmp_path / calls).read_bytes() == unb64(case["rc_calls_csv"])
 
 
-@pytest.mark.parametrize("cores", ["1", "3"])
-def test_cli_scan_multi_file_prefix(golden, golden_dir, tmp_path, cores):
-    """Three files, `-p` prefix; `-c 3` scans them concurrently on three contexts of the same GPU."""
+@pytest.mark.parametrize("cores,mode", [("1", "device"), ("3", "device"), ("3", "streams"), ("3", "zlib")])
+def test_cli_scan_multi_file_prefix(golden, golden_dir, tmp_path, cores, mode, monkeypatch):
+    """Three files, `-p` prefix.  `-c 3`: one after the other with the inflate on the device (default), on three
+    contexts of the same GPU at the same time when asked for (FRENDER_MAX_STREAMS) or with host zlib."""
+    if mode == "streams":
+        monkeypatch.setenv("FRENDER_MAX_STREAMS", "3")
+    if mode == "zlib":
+        monkeypatch.setenv("FRB_GZ_DEVICE", "0")       # the policy follows it (the library reads it once per process)
     case = golden["scan"]["multi"]
     files = []
     for fname in case["files"]:
