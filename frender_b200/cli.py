@@ -386,17 +386,20 @@ def initial_table_log2(files):
     return log2
 
 
-def concurrent_streams(cores, n_files):
-    """Files scanned at the same time on one GPU for `-c N`.  With the inflate on the device one stream does what
-    twenty zlib threads do and a second context only adds its set-up and tear-down (half a second each), so the
-    files go one after the other; with host zlib (FRB_GZ_DEVICE=0) every stream is a zlib thread and N of them
-    are N times as fast.  FRENDER_MAX_STREAMS overrides."""
+def concurrent_streams(cores, files):
+    """Files scanned at the same time on one GPU for `-c N` (one context per stream).  FRENDER_MAX_STREAMS
+    overrides.  With host zlib (FRB_GZ_DEVICE=0) every stream is a zlib thread and N of them are N times as fast.
+    With the inflate on the device one stream does what twenty zlib threads do on a large file, and a second
+    context only adds its buffers (a few GB) -- but a SMALL file keeps the GPU busy for a tenth of the ~20 ms its
+    inflate takes (one warp decodes one chunk from end to end), so many small files go four at a time."""
+    n_files = len(files)
     env = os.environ.get("FRENDER_MAX_STREAMS")
     if env:
         return max(1, min(cores, n_files, int(env)))
     if os.environ.get("FRB_GZ_DEVICE", "1") == "0":
         return max(1, min(cores, n_files, 16))
-    return 1
+    small = max((os.path.getsize(str(f)) for f in files), default=0) < (64 << 20)
+    return max(1, min(cores, 4)) if small and n_files >= 8 else 1
 
 
 def tally_files(ctx, files, names, sample, cores, n_gpus):
@@ -409,8 +412,8 @@ def tally_files(ctx, files, names, sample, cores, n_gpus):
                   f"in {reads} reads.")
         tables = ScanTables(names, total, [per_file[i][2:] for i in range(len(names))])
         ctx.load_total_arrays(*total)
-    elif cores > 1 and len(files) > 1 and concurrent_streams(cores, len(files)) > 1:
-        streams = concurrent_streams(cores, len(files))
+    elif cores > 1 and len(files) > 1 and concurrent_streams(cores, files) > 1:
+        streams = concurrent_streams(cores, files)
         per_file, total = scan_files_concurrent(files, sample, streams, ctx.device, ctx.table_log2, ctx)
         for ordinal, name in enumerate(names):
             reads, uniq = per_file[ordinal][:2]
