@@ -386,20 +386,35 @@ def initial_table_log2(files):
     return log2
 
 
+SMALL_FILE = 32 << 20           # a .fastq.gz below this keeps the GPU a tenth busy on its own
+SMALL_RUN_BYTES = 96 << 20      # compressed bytes of one run (one piece of the device inflate)
+
+
+def small_file_run(files, start):
+    """How many files from files[start] on go through the device as one stream (1: the file on its own)."""
+    total, n = 0, 0
+    for path in files[start:start + 256]:
+        size = os.path.getsize(str(path))
+        if size >= SMALL_FILE or size < 18 or total + size > SMALL_RUN_BYTES:
+            break
+        total += size
+        n += 1
+    return max(n, 1)
+
+
 def concurrent_streams(cores, files):
     """Files scanned at the same time on one GPU for `-c N` (one context per stream).  FRENDER_MAX_STREAMS
     overrides.  With host zlib (FRB_GZ_DEVICE=0) every stream is a zlib thread and N of them are N times as fast.
-    With the inflate on the device one stream does what twenty zlib threads do on a large file, and a second
-    context only adds its buffers (a few GB) -- but a SMALL file keeps the GPU busy for a tenth of the ~20 ms its
-    inflate takes (one warp decodes one chunk from end to end), so many small files go four at a time."""
+    With the inflate on the device one stream does what twenty zlib threads do on a large file, a second context
+    only adds its buffers (a few GB), and runs of small files are inflated together as one stream
+    (small_file_run): the files go one after the other."""
     n_files = len(files)
     env = os.environ.get("FRENDER_MAX_STREAMS")
     if env:
         return max(1, min(cores, n_files, int(env)))
     if os.environ.get("FRB_GZ_DEVICE", "1") == "0":
         return max(1, min(cores, n_files, 16))
-    small = max((os.path.getsize(str(f)) for f in files), default=0) < (64 << 20)
-    return max(1, min(cores, 4)) if small and n_files >= 8 else 1
+    return 1
 
 
 def tally_files(ctx, files, names, sample, cores, n_gpus):
@@ -421,10 +436,17 @@ def tally_files(ctx, files, names, sample, cores, n_gpus):
                   f"in {reads} reads.")
         tables = ScanTables(names, total, [per_file[i][2:4] for i in range(len(names))])
     else:
-        for ordinal, path in enumerate(files):
-            print(f"Tallying barcodes from {names[ordinal]}...", end="")
-            reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
-            print(f"found {uniq} new barcode{'' if uniq == 1 else 's'} in {reads} reads.")
+        ordinal = 0
+        while ordinal < len(files):
+            # a run of small files goes through the device as ONE gzip stream of several members
+            run = small_file_run(files, ordinal) if not sample else 1
+            done = ctx.scan_gz_batch(files[ordinal:ordinal + run], ordinal) if run > 1 else None
+            if done is None:
+                done = [ctx.scan_gz(files[ordinal], ordinal, sample)[:2]]
+            for k, (reads, uniq, *_) in enumerate(done):
+                print(f"Tallying barcodes from {names[ordinal + k]}...found {uniq} new barcode{'' if uniq == 1 else 's'} "
+                      f"in {reads} reads.")
+            ordinal += len(done)
         tables = ScanTables.from_ctx(ctx, names)
     return tables
 

@@ -181,21 +181,56 @@ size_t gz_host_header(const unsigned char* d, size_t n) {
     return pos <= n ? pos : 0;
 }
 
+// One or more .gz files read as ONE stream: gzip files laid end to end are a gzip stream of several members whose
+// text is the files' texts laid end to end (RFC 1952), so a run of small files is inflated by one set of launches.
+struct GzSource {
+    std::vector<std::string> paths;
+    std::vector<uint64_t> start;  // start[i] = stream offset of file i, start[n] = total bytes
+    int open(frb_ctx* c) {
+        start.assign(1, 0);
+        for (const auto& p : paths) {
+            FILE* fh = fopen(p.c_str(), "rb");
+            if (!fh) return fail(c, FRB_ERR_IO, "cannot open %s", p.c_str());
+            fseek(fh, 0, SEEK_END);
+            start.push_back(start.back() + static_cast<uint64_t>(ftell(fh)));
+            fclose(fh);
+        }
+        return FRB_OK;
+    }
+    uint64_t size() const { return start.back(); }
+    bool read(uint64_t off, size_t n, unsigned char* dst) const {
+        for (size_t i = 0; i < paths.size() && n; ++i) {
+            if (off >= start[i + 1]) continue;
+            const uint64_t in_file = off - start[i];
+            const size_t take = static_cast<size_t>(std::min<uint64_t>(n, start[i + 1] - off));
+            FILE* fh = fopen(paths[i].c_str(), "rb");
+            if (!fh) return false;
+            const bool ok = fseek(fh, static_cast<long>(in_file), SEEK_SET) == 0 && fread(dst, 1, take, fh) == take;
+            fclose(fh);
+            if (!ok) return false;
+            off += take, dst += take, n -= take;
+        }
+        return n == 0;
+    }
+};
+
+// a member of the stream that ended in the piece just inflated: where its text ends and where its trailer ends
+// (both counted from the start of the stream)
+struct GzMemberEnd {
+    uint64_t text_end, comp_end;
+};
+
 // Inflate `path` on the device piece by piece; every piece of text (cut behind its last complete line, the rest
 // carried into the next piece; the last piece whole) goes to `sink(dev_ptr, nbytes, last)`, 16-byte aligned,
 // valid until the sink of the piece after next is called.  FRB_GZ_RETRY_HOST: nothing usable happened (the
 // sink may already have been called -- the caller starts the file over).
-template <typename Sink>
-int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const char* path, uint64_t* raw_bytes, Sink&& sink) {
-    FILE* fh = fopen(path, "rb");
-    if (!fh) return fail(c, FRB_ERR_IO, "cannot open %s", path);
-    struct Closer {
-        FILE* f;
-        ~Closer() { fclose(f); }
-    } closer{fh};
-    fseek(fh, 0, SEEK_END);
-    const uint64_t file_bytes = static_cast<uint64_t>(ftell(fh));
-    fseek(fh, 0, SEEK_SET);
+// on_members(vector<GzMemberEnd>) is called for every piece before its sink (a batch of files needs to know which
+// text belongs to which file); `path` names the stream in messages.
+template <typename Sink, typename Members>
+int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const GzSource& src, uint64_t* raw_bytes,
+                           Sink&& sink, Members&& on_members, bool want_members) {
+    const char* const path = src.paths[0].c_str();
+    const uint64_t file_bytes = src.size();
     if (file_bytes < 18) return gz_decline("smaller than an empty member");  // smaller than an empty member: let zlib say what it is
     // One warp decodes one chunk from end to end, so the decode of a piece takes as long as ONE chunk does: a small
     // file is cut into smaller chunks (down to 8 KiB) until there are a few thousand of them.
@@ -217,7 +252,8 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const
     for (const auto& p : plan) largest = std::max(largest, p.second);
     TRY(gz_ensure(c, b, g, static_cast<size_t>((largest + 3) & ~3ull)));
     unsigned char head[1024];
-    const size_t got_head = fread(head, 1, sizeof head, fh);
+    const size_t got_head = static_cast<size_t>(std::min<uint64_t>(sizeof head, file_bytes));
+    if (!src.read(0, got_head, head)) return fail(c, FRB_ERR_IO, "%s: read error", path);
     const size_t hdr = gz_host_header(head, got_head);
     if (!hdr) return gz_decline("no gzip header");
 
@@ -240,7 +276,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const
             const uint64_t end = std::min<uint64_t>(off + plan[k].second + overlap, file_bytes);
             const size_t n = static_cast<size_t>(end - off);
             unsigned char* const hb = b.host[k & 1];
-            bool ok = fseek(fh, static_cast<long>(off), SEEK_SET) == 0 && fread(hb, 1, n, fh) == n;
+            bool ok = src.read(off, n, hb);
             memset(hb + n, 0, 64);
             if (ok) {
                 ok = cudaMemcpyAsync(b.comp[k & 1], hb, n + 64, cudaMemcpyHostToDevice, c->copy) == cudaSuccess &&
@@ -400,6 +436,17 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const
             if (last_piece && member_len) return fail(c, FRB_ERR_IO, "%s: unexpected end of file", path);
         }
         if (hflags[1]) return gz_decline("'\\r' in the text (universal newlines are the host path's job)");
+        if (want_members && n_tr) {  // which text ends where a member (and so, maybe, a file of the batch) ends
+            std::vector<unsigned long long> ends(n_tr);
+            std::vector<unsigned> order(n_tr);
+            std::vector<gz::Trailer> tr(n_tr);
+            CU(c, cudaMemcpy(ends.data(), b.tr_end[1], n_tr * 8ull, cudaMemcpyDeviceToHost));
+            CU(c, cudaMemcpy(order.data(), b.tr_idx[1], n_tr * 4ull, cudaMemcpyDeviceToHost));
+            CU(c, cudaMemcpy(tr.data(), b.trailers, n_tr * sizeof(gz::Trailer), cudaMemcpyDeviceToHost));
+            std::vector<GzMemberEnd> members(n_tr);
+            for (unsigned i = 0; i < n_tr; ++i) members[i] = GzMemberEnd{total_out + ends[i], file_pos + tr[order[i]].comp_end};
+            TRY(on_members(members));
+        }
         total_out += n_sym;
         const uint64_t have = carry_len + n_sym;
         uint64_t usable = have;
@@ -429,18 +476,27 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const
 
 // A stream that expands more than the staging areas allow (long runs) is tried again with larger ones while the
 // memory for them is there; the sink must be able to start over (`restart()` is called before every new attempt).
-template <typename Sink, typename Restart>
-int gz_device_inflate(frb_ctx* c, GzBuffers& b, const char* path, uint64_t* raw_bytes, Sink&& sink, Restart&& restart) {
+template <typename Sink, typename Restart, typename Members>
+int gz_device_inflate_source(frb_ctx* c, GzBuffers& b, const GzSource& src, uint64_t* raw_bytes, Sink&& sink, Restart&& restart,
+                             Members&& on_members, bool want_members) {
     GzConfig g = gz_config();
     for (;;) {
-        const int rc = gz_device_inflate_once(c, b, g, path, raw_bytes, sink);
+        const int rc = gz_device_inflate_once(c, b, g, src, raw_bytes, sink, on_members, want_members);
         if (rc != FRB_GZ_RETRY_SPACE) return rc;
         g.expand *= 8;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (g.expand > 1100 || g.piece * g.expand * 3 > free_b + b.stage_syms * 2) return FRB_GZ_RETRY_HOST;
+        if (g.expand > 1100 || g.piece * g.expand * 3 > free_b + b.stage_syms * 2) return gz_decline("staging areas would not fit");
         TRY(restart());
     }
+}
+
+template <typename Sink, typename Restart>
+int gz_device_inflate(frb_ctx* c, GzBuffers& b, const char* path, uint64_t* raw_bytes, Sink&& sink, Restart&& restart) {
+    GzSource src;
+    src.paths.emplace_back(path);
+    TRY(src.open(c));
+    return gz_device_inflate_source(c, b, src, raw_bytes, sink, restart, [](const std::vector<GzMemberEnd>&) { return FRB_OK; }, false);
 }
 
 }  // namespace

@@ -80,6 +80,7 @@ struct frb_ctx {
     // results
     std::vector<KeyList> files;
     KeyList total;
+    unsigned long long* skip_slot = nullptr;  // device word: where the text begins in the buffer of a batch segment
     bool total_ready = false, in_file = false;
     size_t merged_upto = 0;        // file lists already folded into total_tab
     bool ext_merged = false;       // lists from other contexts were folded in (frb_total_merge)
@@ -431,7 +432,7 @@ int launch_scan(frb_ctx* c, const unsigned char* dev, uint64_t nbytes, uint64_t 
     }
     // the lean (speculative) instantiation serves the tally of whole files: scan rule, no per-read outputs, no -s
     static const bool probe = getenv("FRB_SCAN_TIMING") && strcmp(getenv("FRB_SCAN_TIMING"), "spec") == 0;
-    const bool lean = lean_ok && (!a.timing || probe) && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out &&
+    const bool lean = lean_ok && (!a.timing || probe) && !no_guess && rule == FRB_RULE_SCAN && !keys_out && !rec_off_out && !skip_ptr &&
                       c->cur_limit == ~0ULL && table != nullptr && table == c->file_tab && c->in_file;
     if (table == c->file_tab && c->in_file) {
         if (c->file_composite < 0) c->file_composite = lean ? 1 : 0;
@@ -621,6 +622,7 @@ void frb_destroy(frb_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& f : c->files) free_list(c, f);
     free_list(c, c->total);
+    cudaFree(c->skip_slot);
     cudaFree(c->file_tab), cudaFree(c->total_tab), cudaFree(c->st), cudaFreeHost(c->st_host), cudaFree(c->status), cudaFree(c->redo), cudaFree(c->tile_first), cudaFree(c->block_sums);
     for (auto* p : c->xchg) cudaFree(p);
     for (int i = 0; i < kHostStages; ++i) {
@@ -1174,6 +1176,110 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
         CU(c, cudaMemsetAsync(&c->st->err_code, 0, sizeof(int), c->compute));  // errors of the abandoned attempt
     }
     return scan_gz_host(c, path, file_ordinal, read_limit, n_reads, n_unique, raw_bytes);
+}
+
+// A run of SMALL .gz files in one go: laid end to end they are one gzip stream of several members, which the device
+// inflates with one set of launches (a small file alone leaves the GPU nine tenths idle: one warp decodes one chunk
+// from end to end); the text of every file is then tallied as that file (own table, own list, own ordinals),
+// exactly as frb_scan_gz would one by one.  *used_device = 0: declined, nothing has changed -- scan them one by one
+// (that also is how a damaged file gets its own error message).
+int frb_scan_gz_batch(frb_ctx* c, const char* const* paths, uint32_t n_files, uint32_t first_ordinal, uint64_t* n_reads,
+                      uint64_t* n_unique, uint64_t* raw_bytes, int* used_device) {
+    CU(c, cudaSetDevice(c->device));
+    *used_device = 0;
+    static const bool device_ok = !(getenv("FRB_GZ_DEVICE") && atoi(getenv("FRB_GZ_DEVICE")) == 0);
+    if (!device_ok || n_files == 0) return FRB_OK;
+    if (c->in_file) return fail(c, FRB_ERR_STATE, "frb_scan_gz_batch: previous file not ended");
+    GzSource src;
+    for (uint32_t i = 0; i < n_files; ++i) src.paths.emplace_back(paths[i]);
+    TRY(src.open(c));
+    for (uint32_t i = 0; i < n_files; ++i) {  // every file a gzip file of its own
+        unsigned char magic[3] = {0, 0, 0};
+        if (src.start[i + 1] - src.start[i] < 18 || !src.read(src.start[i], 3, magic) || magic[0] != 0x1f || magic[1] != 0x8b ||
+            magic[2] != 8)
+            return FRB_OK;
+    }
+    if (!c->gzbuf) c->gzbuf = new GzBuffersHolder();
+    if (!c->skip_slot) CU(c, cudaMalloc(&c->skip_slot, 8));
+    const size_t files_before = c->files.size();
+    std::vector<uint64_t> text_end(n_files, ~0ULL);  // where the text of file i ends in the stream's text
+    uint32_t closed = 0;      // files whose end is known
+    uint32_t cur = 0;         // file being tallied
+    bool open = false, first_chunk = true;
+    uint64_t scanned = 0;     // text handed to the sink so far
+    uint64_t file_text_start = 0;
+    auto rollback = [&]() {
+        c->in_file = false;
+        cudaStreamSynchronize(c->compute);
+        cudaMemsetAsync(&c->st->err_code, 0, sizeof(int), c->compute);
+        while (c->files.size() > files_before) {
+            free_list(c, c->files.back());
+            c->files.pop_back();
+        }
+        std::fill(text_end.begin(), text_end.end(), ~0ULL);
+        closed = cur = 0, open = false, first_chunk = true, scanned = 0, file_text_start = 0;
+    };
+    auto on_members = [&](const std::vector<GzMemberEnd>& members) {
+        for (const GzMemberEnd& m : members) {
+            if (closed >= n_files) return gz_decline("batch: a member behind the last file");
+            // the member belongs to the first file that is not closed; that file ends where its last member does
+            if (m.comp_end > src.start[closed + 1]) return gz_decline("batch: a file does not end with a member trailer");
+            if (m.comp_end == src.start[closed + 1]) text_end[closed++] = m.text_end;
+        }
+        return FRB_OK;
+    };
+    auto sink = [&](unsigned char* dev, uint64_t n, bool last) {
+        uint64_t pos = 0;
+        for (;;) {
+            if (cur >= n_files) {
+                if (pos < n) return gz_decline("batch: text behind the last file");
+                break;
+            }
+            if (!open) {
+                TRY(frb_scan_begin(c, first_ordinal + cur, 0));
+                open = true, first_chunk = true;
+            }
+            const bool ends_here = cur < closed && text_end[cur] <= scanned + n;
+            const uint64_t seg_end = ends_here ? text_end[cur] - scanned : n;
+            if (seg_end > pos) {  // text begins `skip` bytes into a 16-byte aligned buffer
+                const uint64_t base = pos & ~15ULL;
+                CU(c, cudaMemsetAsync(c->skip_slot, 0, 8, c->compute));
+                if (pos & 15) CU(c, cudaMemsetAsync(c->skip_slot, static_cast<int>(pos & 15), 1, c->compute));
+                TRY(launch_scan(c, dev + base, seg_end - base, first_chunk ? 0 : FRB_CARRY, FRB_RULE_SCAN, nullptr, nullptr,
+                                c->file_tab, 0, ~0ULL, c->skip_slot));
+                first_chunk = false;
+            }
+            pos = seg_end;
+            if (!ends_here) break;
+            TRY(frb_scan_end(c, &n_reads[cur], &n_unique[cur]));
+            if (raw_bytes) raw_bytes[cur] = text_end[cur] - file_text_start;
+            file_text_start = text_end[cur];
+            open = false;
+            ++cur;
+        }
+        scanned += n;
+        if (last && (cur < n_files || open)) return gz_decline("batch: the stream ended inside a file");
+        return FRB_OK;
+    };
+    uint64_t raw = 0;
+    const int rc = gz_device_inflate_source(c, c->gzbuf->b, src, &raw, sink,
+                                            [&]() {
+                                                rollback();
+                                                return FRB_OK;
+                                            },
+                                            on_members, true);
+    if (rc == FRB_OK) {
+        c->gz_device_files += n_files;
+        *used_device = 1;
+        return FRB_OK;
+    }
+    rollback();
+    // anything about the DATA (a damaged file, a header that does not parse, ...) is reported by the one-by-one path,
+    // which knows the file it belongs to
+    if (rc == FRB_GZ_RETRY_HOST || rc == FRB_ERR_IO || rc == FRB_ERR_BAD_HEADER || rc == FRB_ERR_BAD_ALPHABET ||
+        rc == FRB_ERR_KEY_TOO_LONG || rc == FRB_ERR_TABLE_FULL)
+        return FRB_OK;
+    return rc;
 }
 
 // Test / tooling entry: inflate a .gz on the device into host memory.  *used_device = 0 when the device path

@@ -60,6 +60,7 @@ struct Chunk {
 // A member trailer the decoder passed: the member ends `local_end` symbols into chunk `chunk`.
 struct Trailer {
     unsigned int chunk, local_end, crc, isize;
+    unsigned long long comp_end;   // byte behind the trailer in the piece buffer (which FILE of a batch ends here)
 };
 
 // x^(2^k) mod P for k < 32 (P = the CRC-32 polynomial, reflected; made by the host), kernel parameter
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) gz_decode_kernel(const unsi
                 const unsigned t = atomicAdd(trailer_n, 1u);
                 if (t < trailer_cap) {
                     const unsigned crc = d[b] | (d[b + 1] << 8) | (d[b + 2] << 16) | (static_cast<unsigned>(d[b + 3]) << 24);
-                    trailers[t] = Trailer{c, n, crc, isize};
+                    trailers[t] = Trailer{c, n, crc, isize, b + 8};
                 }
             }
             unsigned long long nb = b + 8;

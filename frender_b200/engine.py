@@ -137,6 +137,19 @@ class Context:
         self.file_names.append(os.path.basename(str(path)))
         return reads.value, uniq.value, raw.value
 
+    def scan_gz_batch(self, paths, first_ordinal):
+        """A run of small fastq.gz files in one go (frb_scan_gz_batch): [(reads, unique keys, decompressed bytes)]
+        per file, as scan_gz would give one by one -- or None when the library declined (scan them one by one)."""
+        n = len(paths)
+        names = (C.c_char_p * n)(*[os.fsencode(str(p)) for p in paths])
+        reads, uniq, raw = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        used = C.c_int()
+        self._ck(lib.frb_scan_gz_batch(self._h, names, n, first_ordinal, _ptr(reads), _ptr(uniq), _ptr(raw), C.byref(used)))
+        if not used.value:
+            return None
+        self.file_names.extend(os.path.basename(str(p)) for p in paths)
+        return list(zip(reads.tolist(), uniq.tolist(), raw.tolist()))
+
     def gz_inflate(self, path, cap):
         """A .gz file inflated on the device (tests, tools).  Returns the bytes, or None when the device path
         declined the stream (frb_scan_gz then inflates it with zlib on a host thread)."""

@@ -108,10 +108,18 @@ int frb_scan_chunk_host(frb_ctx* ctx, const void* host, uint64_t nbytes, uint64_
 int frb_scan_chunk_dev(frb_ctx* ctx, const void* dev, uint64_t nbytes, uint64_t line_base, int rule,
                        uint64_t* keys_out_dev, uint64_t* rec_off_out_dev);
 int frb_scan_end(frb_ctx* ctx, uint64_t* n_reads, uint64_t* n_unique);
-/* Whole .gz file through the library's own inflate pipeline (zlib worker thread, pinned
- * double buffers, H2D overlapped with the kernels): begin + chunks + end. Replaces F:159-177. */
+/* Whole .gz file: begin + chunks + end.  Replaces F:159-177.  The deflate stream is inflated ON THE DEVICE (compressed
+ * bytes over PCIe, CRC32 + ISIZE of every member verified there); read_limit != 0 (-s), FRB_GZ_DEVICE=0 and streams
+ * the device path declines go through zlib on a host thread (pinned double buffers, H2D overlapped with the kernels).
+ * A file that ends early, is not gzip or fails its CRC is FRB_ERR_IO on either path. */
 int frb_scan_gz(frb_ctx* ctx, const char* path, uint32_t file_ordinal, uint64_t read_limit,
                 uint64_t* n_reads, uint64_t* n_unique, uint64_t* raw_bytes);
+/* n_files SMALL .gz files (ordinals first_ordinal ...) in one go: laid end to end they are one multi-member gzip
+ * stream, inflated by one set of launches; every file is then tallied as itself, with the results frb_scan_gz would
+ * give one by one (n_reads / n_unique / raw_bytes: arrays of n_files).  *used_device = 0: declined, nothing changed --
+ * call frb_scan_gz per file (which also is how a damaged file gets an error message of its own). */
+int frb_scan_gz_batch(frb_ctx* ctx, const char* const* paths, uint32_t n_files, uint32_t first_ordinal,
+                      uint64_t* n_reads, uint64_t* n_unique, uint64_t* raw_bytes, int* used_device);
 /* A .gz file inflated on the device into host memory (tests, tools).  *used_device = 0: the device path declined
  * the stream (blocks larger than a chunk, '\r' in the text, ...) and nothing was written; frb_scan_gz falls back
  * to zlib on a host thread for such a file.                                                                */

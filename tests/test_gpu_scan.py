@@ -348,3 +348,51 @@ def test_demux_ok_on_the_device(ctx, golden, golden_dir):
         m3 = m.copy()
         m3[4 + unused[0], :] = 2
         assert ctx.demux_ok(m3, None)[2] is None
+
+
+def test_scan_gz_batch_equals_one_by_one(ctx, golden, golden_dir, tmp_path):
+    """A run of small files as ONE multi-member gzip stream (frb_scan_gz_batch): per-file tallies, the total and its
+    order are what the reference tallied file by file (configs[4] golden), whatever the files look like inside --
+    several members, stored blocks, no newline at the end, no reads at all."""
+    import gzip
+    import zlib
+    import frender_oracle as O
+    from frender_b200 import synth
+    case = golden["tally"]["c5"]
+    files = [os.path.join(golden_dir, f"c5__{f}") for f in case["files"]]
+    ctx.reset()
+    done = ctx.scan_gz_batch(files, 0)
+    assert done is not None, "the library declined the run"
+    got = {k.split("__", 1)[-1]: list(v.items()) for k, v in ctx.counter().items()}
+    assert list(got) == list(case["tally"])
+    assert {k: [list(x) for x in v] for k, v in got.items()} == case["tally"]
+    assert [r for r, _, _ in done] == [sum(n for _, n in case["tally"][f]) for f in case["files"]]
+    # odd files in one run, against the oracle file by file
+    spec = synth.make_spec("C1", n_samples=12)
+    texts = [synth.generate(spec, 0, 3000), synth.generate(spec, 3000, 3001)[:-1], b"", synth.generate(spec, 4000, 9000),
+             synth.generate(spec, 9000, 9500)]
+    blobs = [gzip.compress(texts[0], 6), gzip.compress(texts[1], 9), gzip.compress(b""),
+             gzip.compress(texts[3][:200_000], 1) + gzip.compress(texts[3][200_000:], 6)]
+    stored = zlib.compressobj(0, zlib.DEFLATED, 31)
+    blobs.append(stored.compress(texts[4]) + stored.flush())
+    paths = []
+    for i, blob in enumerate(blobs):
+        p = tmp_path / f"f{i}_R1_001.fastq.gz"
+        p.write_bytes(blob)
+        paths.append(p)
+    ctx.reset()
+    done = ctx.scan_gz_batch(paths, 0)
+    assert done is not None, "the library declined the run"
+    want = O.tally_barcodes(1, paths)
+    have = ctx.counter()
+    assert {k: list(v.items()) for k, v in have.items()} == {k: list(v.items()) for k, v in want.items()}
+    assert [raw for _, _, raw in done] == [len(t) for t in texts]
+    # a damaged file in the run: declined as a whole, nothing kept; one by one names the file
+    from frender_b200.engine import FrbError
+    bad = tmp_path / "bad_R1_001.fastq.gz"
+    bad.write_bytes(blobs[0][:-8] + bytes([blobs[0][-8] ^ 1]) + blobs[0][-7:])
+    ctx.reset()
+    assert ctx.scan_gz_batch([paths[0], bad, paths[4]], 0) is None
+    assert ctx.counter() == {"total": {}} or list(ctx.counter()) == ["total"]
+    with pytest.raises(FrbError, match="bad_R1_001"):
+        ctx.scan_gz(bad, 0)
