@@ -46,7 +46,7 @@ SIGNATURES = {
     "frb_scan_chunk_dev": (C.c_int, [vp, vp, u64, u64, C.c_int, vp, vp]),
     "frb_scan_end": (C.c_int, [vp, P(u64), P(u64)]),
     "frb_scan_gz": (C.c_int, [vp, C.c_char_p, u32, u64, P(u64), P(u64), P(u64)]),
-    "frb_scan_gz_batch": (C.c_int, [vp, vp, u32, u32, vp, vp, vp, P(C.c_int)]),
+    "frb_scan_gz_batch": (C.c_int, [vp, vp, vp, u32, vp, vp, vp, P(C.c_int)]),
     "frb_gz_inflate": (C.c_int, [vp, C.c_char_p, vp, u64, P(u64), P(C.c_int)]),
     "frb_file_count": (C.c_int, [vp, P(u32)]),
     "frb_file_size": (C.c_int, [vp, u32, P(u64), P(u64)]),

@@ -175,10 +175,17 @@ def _scan_worker(rank, n_ranks, device, ident, jobs, sample, table_log2, conn):
         ctx.nccl_init(ident, rank, n_ranks)
         ctx.reset()
         out = []
-        for k, (ordinal, path) in enumerate(jobs):
-            reads, uniq, _ = ctx.scan_gz(path, ordinal, sample)
-            fk, fc, _ = ctx.file_arrays(k)
-            out.append((ordinal, reads, uniq, fk, fc))
+        k = 0
+        while k < len(jobs):                    # runs of small files as one stream, like the one-GPU path
+            paths = [path for _, path in jobs]
+            run = small_file_run(paths, k) if not sample else 1
+            done = ctx.scan_gz_batch(paths[k:k + run], [o for o, _ in jobs[k:k + run]]) if run > 1 else None
+            if done is None:
+                done = [ctx.scan_gz(jobs[k][1], jobs[k][0], sample)[:2]]
+            for j, (reads, uniq, *_) in enumerate(done):
+                fk, fc, _ = ctx.file_arrays(k + j)
+                out.append((jobs[k + j][0], reads, uniq, fk, fc))
+            k += len(done)
         conn.send(("scanned", None, None))
         if not conn.recv():                     # another rank failed: no collective
             return

@@ -1183,7 +1183,7 @@ int frb_scan_gz(frb_ctx* c, const char* path, uint32_t file_ordinal, uint64_t re
 // from end to end); the text of every file is then tallied as that file (own table, own list, own ordinals),
 // exactly as frb_scan_gz would one by one.  *used_device = 0: declined, nothing has changed -- scan them one by one
 // (that also is how a damaged file gets its own error message).
-int frb_scan_gz_batch(frb_ctx* c, const char* const* paths, uint32_t n_files, uint32_t first_ordinal, uint64_t* n_reads,
+int frb_scan_gz_batch(frb_ctx* c, const char* const* paths, const uint32_t* ordinals, uint32_t n_files, uint64_t* n_reads,
                       uint64_t* n_unique, uint64_t* raw_bytes, int* used_device) {
     CU(c, cudaSetDevice(c->device));
     *used_device = 0;
@@ -1236,7 +1236,7 @@ int frb_scan_gz_batch(frb_ctx* c, const char* const* paths, uint32_t n_files, ui
                 break;
             }
             if (!open) {
-                TRY(frb_scan_begin(c, first_ordinal + cur, 0));
+                TRY(frb_scan_begin(c, ordinals[cur], 0));
                 open = true, first_chunk = true;
             }
             const bool ends_here = cur < closed && text_end[cur] <= scanned + n;

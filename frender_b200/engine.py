@@ -137,14 +137,18 @@ class Context:
         self.file_names.append(os.path.basename(str(path)))
         return reads.value, uniq.value, raw.value
 
-    def scan_gz_batch(self, paths, first_ordinal):
+    def scan_gz_batch(self, paths, ordinals):
         """A run of small fastq.gz files in one go (frb_scan_gz_batch): [(reads, unique keys, decompressed bytes)]
-        per file, as scan_gz would give one by one -- or None when the library declined (scan them one by one)."""
+        per file, as scan_gz would give one by one -- or None when the library declined (scan them one by one).
+        ordinals: the files' ordinals, or the first of consecutive ones."""
         n = len(paths)
+        if isinstance(ordinals, int):
+            ordinals = range(ordinals, ordinals + n)
+        ords = np.array(list(ordinals), np.uint32)
         names = (C.c_char_p * n)(*[os.fsencode(str(p)) for p in paths])
         reads, uniq, raw = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
         used = C.c_int()
-        self._ck(lib.frb_scan_gz_batch(self._h, names, n, first_ordinal, _ptr(reads), _ptr(uniq), _ptr(raw), C.byref(used)))
+        self._ck(lib.frb_scan_gz_batch(self._h, names, _ptr(ords), n, _ptr(reads), _ptr(uniq), _ptr(raw), C.byref(used)))
         if not used.value:
             return None
         self.file_names.extend(os.path.basename(str(p)) for p in paths)

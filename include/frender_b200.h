@@ -114,11 +114,11 @@ int frb_scan_end(frb_ctx* ctx, uint64_t* n_reads, uint64_t* n_unique);
  * A file that ends early, is not gzip or fails its CRC is FRB_ERR_IO on either path. */
 int frb_scan_gz(frb_ctx* ctx, const char* path, uint32_t file_ordinal, uint64_t read_limit,
                 uint64_t* n_reads, uint64_t* n_unique, uint64_t* raw_bytes);
-/* n_files SMALL .gz files (ordinals first_ordinal ...) in one go: laid end to end they are one multi-member gzip
+/* n_files SMALL .gz files (file ordinals ordinals[i]) in one go: laid end to end they are one multi-member gzip
  * stream, inflated by one set of launches; every file is then tallied as itself, with the results frb_scan_gz would
  * give one by one (n_reads / n_unique / raw_bytes: arrays of n_files).  *used_device = 0: declined, nothing changed --
  * call frb_scan_gz per file (which also is how a damaged file gets an error message of its own). */
-int frb_scan_gz_batch(frb_ctx* ctx, const char* const* paths, uint32_t n_files, uint32_t first_ordinal,
+int frb_scan_gz_batch(frb_ctx* ctx, const char* const* paths, const uint32_t* ordinals, uint32_t n_files,
                       uint64_t* n_reads, uint64_t* n_unique, uint64_t* raw_bytes, int* used_device);
 /* A .gz file inflated on the device into host memory (tests, tools).  *used_device = 0: the device path declined
  * the stream (blocks larger than a chunk, '\r' in the text, ...) and nothing was written; frb_scan_gz falls back
