@@ -48,7 +48,9 @@ struct GzBuffers {
 
 struct GzConfig {
     size_t piece = 128u << 20;   // compressed bytes per piece
-    size_t stride = 32u << 10;   // compressed bytes per chunk (one warp)
+    size_t stride = 48u << 10;   // compressed bytes per chunk (one warp): the finder's time goes with the number of chunks,
+                                 // the decode kernel's does not until there are fewer chunks than warp slots (measured: 16 KiB
+                                 // 10.6, 32 KiB 13.4, 48 KiB 14.9, 64 KiB 13.3, 96 KiB 12.0 GB/s inflated)
     size_t expand = 12;          // staging symbols per compressed byte
     size_t carry = 4u << 20;     // room for an unfinished line in front of a piece's text
     bool stride_fixed = false;   // FRB_GZ_STRIDE_KB given: no per-file choice
@@ -237,7 +239,7 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const
     GzConfig g = g_in;
     const uint64_t overlap = 3 * std::max<uint64_t>(g_in.stride, 32u << 10);  // compressed bytes read behind a piece
     if (!g.stride_fixed)
-        while (g.stride > (8u << 10) && file_bytes / g.stride < 2048) g.stride >>= 1;
+        while (g.stride / 2 >= (8u << 10) && file_bytes / g.stride < 2048) g.stride >>= 1;
     // Pieces begin at fixed file offsets k * piece (so that they can be read ahead); the last one takes up to a
     // piece and a half rather than leaving a small rest for a launch of its own.
     const size_t piece = std::min<uint64_t>(g.piece, (file_bytes + 3) & ~3ull);
