@@ -29,7 +29,56 @@ def load():
                                        C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.oracle_revcomp_sheet.restype = None
     lib.oracle_revcomp_sheet.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+    lib.oracle_route.restype = C.c_int
+    lib.oracle_route.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_void_p,
+                                 C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.oracle_fnv1a_segments.restype = None
+    lib.oracle_fnv1a_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     return lib
+
+
+FNV_BASIS = 14695981039346656037
+
+
+def route_sums(r1, n1, r2, n2, keys, sinks, n_sinks):
+    """The demux loop (F:774-810) over R1/R2 at host addresses r1 / r2 (ints, or bytes objects): per sink the byte
+    counts, record count and order-sensitive FNV-1a digests of both mates, as a structured numpy array with the
+    fields bytes1, bytes2, hash1, hash2, records.  keys: list of str, sinks: sink id per key.  SystemExit like the
+    reference for a key that is not in the table."""
+    import numpy as np
+    lib = load()
+    blob = "".join(keys).encode()
+    off = np.zeros(len(keys) + 1, np.uint32)
+    np.cumsum([len(k) for k in keys], out=off[1:])
+    sk = np.ascontiguousarray(sinks, np.uint32)
+    out = np.zeros(n_sinks, np.dtype([("bytes1", "u8"), ("bytes2", "u8"), ("hash1", "u8"), ("hash2", "u8"), ("records", "u8")]))
+    keep = []
+
+    def addr(x, n):
+        if isinstance(x, int):
+            return C.c_void_p(x), n
+        buf = np.frombuffer(x, np.uint8)
+        keep.append(buf)
+        return C.c_void_p(buf.ctypes.data), buf.size
+
+    a1, n1 = addr(r1, n1)
+    a2, n2 = addr(r2, n2)
+    bad = C.c_uint64()
+    rc = lib.oracle_route(a1, n1, a2, n2, blob, off.ctypes.data_as(C.c_void_p), sk.ctypes.data_as(C.c_void_p), len(keys),
+                          n_sinks, out.ctypes.data_as(C.c_void_p), C.byref(bad))
+    if rc == -1:
+        raise SystemExit(f"Couldn't find barcode of record {bad.value} in supplied frender result file!")
+    assert rc == 0
+    return out
+
+
+def fnv1a_segments(hashes, base_addr, off):
+    """hashes[s] continued over the bytes base[off[s]:off[s + 1]] for every sink (hashes: uint64 array, updated)."""
+    import numpy as np
+    lib = load()
+    off = np.ascontiguousarray(off, np.uint64)
+    lib.oracle_fnv1a_segments(hashes.ctypes.data_as(C.c_void_p), C.c_void_p(base_addr), off.ctypes.data_as(C.c_void_p),
+                              len(off) - 1)
 
 
 def tally(data, rule=0, sample=0):

@@ -202,3 +202,91 @@ int oracle_classify_rc(const char* key, const char* idx1, const char* idx2, cons
 void oracle_revcomp_sheet(const char* idx2, int rows, int l2, char* out) {
     for (int r = 0; r < rows; ++r) revcomp(idx2 + (size_t)r * l2, l2, out + (size_t)r * l2);
 }
+
+/* ---- demux loop (F:774-810) at scale: per-sink digests ------------------------------------------------------
+ * Walks R1 and R2 as the reference does -- groups of four lines (F:719-723: a trailing partial group still is a
+ * record), zipped, so the shorter file ends the loop (F:777) -- takes the key from the R2 header (text behind its
+ * last ':' up to the line end, F:778), looks the key up (keys are given as strings, sink ids beside them) and
+ * "writes" the eight lines to the sink: here that is a byte count and an order-sensitive FNV-1a digest per sink and
+ * mate, which a run of the router at ANY chunking must reproduce exactly.  Returns 0, or -1 with *bad_record = the
+ * first record whose key is not in the table (F:807-810). */
+typedef struct {
+    uint64_t bytes1, bytes2, hash1, hash2, records;
+} route_sum_t;
+
+static uint64_t fnv_more(uint64_t h, const unsigned char* p, size_t n) {
+    for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 1099511628211ULL;
+    return h;
+}
+
+/* one FNV-1a step per sink: hashes[s] over base[off[s], off[s + 1]) */
+void oracle_fnv1a_segments(uint64_t* hashes, const unsigned char* base, const uint64_t* off, uint32_t n_sinks) {
+    for (uint32_t s = 0; s < n_sinks; s++) hashes[s] = fnv_more(hashes[s], base + off[s], (size_t)(off[s + 1] - off[s]));
+}
+
+static size_t record_end(const unsigned char* d, size_t n, size_t pos) { /* behind four lines, or n */
+    for (int k = 0; k < 4 && pos < n; k++) {
+        const unsigned char* nl = memchr(d + pos, '\n', n - pos);
+        pos = nl ? (size_t)(nl - d) + 1 : n;
+    }
+    return pos;
+}
+
+int oracle_route(const unsigned char* r1, uint64_t n1, const unsigned char* r2, uint64_t n2, const char* keys,
+                 const uint32_t* key_off, const uint32_t* sinks, uint64_t n_keys, uint32_t n_sinks, route_sum_t* out,
+                 uint64_t* bad_record) {
+    uint64_t cap = 16;
+    while (cap < 2 * n_keys + 2) cap <<= 1;
+    int64_t* slot = malloc(cap * sizeof(int64_t));
+    if (!slot) return -3;
+    for (uint64_t i = 0; i < cap; i++) slot[i] = -1;
+    for (uint64_t i = 0; i < n_keys; i++) { /* a repeated key keeps its last row, as a dict does (F:660) */
+        const char* k = keys + key_off[i];
+        const size_t len = key_off[i + 1] - key_off[i];
+        uint64_t h = fnv(k, len) & (cap - 1);
+        while (slot[h] >= 0) {
+            const uint64_t j = (uint64_t)slot[h];
+            if (key_off[j + 1] - key_off[j] == len && memcmp(keys + key_off[j], k, len) == 0) break;
+            h = (h + 1) & (cap - 1);
+        }
+        slot[h] = (int64_t)i;
+    }
+    for (uint32_t s = 0; s < n_sinks; s++) {
+        out[s].bytes1 = out[s].bytes2 = out[s].records = 0;
+        out[s].hash1 = out[s].hash2 = 14695981039346656037ULL;
+    }
+    size_t p1 = 0, p2 = 0;
+    uint64_t rec = 0;
+    int rc = 0;
+    while (p1 < n1 && p2 < n2) {
+        const size_t e1 = record_end(r1, n1, p1), e2 = record_end(r2, n2, p2);
+        const unsigned char* nl = memchr(r2 + p2, '\n', e2 - p2);
+        size_t hend = nl ? (size_t)(nl - r2) : e2; /* header line without its '\n' */
+        size_t ks = hend;
+        while (ks > p2 && r2[ks - 1] != ':') ks--;
+        const size_t len = hend - ks;
+        uint64_t h = fnv((const char*)r2 + ks, len) & (cap - 1);
+        int64_t hit = -1;
+        while (slot[h] >= 0) {
+            const uint64_t j = (uint64_t)slot[h];
+            if (key_off[j + 1] - key_off[j] == len && memcmp(keys + key_off[j], r2 + ks, len) == 0) {
+                hit = (int64_t)j;
+                break;
+            }
+            h = (h + 1) & (cap - 1);
+        }
+        if (hit < 0) {
+            *bad_record = rec;
+            rc = -1;
+            break;
+        }
+        route_sum_t* s = &out[sinks[hit]];
+        s->bytes1 += e1 - p1, s->bytes2 += e2 - p2, s->records++;
+        s->hash1 = fnv_more(s->hash1, r1 + p1, e1 - p1);
+        s->hash2 = fnv_more(s->hash2, r2 + p2, e2 - p2);
+        p1 = e1, p2 = e2;
+        rec++;
+    }
+    free(slot);
+    return rc;
+}

@@ -1,6 +1,7 @@
 """The C oracle against the Python oracle / the reference's golden outputs (CPU)."""
 import gzip
 import os
+import sys
 
 import pytest
 
@@ -70,3 +71,39 @@ def test_c_rc_first_pass_golden(golden, name):
         assert {f: want[f] for f in got} == got, key
     calls = c_oracle.rc_calls(keys, counts, res, idx)
     assert calls == {k: (v["call"], v["reads_f"], v["reads_rc"]) for k, v in case["rc_calls"]}
+
+
+def test_c_route_digests_equal_the_python_oracle():
+    """oracle_route (the demux loop F:774-810 in C, per-sink byte counts and order-sensitive digests) against
+    route_pairs, which the reference's golden demux outputs pin: a short mate, a partial tail, an unknown key."""
+    import random
+
+    import numpy as np
+    import c_oracle
+    import frender_oracle as O
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_route import make_pair
+    role_of = {"index_hop": "#hop", "ambiguous": "#amb", "undetermined": "#und"}
+    for seed, kwargs in ((1, {}), (2, {"crop_tail": 9}), (3, {"r2_records": 1700})):
+        t1, t2, table = make_pair(random.Random(seed), 2500, **kwargs)
+        roles = O.sink_names(table)
+        names = sorted({n for n in roles.values() if n})
+        sid = {n: i for i, n in enumerate(names)}
+        keys = list(table)
+        routes = [sid[roles[table[k][1]] if table[k][0] == "demuxable" else roles[role_of[table[k][0]]]] for k in keys]
+        want = O.route_pairs(t1.splitlines(keepends=True), t2.splitlines(keepends=True), table, roles)
+        got = c_oracle.route_sums(t1.encode(), 0, t2.encode(), 0, keys, routes, len(names))
+        for name, i in sid.items():
+            for mate, stream in enumerate(want[name]):
+                h = np.full(1, c_oracle.FNV_BASIS, np.uint64)
+                if stream:
+                    c_oracle.fnv1a_segments(h, np.frombuffer(stream, np.uint8).ctypes.data, [0, len(stream)])
+                assert got[i][f"bytes{mate + 1}"] == len(stream) and got[i][f"hash{mate + 1}"] == h[0], (seed, name, mate)
+        assert int(got["records"].sum()) == sum(v[1].count(b"\n@M0:") + (1 if v[1] else 0) for v in want.values())
+    t1, t2, table = make_pair(random.Random(7), 100)
+    headers = t2.splitlines()[::4]
+    lost = headers[40].rsplit(":", 1)[1]
+    first = next(i for i, hd in enumerate(headers) if hd.rsplit(":", 1)[1] == lost)
+    keys = [k for k in table if k != lost]
+    with pytest.raises(SystemExit, match=f"record {first} "):
+        c_oracle.route_sums(t1.encode(), 0, t2.encode(), 0, keys, [0] * len(keys), 1)

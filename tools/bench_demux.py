@@ -19,7 +19,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def measure(device=0, pairs=4_000_000, chunk_mb=64, steps=3, warmup=1, ctx=None):
+def measure(device=0, pairs=4_000_000, chunk_mb=64, steps=3, warmup=1, ctx=None, oracle_check=True):
     from frender_b200 import _lib as L
     from frender_b200 import synth
     from frender_b200.engine import C, Context
@@ -72,8 +72,16 @@ def measure(device=0, pairs=4_000_000, chunk_mb=64, steps=3, warmup=1, ctx=None)
     (h1, n1), (h2, n2) = mates
     n_chunks = max((n1 + chunk - 1) // chunk, (n2 + chunk - 1) // chunk)
 
+    digest = None
+    if oracle_check:   # the checker (oracle/, test infrastructure): the reference's loop restated in C, per-sink digests
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+        import c_oracle
+        from frender_b200.engine import unpack_keys
+        digest = [np.full(n_sinks, c_oracle.FNV_BASIS, np.uint64), np.full(n_sinks, c_oracle.FNV_BASIS, np.uint64)]
+
     def stream(check):
-        """One pass of both mates through the router; check: count the records of every sink on the way."""
+        """One pass of both mates through the router; check: count the records of every sink on the way (and, with
+        the oracle, continue every sink's order-sensitive digest over the bytes it receives)."""
         ck(lib.frb_route_reset(h))
         total, in_flight = 0, 0
         per_sink = np.zeros(n_sinks, np.int64)
@@ -90,6 +98,9 @@ def measure(device=0, pairs=4_000_000, chunk_mb=64, steps=3, warmup=1, ctx=None)
                 out = np.ctypeslib.as_array((C.c_uint8 * int(off1[-1])).from_address(o1.value))
                 nl = np.flatnonzero(out == 10)
                 per_sink[:] += np.diff(np.searchsorted(nl, off1.astype(np.int64))) // 4
+            if check and digest is not None:
+                c_oracle.fnv1a_segments(digest[0], o1.value, off1)
+                c_oracle.fnv1a_segments(digest[1], o2.value, off2)
 
         for k in range(n_chunks):
             a0, b0 = min(k * chunk, n1), min(k * chunk, n2)
@@ -109,6 +120,13 @@ def measure(device=0, pairs=4_000_000, chunk_mb=64, steps=3, warmup=1, ctx=None)
     assert total == pairs, (total, pairs)
     assert bytes1 == n1 and bytes2 == n2, "sink bytes do not add up to the input"
     assert (per_sink == want_per_sink).all(), "per-sink record counts differ from the classification"
+    checked = "every pair routed once; per-sink record counts == classification's read counts; sink bytes == input bytes"
+    if digest is not None:
+        want = c_oracle.route_sums(h1.value, n1, h2.value, n2, unpack_keys(keys), sink.astype(np.uint32), n_sinks)
+        assert (want["records"].astype(np.int64) == per_sink).all(), "per-sink records differ from the C oracle's demux loop"
+        assert (want["hash1"] == digest[0]).all() and (want["hash2"] == digest[1]).all(), \
+            "a sink's byte stream differs from the C oracle's demux loop"
+        checked += "; every sink's R1 and R2 byte stream (order-sensitive FNV-1a digest) == the C oracle's restatement of F:774-810"
     for _ in range(warmup):
         stream(False)
     ctx.prof(True)
@@ -135,7 +153,7 @@ def measure(device=0, pairs=4_000_000, chunk_mb=64, steps=3, warmup=1, ctx=None)
            "parser_ms": scan_ms / steps, "router_ms": route_ms / steps,
            "algorithmic_bytes": int(moved), "kernel_gbs": moved / (kernel_ms / 1e3) / 1e9,
            "gpu_launches_per_pass": launches,
-           "checked": "every pair routed once; per-sink record counts == classification's read counts; sink bytes == input bytes"}
+           "checked": checked}
     if own:
         ctx.close()
     return out
