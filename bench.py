@@ -20,6 +20,10 @@ __graft_entry__.build(); the oracle port when it is absent) with all host cores 
 lane: the first reads of the stream the e2e leg uses.
 After the timed loop the result is CHECKED: counts sum to the reads, shares of the ranks are disjoint, and the
 first 3 M reads of the lane -- tally, both matcher passes, orientation calls -- equal the C oracle's.
+`--scaling strong` (N > 1) deals the record chunks of ONE lane to the ranks instead of one lane each.
+At N = 1 the line also carries a `demux` object: BASELINE configs[3] through the record router as a stream
+(tools/bench_demux.py: 4 M pairs, 64 MB chunks cut anywhere, two in flight, every sink's byte stream compared with
+the C oracle's demux loop); `--workload demux` makes that the line, with the reference's frender_demux beside it.
 """
 import argparse
 import json
