@@ -380,6 +380,21 @@ int gz_device_inflate_once(frb_ctx* c, GzBuffers& b, const GzConfig& g_in, const
         cv.notify_all();
         const unsigned* hflags = reinterpret_cast<const unsigned*>(b.scalars_host + 2);
         const uint64_t n_sym = b.scalars_host[0];
+        if (getenv("FRB_GZ_VERBOSE")) {  // how long the chunks really are: the longest one is the decode kernel's time
+            std::vector<gz::Chunk> all(n_chunks);
+            cudaMemcpy(all.data(), b.chunks, n_chunks * sizeof(gz::Chunk), cudaMemcpyDeviceToHost);
+            unsigned found = 0, longest_at = 0;
+            uint64_t longest = 0, longest_out = 0;
+            for (unsigned k = 0; k < n_chunks; ++k) {
+                if (!all[k].found) continue;
+                ++found;
+                const uint64_t len = (all[k].end_bit - all[k].start_bit) / 8;
+                if (len > longest) longest = len, longest_at = k, longest_out = all[k].n_out;
+            }
+            fprintf(stderr, "gz: piece %d: %u of %u chunks have a block start; longest chunk %llu compressed bytes -> %llu "
+                            "symbols (chunk %u), stride %zu\n", piece_no, found, n_chunks, (unsigned long long)longest,
+                    (unsigned long long)longest_out, longest_at, g.stride);
+        }
         if (hflags[2]) return gz_decline("no block start found behind the piece");  // (nothing was decoded)
         if (hflags[0] != 0xFFFFFFFFu) {  // a chunk failed: which way?
             gz::Chunk bad;
