@@ -84,3 +84,19 @@ def test_initial_table_size_follows_the_input(tmp_path, monkeypatch):
     assert 16 <= lo < hi <= 32
     monkeypatch.setenv("FRENDER_TABLE_LOG2", "19")
     assert cli.initial_table_log2([big]) == 19
+
+
+def test_text_chunks_random_newline_mixes(tmp_path):
+    """Random mixes of "\\r", "\\n", "\\r\\n" and text, random read sizes: always the bytes of text mode."""
+    import random
+    from frender_b200.cli import TextChunks
+    rng = random.Random(20)
+    for case in range(40):
+        raw = b"".join(rng.choice([b"\r", b"\n", b"\r\n", b"A", b"@x:1", b"+", b"FF"]) for _ in range(rng.randint(0, 200)))
+        p = tmp_path / f"m{case}.gz"
+        p.write_bytes(gzip.compress(raw))
+        want = gzip.open(p, "rt").read().encode()
+        t, got = TextChunks(p), b""
+        while not t.eof:
+            got += t.read(rng.randint(1, 17))
+        assert got == want, (case, raw)
